@@ -1,0 +1,179 @@
+/*
+ * sopro_b200 — C-ABI of the B200-native Sopro hot path.
+ *
+ * The reference (samuel-vitorino/sopro) is pure Python/PyTorch and has no FFI;
+ * every entry point below names the reference interface it replaces
+ * (paths relative to the reference's src/sopro/).  Plain pointers and sizes
+ * only, no torch types.  Unless a parameter says "host", pointers are CUDA
+ * device pointers owned by the caller; `stream` is a cudaStream_t passed as
+ * void* (NULL = legacy default stream).  Every function returns 0 on success
+ * or a negative sopro_status; sopro_last_error() gives the message for the
+ * calling thread.  There is no CPU fallback: creating an engine on a device
+ * that is not sm_100 fails.
+ */
+#ifndef SOPRO_B200_H_
+#define SOPRO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOPRO_MAX_AR_LAYERS 16
+
+enum sopro_status {
+  SOPRO_OK = 0,
+  SOPRO_ERR_INVALID = -1,     /* bad argument / unsupported geometry */
+  SOPRO_ERR_CUDA = -2,        /* a CUDA runtime call failed */
+  SOPRO_ERR_UNSUPPORTED = -3, /* device is not sm_100, or feature not built */
+  SOPRO_ERR_STATE = -4        /* call out of order */
+};
+
+enum sopro_wdtype { SOPRO_W_F32 = 0, SOPRO_W_BF16 = 1 };
+
+/* Geometry of the AR generator.  Replaces the fields of SoproTTSConfig the AR
+ * path reads (config.py:14-27) + the literals in nn/generator.py:12-42. */
+typedef struct sopro_ar_config {
+  int32_t d_model;                          /* cfg.d_model (384) */
+  int32_t n_layers;                         /* cfg.n_layers_ar (6) */
+  int32_t kernel;                           /* cfg.ar_kernel (13) */
+  int32_t n_heads;                          /* 4, nn/generator.py:36 */
+  int32_t vocab;                            /* codebook_size + 1 (2049), model.py:83 */
+  int32_t eos_id;                           /* codebook_size, model.py:59 */
+  int32_t dilation[SOPRO_MAX_AR_LAYERS];    /* nn/generator.py:16-20 */
+  int32_t has_attn[SOPRO_MAX_AR_LAYERS];    /* 1 if a TextXAttnBlock follows block i */
+  int32_t weight_dtype;                     /* sopro_wdtype: storage of the matrices */
+} sopro_ar_config_t;
+
+/* HOST pointers to fp32 tensors in the reference's state_dict layout. */
+typedef struct sopro_ar_layer_weights {
+  const float* norm_w;    /* ar.blocks.i.norm.weight      [D]        nn/blocks.py:123 */
+  const float* glu_w;     /* ar.blocks.i.glu.pro.weight   [2D, D]    nn/blocks.py:19 */
+  const float* glu_b;     /* ar.blocks.i.glu.pro.bias     [2D] */
+  const float* dw_w;      /* ar.blocks.i.dw.dw.weight     [D, 1, k]  nn/blocks.py:48 */
+  const float* dw_b;      /* ar.blocks.i.dw.dw.bias       [D] */
+  const float* ffn_norm_w;/* ar.blocks.i.ff.0.weight      [D]        nn/blocks.py:129 */
+  const float* ffn_w1;    /* ar.blocks.i.ff.1.weight      [4D, D] */
+  const float* ffn_b1;    /* ar.blocks.i.ff.1.bias        [4D] */
+  const float* ffn_w2;    /* ar.blocks.i.ff.3.weight      [D, 4D] */
+  const float* ffn_b2;    /* ar.blocks.i.ff.3.bias        [D] */
+  /* cross-attention after block i (NULL when has_attn[i] == 0)  nn/text.py:57-65 */
+  const float* nq_w;      /* ar.x_attns.i.nq.weight       [D] */
+  const float* nkv_w;     /* ar.x_attns.i.nkv.weight      [D] */
+  const float* q_w;       /* ar.x_attns.i.q_proj.weight   [D, D] */
+  const float* k_w;       /* ar.x_attns.i.k_proj.weight   [D, D] */
+  const float* v_w;       /* ar.x_attns.i.v_proj.weight   [D, D] */
+  const float* o_w;       /* ar.x_attns.i.out_proj.weight [D, D] */
+  float gate_tanh;        /* tanh(ar.x_attns.i.gate), evaluated by the caller in fp32 (nn/text.py:131) */
+} sopro_ar_layer_weights_t;
+
+typedef struct sopro_ar_weights {
+  sopro_ar_layer_weights_t layer[SOPRO_MAX_AR_LAYERS];
+  const float* final_norm_w; /* ar.norm.weight  [D]      nn/generator.py:41 */
+  const float* head_w;       /* ar.head.weight  [V, D]   nn/generator.py:42 */
+  const float* head_b;       /* ar.head.bias    [V] */
+  const float* cb_embed;     /* cb_embed.emb.weight [Q*V'+1, D]  nn/embeddings.py:47-49 */
+  int64_t cb_embed_rows;     /* Q*codebook_size + 1 */
+  int64_t bos_row;           /* Q*codebook_size, nn/embeddings.py:49 */
+} sopro_ar_weights_t;
+
+/* Per-utterance sampling knobs: kwargs of SoproTTSModel.ar_stream (model.py:218-231)
+ * plus the literals it passes to sample_token (model.py:284-291). */
+typedef struct sopro_ar_sampling {
+  float top_p;               /* 0.9 */
+  float temperature;         /* 1.05 */
+  float recovery_top_p;      /* 0.85 */
+  float recovery_temp;       /* 1.2 */
+  float repetition_penalty;  /* 1.1 */
+  int32_t top_k;             /* 50; must be in [1, 64] */
+  int32_t anti_loop;         /* 1 */
+  int32_t loop_streak;       /* 8 */
+  int32_t min_gen_frames;    /* cfg.min_gen_frames (12) */
+  int32_t stop_on_first_eos; /* 1 = what generate_tokens/stream consumers do (model.py:382-383,
+                                streaming.py:114-115); 0 = ar_stream's own rule (model.py:304) */
+} sopro_ar_sampling_t;
+
+typedef struct sopro_engine sopro_engine_t;
+typedef struct sopro_ar_session sopro_ar_session_t;
+
+const char* sopro_last_error(void);
+const char* sopro_version(void);
+
+/* Engine = device-resident copy of the AR step weights (converted to
+ * cfg->weight_dtype).  Replaces SoproTTSModel.ar + cb_embed residency after
+ * SoproTTS.from_pretrained (model.py:443-446). */
+int sopro_engine_create(const sopro_ar_config_t* cfg, const sopro_ar_weights_t* host_weights,
+                        int device, sopro_engine_t** out);
+int sopro_engine_destroy(sopro_engine_t* e);
+/* bytes of step-resident weights as stored on the device (W_step of SURVEY.md §8d) */
+int64_t sopro_engine_step_weight_bytes(const sopro_engine_t* e);
+int sopro_engine_num_sms(const sopro_engine_t* e);
+
+/* Session = state of a batch of independent utterances: conv ring buffers, text
+ * K/V, history, outputs.  Replaces ARRVQ1Generator.init_stream_state
+ * (nn/generator.py:44-68) and the locals of ar_stream (model.py:242-255). */
+int sopro_ar_session_create(sopro_engine_t* e, int max_batch, int max_steps, int max_text_len,
+                            sopro_ar_session_t** out);
+int sopro_ar_session_destroy(sopro_ar_session_t* s);
+
+/* Launch geometry override (0 = automatic): utterances per CTA team. */
+int sopro_ar_session_set_team(sopro_ar_session_t* s, int utts_per_team);
+
+/* Start `batch` utterances.  Zeroes the rings, builds the text K/V caches on the
+ * device (TextXAttnBlock.build_kv_cache, nn/text.py:75-83), resets history.
+ *   cond_ar   [batch, steps, D] f32   prep["cond_ar"] rows 0..steps-1 (model.py:272)
+ *   txt_seq   [batch, text_stride, D] f32   prep["txt_seq"], padded to text_stride rows
+ *   text_len  [batch] i32 HOST        valid rows per utterance (text_mask, model.py:186)
+ *   noise     [batch, steps, noise_k] f32   Exp(1) draws: what torch.multinomial would
+ *             consume at each step, q of argmax(p/q); noise_k >= top_k when top_p < 1
+ *             (rank-aligned, sampling.py:83-84), noise_k >= vocab otherwise (sampling.py:93)
+ *   sampling  [batch] HOST
+ */
+int sopro_ar_begin(sopro_ar_session_t* s, int batch, int steps, const float* cond_ar,
+                   const float* txt_seq, int text_stride, const int32_t* text_len,
+                   const float* noise, int noise_k, const sopro_ar_sampling_t* sampling,
+                   void* stream);
+
+/* Advance every live utterance by up to n_steps frames (the body of the
+ * `for t in range(max_steps)` loop, model.py:265-305) in ONE persistent kernel.
+ * Asynchronous on `stream`. Returns after enqueueing. */
+int sopro_ar_run(sopro_ar_session_t* s, int n_steps, void* stream);
+
+/* Device views of the outputs (valid until the session is destroyed):
+ *   tokens   [batch, steps] i32   token per step: what ar_stream yields (model.py:302)
+ *   n_tokens [batch] i32          steps taken so far;   done [batch] i32 */
+int sopro_ar_outputs(sopro_ar_session_t* s, const int32_t** tokens, const int32_t** n_tokens,
+                     const int32_t** done);
+/* Synchronous copy to HOST buffers (tokens row stride = steps given to begin). */
+int sopro_ar_read(sopro_ar_session_t* s, int32_t* tokens_host, int32_t* n_tokens_host,
+                  int32_t* done_host, void* stream);
+/* steps the slowest live utterance has reached (host value, after the last run completes) */
+int sopro_ar_position(sopro_ar_session_t* s);
+
+/* One-call host-buffer path (what a ctypes/cgo caller with numpy-like buffers uses;
+ * bench.py's e2e leg): H2D of cond/text/noise, begin, run to completion, D2H of
+ * tokens, synchronises `stream`.  All pointers HOST. */
+int sopro_ar_generate_host(sopro_ar_session_t* s, int batch, int steps, const float* cond_ar,
+                           const float* txt_seq, int text_stride, const int32_t* text_len,
+                           const float* noise, int noise_k, const sopro_ar_sampling_t* sampling,
+                           int32_t* tokens_out, int32_t* n_tokens_out, void* stream);
+
+/* ---- test / debug hooks (used by tests/, not by the product path) ---- */
+/* teacher forcing: token fed back at step t is forced[b, t]; the sampled one goes to
+ * `sampled` (sopro_ar_debug_sampled).  NULL disables. [batch, steps] i32 device. */
+int sopro_ar_set_forced_tokens(sopro_ar_session_t* s, const int32_t* forced);
+/* trace_blocks [steps, n_layers, batch, D] f32 (residual stream after block i incl. its
+ * cross-attention), trace_logits [steps, batch, V] f32; NULL disables. device. */
+int sopro_ar_set_trace(sopro_ar_session_t* s, float* trace_blocks, float* trace_logits);
+/* copy the sampled (pre-forcing) tokens into dst [batch, steps] i32 (device) */
+int sopro_ar_debug_sampled(sopro_ar_session_t* s, int32_t* dst, void* stream);
+/* copy the text K/V built by sopro_ar_begin into k_dst / v_dst, each
+ * [n_attn_layers, batch, H, Lpad, Dh] f32 (device), Lpad = max_text_len rounded up to 4 */
+int sopro_ar_debug_kv(sopro_ar_session_t* s, float* k_dst, float* v_dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOPRO_B200_H_ */

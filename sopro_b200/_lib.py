@@ -1,0 +1,101 @@
+"""ctypes binding of the C-ABI in include/sopro_b200.h (sopro_b200/lib/libsopro_b200.so).
+
+There is NO fallback: if the shared library is missing or fails to load, importing
+this module raises.  Build it with ./build.sh (or __graft_entry__.build())."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+MAX_AR_LAYERS = 16
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsopro_b200.so")
+
+
+class SoproError(RuntimeError):
+    pass
+
+
+class ArConfig(C.Structure):
+    _fields_ = [
+        ("d_model", C.c_int32), ("n_layers", C.c_int32), ("kernel", C.c_int32), ("n_heads", C.c_int32),
+        ("vocab", C.c_int32), ("eos_id", C.c_int32),
+        ("dilation", C.c_int32 * MAX_AR_LAYERS), ("has_attn", C.c_int32 * MAX_AR_LAYERS),
+        ("weight_dtype", C.c_int32),
+    ]
+
+
+_FP = C.POINTER(C.c_float)
+
+
+class ArLayerWeights(C.Structure):
+    _fields_ = [(n, _FP) for n in (
+        "norm_w", "glu_w", "glu_b", "dw_w", "dw_b", "ffn_norm_w", "ffn_w1", "ffn_b1", "ffn_w2", "ffn_b2",
+        "nq_w", "nkv_w", "q_w", "k_w", "v_w", "o_w")] + [("gate_tanh", C.c_float)]
+
+
+class ArWeights(C.Structure):
+    _fields_ = [
+        ("layer", ArLayerWeights * MAX_AR_LAYERS),
+        ("final_norm_w", _FP), ("head_w", _FP), ("head_b", _FP), ("cb_embed", _FP),
+        ("cb_embed_rows", C.c_int64), ("bos_row", C.c_int64),
+    ]
+
+
+class ArSampling(C.Structure):
+    _fields_ = [
+        ("top_p", C.c_float), ("temperature", C.c_float), ("recovery_top_p", C.c_float),
+        ("recovery_temp", C.c_float), ("repetition_penalty", C.c_float),
+        ("top_k", C.c_int32), ("anti_loop", C.c_int32), ("loop_streak", C.c_int32),
+        ("min_gen_frames", C.c_int32), ("stop_on_first_eos", C.c_int32),
+    ]
+
+
+# every symbol include/sopro_b200.h declares: name -> (restype, argtypes)
+_VP, _I, _I32P = C.c_void_p, C.c_int, C.POINTER(C.c_int32)
+SYMBOLS = {
+    "sopro_last_error": (C.c_char_p, []),
+    "sopro_version": (C.c_char_p, []),
+    "sopro_engine_create": (_I, [C.POINTER(ArConfig), C.POINTER(ArWeights), _I, C.POINTER(_VP)]),
+    "sopro_engine_destroy": (_I, [_VP]),
+    "sopro_engine_step_weight_bytes": (C.c_int64, [_VP]),
+    "sopro_engine_num_sms": (_I, [_VP]),
+    "sopro_ar_session_create": (_I, [_VP, _I, _I, _I, C.POINTER(_VP)]),
+    "sopro_ar_session_destroy": (_I, [_VP]),
+    "sopro_ar_session_set_team": (_I, [_VP, _I]),
+    "sopro_ar_begin": (_I, [_VP, _I, _I, _VP, _VP, _I, _I32P, _VP, _I, C.POINTER(ArSampling), _VP]),
+    "sopro_ar_run": (_I, [_VP, _I, _VP]),
+    "sopro_ar_outputs": (_I, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
+    "sopro_ar_read": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "sopro_ar_position": (_I, [_VP]),
+    "sopro_ar_generate_host": (_I, [_VP, _I, _I, _VP, _VP, _I, _I32P, _VP, _I, C.POINTER(ArSampling), _VP, _VP, _VP]),
+    "sopro_ar_set_forced_tokens": (_I, [_VP, _VP]),
+    "sopro_ar_set_trace": (_I, [_VP, _VP, _VP]),
+    "sopro_ar_debug_sampled": (_I, [_VP, _VP, _VP]),
+    "sopro_ar_debug_kv": (_I, [_VP, _VP, _VP, _VP]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SoproError(
+            f"{LIB_PATH} not found: the CUDA extension is not built (run ./build.sh). "
+            "sopro_b200 has no CPU or PyTorch fallback for the hot path.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().sopro_last_error()
+        raise SoproError(f"sopro_b200 error {rc}: {msg.decode() if msg else '?'}")

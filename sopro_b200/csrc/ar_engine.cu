@@ -1,0 +1,671 @@
+// Host side of the AR engine + the C-ABI declared in include/sopro_b200.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sopro_b200.h"
+#include "ar_kernel.cuh"
+
+using namespace sopro;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return fail(SOPRO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+uint16_t f32_to_bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  const uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return (uint16_t)(u >> 16);
+}
+
+struct Arena {
+  std::vector<unsigned char> host;
+  size_t add(size_t bytes) {
+    const size_t off = align_up(host.size(), 256);
+    host.resize(off + bytes);
+    return off;
+  }
+  size_t add_f32(const float* src, size_t n) {
+    const size_t off = add(n * 4);
+    memcpy(host.data() + off, src, n * 4);
+    return off;
+  }
+  size_t add_mat(const float* src, size_t n, int wdtype) {
+    if (wdtype == SOPRO_W_F32) return add_f32(src, n);
+    const size_t off = add(n * 2);
+    uint16_t* d = reinterpret_cast<uint16_t*>(host.data() + off);
+    for (size_t i = 0; i < n; ++i) d[i] = f32_to_bf16_rne(src[i]);
+    return off;
+  }
+};
+
+}  // namespace
+
+struct sopro_engine {
+  int device = 0;
+  int n_sms = 0;
+  sopro_ar_config_t cfg{};
+  int D = 0, F = 0, V = 0, Vpad = 0, H = 0, Dh = 0, Kc = 0, n_layers = 0, n_attn = 0;
+  unsigned char* dev = nullptr;  // weight arena
+  size_t dev_bytes = 0;
+  int64_t step_weight_bytes = 0;
+  LayerDev layer[kMaxLayers]{};
+  const float* nkv_w[kMaxLayers]{};  // per attn slot
+  const void* wk[kMaxLayers]{};
+  const void* wv[kMaxLayers]{};
+  const float* final_norm_w = nullptr;
+  const void* head_w = nullptr;
+  const float* head_b = nullptr;
+  const float* emb = nullptr;
+  long long ring_floats_per_utt = 0;
+};
+
+struct sopro_ar_session {
+  sopro_engine* e = nullptr;
+  int max_batch = 0, max_steps = 0, Lmax = 0;
+  int utts_per_team = 0;  // 0 = auto
+  // device buffers
+  float *ring = nullptr, *xa = nullptr, *xb = nullptr, *hbuf = nullptr, *qbuf = nullptr, *abuf = nullptr,
+        *logits = nullptr, *kc = nullptr, *vc = nullptr;
+  int *tokens = nullptr, *sampled = nullptr, *text_len = nullptr, *n_tokens = nullptr, *done = nullptr;
+  UttState* st = nullptr;
+  SamplingDev* samp = nullptr;
+  unsigned* barrier = nullptr;
+  // staging for the host-buffer path
+  float *h_cond = nullptr, *h_txt = nullptr, *h_noise = nullptr;
+  size_t h_cond_cap = 0, h_txt_cap = 0, h_noise_cap = 0;
+  // current batch
+  int B = 0, steps = 0, noise_k = 0, t_pos = 0;
+  const float* cond = nullptr;
+  const float* noise = nullptr;
+  const int* forced = nullptr;
+  float* trace_blocks = nullptr;
+  float* trace_logits = nullptr;
+  bool begun = false;
+  std::vector<UttState> host_st;
+};
+
+extern "C" {
+
+const char* sopro_last_error(void) { return g_err.c_str(); }
+const char* sopro_version(void) { return "sopro_b200 0.1 (sm_100a)"; }
+
+int sopro_engine_create(const sopro_ar_config_t* cfg, const sopro_ar_weights_t* w, int device,
+                        sopro_engine_t** out) {
+  if (!cfg || !w || !out) return fail(SOPRO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0)
+    return fail(SOPRO_ERR_UNSUPPORTED, "no CUDA device (%s); this engine has no CPU fallback",
+                ce == cudaSuccess ? "device count 0" : cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(SOPRO_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(SOPRO_ERR_UNSUPPORTED, "device %d is sm_%d%d; this build targets sm_100a only", device, prop.major,
+                prop.minor);
+  const int D = cfg->d_model, NL = cfg->n_layers, Kc = cfg->kernel, H = cfg->n_heads, V = cfg->vocab;
+  if (D <= 0 || D % 4 != 0) return fail(SOPRO_ERR_INVALID, "d_model must be a positive multiple of 4 (got %d)", D);
+  if (NL <= 0 || NL > kMaxLayers) return fail(SOPRO_ERR_INVALID, "n_layers must be in [1,%d]", kMaxLayers);
+  if (H <= 0 || D % H != 0 || (D / H) % 4 != 0) return fail(SOPRO_ERR_INVALID, "bad head geometry D=%d H=%d", D, H);
+  if (Kc < 1 || Kc > 64) return fail(SOPRO_ERR_INVALID, "kernel must be in [1,64]");
+  if (V < 2 || V > kSampNPT * kThreads) return fail(SOPRO_ERR_INVALID, "vocab must be in [2,%d]", kSampNPT * kThreads);
+  if (cfg->eos_id < 0 || cfg->eos_id >= V) return fail(SOPRO_ERR_INVALID, "eos_id out of range");
+  if (cfg->weight_dtype != SOPRO_W_F32 && cfg->weight_dtype != SOPRO_W_BF16)
+    return fail(SOPRO_ERR_INVALID, "weight_dtype must be 0 (f32) or 1 (bf16)");
+  if (w->cb_embed_rows < V || w->bos_row < 0 || w->bos_row >= w->cb_embed_rows)
+    return fail(SOPRO_ERR_INVALID, "cb_embed has %lld rows, need >= vocab %d and a valid bos_row",
+                (long long)w->cb_embed_rows, V);
+  CK(cudaSetDevice(device));
+
+  sopro_engine* e = new sopro_engine();
+  e->device = device;
+  e->n_sms = prop.multiProcessorCount;
+  e->cfg = *cfg;
+  e->D = D;
+  e->F = 4 * D;
+  e->V = V;
+  e->Vpad = (int)align_up((size_t)V, 4);
+  e->H = H;
+  e->Dh = D / H;
+  e->Kc = Kc;
+  e->n_layers = NL;
+  const int wd = cfg->weight_dtype;
+  const size_t wsz = wd == SOPRO_W_F32 ? 4 : 2;
+
+  Arena A;
+  struct Off {
+    size_t norm_w, glu_w, glu_b, dw_w, dw_b, ffn_norm_w, w1, b1, w2, b2, nq_w, nkv_w, wq, wk, wv, wo;
+  } off[kMaxLayers];
+  int64_t step_bytes = 0;
+  int n_attn = 0;
+  long long ring_off = 0;
+  for (int i = 0; i < NL; ++i) {
+    const sopro_ar_layer_weights_t& L = w->layer[i];
+    if (!L.norm_w || !L.glu_w || !L.glu_b || !L.dw_w || !L.dw_b || !L.ffn_norm_w || !L.ffn_w1 || !L.ffn_b1 ||
+        !L.ffn_w2 || !L.ffn_b2) {
+      delete e;
+      return fail(SOPRO_ERR_INVALID, "layer %d: null weight pointer", i);
+    }
+    if (cfg->dilation[i] < 1) {
+      delete e;
+      return fail(SOPRO_ERR_INVALID, "layer %d: dilation must be >= 1", i);
+    }
+    off[i].norm_w = A.add_f32(L.norm_w, D);
+    off[i].glu_w = A.add_mat(L.glu_w, (size_t)2 * D * D, wd);
+    off[i].glu_b = A.add_f32(L.glu_b, 2 * D);
+    off[i].dw_w = A.add_f32(L.dw_w, (size_t)D * Kc);
+    off[i].dw_b = A.add_f32(L.dw_b, D);
+    off[i].ffn_norm_w = A.add_f32(L.ffn_norm_w, D);
+    off[i].w1 = A.add_mat(L.ffn_w1, (size_t)4 * D * D, wd);
+    off[i].b1 = A.add_f32(L.ffn_b1, 4 * D);
+    off[i].w2 = A.add_mat(L.ffn_w2, (size_t)4 * D * D, wd);
+    off[i].b2 = A.add_f32(L.ffn_b2, D);
+    step_bytes += (int64_t)(D + 2 * D + (size_t)D * Kc + D + D + 4 * D + D) * 4 + (int64_t)(2 + 4 + 4) * D * D * wsz;
+    if (cfg->has_attn[i]) {
+      if (!L.nq_w || !L.nkv_w || !L.q_w || !L.k_w || !L.v_w || !L.o_w) {
+        delete e;
+        return fail(SOPRO_ERR_INVALID, "layer %d: has_attn set but attention weights are null", i);
+      }
+      off[i].nq_w = A.add_f32(L.nq_w, D);
+      off[i].nkv_w = A.add_f32(L.nkv_w, D);
+      off[i].wq = A.add_mat(L.q_w, (size_t)D * D, wd);
+      off[i].wk = A.add_mat(L.k_w, (size_t)D * D, wd);
+      off[i].wv = A.add_mat(L.v_w, (size_t)D * D, wd);
+      off[i].wo = A.add_mat(L.o_w, (size_t)D * D, wd);
+      step_bytes += (int64_t)D * 4 + (int64_t)2 * D * D * wsz + 4;
+    }
+  }
+  const size_t off_fn = A.add_f32(w->final_norm_w, D);
+  const size_t off_hw = A.add_mat(w->head_w, (size_t)V * D, wd);
+  const size_t off_hb = A.add_f32(w->head_b, V);
+  step_bytes += (int64_t)D * 4 + (int64_t)V * D * wsz + (int64_t)V * 4;
+  // compact embedding table: rows 0..V-1 (cb_index 0 -> row == token id, nn/embeddings.py:51-55;
+  // row V-1 == table row 2048 is what an early EOS feeds back) + the BOS row
+  const size_t off_emb = A.add((size_t)(V + 1) * D * 4);
+  memcpy(A.host.data() + off_emb, w->cb_embed, (size_t)V * D * 4);
+  memcpy(A.host.data() + off_emb + (size_t)V * D * 4, w->cb_embed + (size_t)w->bos_row * D, (size_t)D * 4);
+
+  e->dev_bytes = align_up(A.host.size(), 256);
+  cudaError_t err = cudaMalloc(&e->dev, e->dev_bytes);
+  if (err != cudaSuccess) {
+    delete e;
+    return fail(SOPRO_ERR_CUDA, "cudaMalloc(%zu) failed: %s", e->dev_bytes, cudaGetErrorString(err));
+  }
+  err = cudaMemcpy(e->dev, A.host.data(), A.host.size(), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    cudaFree(e->dev);
+    delete e;
+    return fail(SOPRO_ERR_CUDA, "weight upload failed: %s", cudaGetErrorString(err));
+  }
+  auto F32 = [&](size_t o) { return reinterpret_cast<const float*>(e->dev + o); };
+  auto PTR = [&](size_t o) { return reinterpret_cast<const void*>(e->dev + o); };
+  for (int i = 0; i < NL; ++i) {
+    LayerDev& L = e->layer[i];
+    L.norm_w = F32(off[i].norm_w);
+    L.glu_w = PTR(off[i].glu_w);
+    L.glu_b = F32(off[i].glu_b);
+    L.dw_w = F32(off[i].dw_w);
+    L.dw_b = F32(off[i].dw_b);
+    L.ffn_norm_w = F32(off[i].ffn_norm_w);
+    L.w1 = PTR(off[i].w1);
+    L.b1 = F32(off[i].b1);
+    L.w2 = PTR(off[i].w2);
+    L.b2 = F32(off[i].b2);
+    L.dil = cfg->dilation[i];
+    L.ring_len = (Kc - 1) * L.dil + 1;
+    L.has_attn = cfg->has_attn[i] ? 1 : 0;
+    L.attn_slot = -1;
+    if (L.has_attn) {
+      L.nq_w = F32(off[i].nq_w);
+      L.wq = PTR(off[i].wq);
+      L.wo = PTR(off[i].wo);
+      L.gate_tanh = w->layer[i].gate_tanh;
+      L.attn_slot = n_attn;
+      e->nkv_w[n_attn] = F32(off[i].nkv_w);
+      e->wk[n_attn] = PTR(off[i].wk);
+      e->wv[n_attn] = PTR(off[i].wv);
+      ++n_attn;
+    }
+    ring_off += (long long)L.ring_len * D;  // per utterance; scaled by batch at session time
+  }
+  e->n_attn = n_attn;
+  e->ring_floats_per_utt = ring_off;
+  e->final_norm_w = F32(off_fn);
+  e->head_w = PTR(off_hw);
+  e->head_b = F32(off_hb);
+  e->emb = F32(off_emb);
+  e->step_weight_bytes = step_bytes;
+  *out = e;
+  return SOPRO_OK;
+}
+
+int sopro_engine_destroy(sopro_engine_t* e) {
+  if (!e) return SOPRO_OK;
+  cudaSetDevice(e->device);
+  if (e->dev) cudaFree(e->dev);
+  delete e;
+  return SOPRO_OK;
+}
+
+int64_t sopro_engine_step_weight_bytes(const sopro_engine_t* e) { return e ? e->step_weight_bytes : 0; }
+int sopro_engine_num_sms(const sopro_engine_t* e) { return e ? e->n_sms : 0; }
+
+static void session_free(sopro_ar_session* s) {
+  cudaFree(s->ring);
+  cudaFree(s->xa);
+  cudaFree(s->xb);
+  cudaFree(s->hbuf);
+  cudaFree(s->qbuf);
+  cudaFree(s->abuf);
+  cudaFree(s->logits);
+  cudaFree(s->kc);
+  cudaFree(s->vc);
+  cudaFree(s->tokens);
+  cudaFree(s->sampled);
+  cudaFree(s->text_len);
+  cudaFree(s->n_tokens);
+  cudaFree(s->done);
+  cudaFree(s->st);
+  cudaFree(s->samp);
+  cudaFree(s->barrier);
+  cudaFree(s->h_cond);
+  cudaFree(s->h_txt);
+  cudaFree(s->h_noise);
+}
+
+int sopro_ar_session_create(sopro_engine_t* e, int max_batch, int max_steps, int max_text_len,
+                            sopro_ar_session_t** out) {
+  if (!e || !out) return fail(SOPRO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (max_batch < 1 || max_steps < 1 || max_text_len < 1)
+    return fail(SOPRO_ERR_INVALID, "max_batch, max_steps, max_text_len must be >= 1");
+  if (max_batch > e->n_sms * kMaxUttPerTeam)
+    return fail(SOPRO_ERR_INVALID, "max_batch %d exceeds %d (SMs x %d utterances per team)", max_batch,
+                e->n_sms * kMaxUttPerTeam, kMaxUttPerTeam);
+  CK(cudaSetDevice(e->device));
+  sopro_ar_session* s = new sopro_ar_session();
+  s->e = e;
+  s->max_batch = max_batch;
+  s->max_steps = max_steps;
+  s->Lmax = (int)align_up((size_t)max_text_len, 4);
+  const size_t B = max_batch, D = e->D, F = e->F;
+  const size_t kv = (size_t)std::max(e->n_attn, 1) * B * s->Lmax * D;
+  cudaError_t err = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) {
+    if (err == cudaSuccess) err = cudaMalloc(p, std::max<size_t>(bytes, 256));
+  };
+  A((void**)&s->ring, (size_t)e->ring_floats_per_utt * B * 4);
+  A((void**)&s->xa, B * D * 4);
+  A((void**)&s->xb, B * D * 4);
+  A((void**)&s->hbuf, B * F * 4);
+  A((void**)&s->qbuf, B * D * 4);
+  A((void**)&s->abuf, B * D * 4);
+  A((void**)&s->logits, B * e->Vpad * 4);
+  A((void**)&s->kc, kv * 4);
+  A((void**)&s->vc, kv * 4);
+  A((void**)&s->tokens, B * max_steps * 4);
+  A((void**)&s->sampled, B * max_steps * 4);
+  A((void**)&s->text_len, B * 4);
+  A((void**)&s->n_tokens, B * 4);
+  A((void**)&s->done, B * 4);
+  A((void**)&s->st, B * sizeof(UttState));
+  A((void**)&s->samp, B * sizeof(SamplingDev));
+  A((void**)&s->barrier, (size_t)e->n_sms * 32 * 4);
+  if (err != cudaSuccess) {
+    session_free(s);
+    delete s;
+    return fail(SOPRO_ERR_CUDA, "session allocation failed: %s", cudaGetErrorString(err));
+  }
+  *out = s;
+  return SOPRO_OK;
+}
+
+int sopro_ar_session_destroy(sopro_ar_session_t* s) {
+  if (!s) return SOPRO_OK;
+  cudaSetDevice(s->e->device);
+  session_free(s);
+  delete s;
+  return SOPRO_OK;
+}
+
+int sopro_ar_session_set_team(sopro_ar_session_t* s, int utts_per_team) {
+  if (!s) return fail(SOPRO_ERR_INVALID, "null session");
+  if (utts_per_team < 0 || utts_per_team > kMaxUttPerTeam)
+    return fail(SOPRO_ERR_INVALID, "utts_per_team must be in [0,%d]", kMaxUttPerTeam);
+  s->utts_per_team = utts_per_team;
+  return SOPRO_OK;
+}
+
+}  // extern "C"
+
+template <typename WT>
+static int launch_kv(sopro_ar_session* s, const float* txt, int text_stride, const std::vector<int>& lens,
+                     cudaStream_t st) {
+  sopro_engine* e = s->e;
+  if (e->n_attn == 0) return SOPRO_OK;
+  KvParams kp{};
+  kp.D = e->D;
+  kp.H = e->H;
+  kp.Dh = e->Dh;
+  kp.B = s->B;
+  kp.Lmax = s->Lmax;
+  kp.text_stride = text_stride;
+  kp.n_attn = e->n_attn;
+  kp.txt = txt;
+  kp.text_len = s->text_len;
+  for (int i = 0; i < e->n_attn; ++i) {
+    kp.nkv_w[i] = e->nkv_w[i];
+    kp.wk[i] = e->wk[i];
+    kp.wv[i] = e->wv[i];
+  }
+  kp.kc = s->kc;
+  kp.vc = s->vc;
+  int maxlen = 0;
+  for (int v : lens) maxlen = std::max(maxlen, v);
+  dim3 grid((maxlen + 15) / 16, s->B, e->n_attn);
+  const size_t smem = (size_t)16 * e->D * 4;
+  CK(cudaFuncSetAttribute(kv_build_kernel<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kv_build_kernel<WT><<<grid, kThreads, smem, st>>>(kp);
+  CK(cudaGetLastError());
+  return SOPRO_OK;
+}
+
+extern "C" {
+
+int sopro_ar_begin(sopro_ar_session_t* s, int batch, int steps, const float* cond_ar, const float* txt_seq,
+                   int text_stride, const int32_t* text_len, const float* noise, int noise_k,
+                   const sopro_ar_sampling_t* sampling, void* stream) {
+  if (!s || !cond_ar || !txt_seq || !text_len || !noise || !sampling)
+    return fail(SOPRO_ERR_INVALID, "null argument");
+  sopro_engine* e = s->e;
+  if (batch < 1 || batch > s->max_batch) return fail(SOPRO_ERR_INVALID, "batch %d not in [1,%d]", batch, s->max_batch);
+  if (steps < 1 || steps > s->max_steps) return fail(SOPRO_ERR_INVALID, "steps %d not in [1,%d]", steps, s->max_steps);
+  if (text_stride < 1) return fail(SOPRO_ERR_INVALID, "text_stride must be >= 1");
+  std::vector<int> lens(batch);
+  std::vector<SamplingDev> sd(batch);
+  for (int b = 0; b < batch; ++b) {
+    lens[b] = text_len[b];
+    if (lens[b] < 1 || lens[b] > s->Lmax || lens[b] > text_stride)
+      return fail(SOPRO_ERR_INVALID, "text_len[%d]=%d not in [1,min(%d,%d)]", b, lens[b], s->Lmax, text_stride);
+    const sopro_ar_sampling_t& q = sampling[b];
+    if (q.top_k < 1 || q.top_k > kMaxTopK)
+      return fail(SOPRO_ERR_INVALID, "sampling[%d].top_k=%d not in [1,%d] (top_k=0 is not on the ar_stream path)", b,
+                  q.top_k, kMaxTopK);
+    const int need = (q.top_p < 1.0f && q.recovery_top_p < 1.0f) ? std::min(q.top_k, e->V) : e->V;
+    if (noise_k < need)
+      return fail(SOPRO_ERR_INVALID, "noise_k=%d too small: utterance %d needs %d draws per step", noise_k, b, need);
+    sd[b].top_p = q.top_p;
+    sd[b].temperature = q.temperature;
+    sd[b].rec_top_p = q.recovery_top_p;
+    sd[b].rec_temp = q.recovery_temp;
+    sd[b].rep_pen = q.repetition_penalty;
+    sd[b].top_k = q.top_k;
+    sd[b].anti_loop = q.anti_loop;
+    sd[b].loop_streak = q.loop_streak;
+    sd[b].min_gen = q.min_gen_frames;
+    sd[b].stop_on_first_eos = q.stop_on_first_eos;
+  }
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  s->B = batch;
+  s->steps = steps;
+  s->noise_k = noise_k;
+  s->cond = cond_ar;
+  s->noise = noise;
+  s->t_pos = 0;
+  s->host_st.assign(batch, UttState{0, -1, 0, 0, 0, {0, 0, 0}});
+  CK(cudaMemcpyAsync(s->text_len, lens.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s->samp, sd.data(), (size_t)batch * sizeof(SamplingDev), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s->st, s->host_st.data(), (size_t)batch * sizeof(UttState), cudaMemcpyHostToDevice, st));
+  // the pageable host vectors above die at return: make the copies complete first
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMemsetAsync(s->ring, 0, (size_t)e->ring_floats_per_utt * batch * 4, st));
+  CK(cudaMemsetAsync(s->tokens, 0, (size_t)batch * steps * 4, st));
+  CK(cudaMemsetAsync(s->sampled, 0, (size_t)batch * steps * 4, st));
+  CK(cudaMemsetAsync(s->n_tokens, 0, (size_t)batch * 4, st));
+  CK(cudaMemsetAsync(s->done, 0, (size_t)batch * 4, st));
+  const size_t kv = (size_t)std::max(e->n_attn, 1) * batch * s->Lmax * e->D;
+  CK(cudaMemsetAsync(s->kc, 0, kv * 4, st));
+  CK(cudaMemsetAsync(s->vc, 0, kv * 4, st));
+  int rc = e->cfg.weight_dtype == SOPRO_W_F32 ? launch_kv<float>(s, txt_seq, text_stride, lens, st)
+                                               : launch_kv<__nv_bfloat16>(s, txt_seq, text_stride, lens, st);
+  if (rc != SOPRO_OK) return rc;
+  s->begun = true;
+  return SOPRO_OK;
+}
+
+}  // extern "C"
+
+template <typename WT>
+static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t st) {
+  sopro_engine* e = s->e;
+  ArParams p{};
+  p.D = e->D;
+  p.F = e->F;
+  p.V = e->V;
+  p.Vpad = e->Vpad;
+  p.H = e->H;
+  p.Dh = e->Dh;
+  p.Kc = e->Kc;
+  p.n_layers = e->n_layers;
+  p.eos_id = e->cfg.eos_id;
+  long long roff = 0;
+  for (int i = 0; i < e->n_layers; ++i) {
+    p.layer[i] = e->layer[i];
+    p.layer[i].ring_off = roff;
+    roff += (long long)e->layer[i].ring_len * e->D * s->B;
+  }
+  p.final_norm_w = e->final_norm_w;
+  p.head_w = e->head_w;
+  p.head_b = e->head_b;
+  p.emb = e->emb;
+  p.B = s->B;
+  p.steps = s->steps;
+  p.Lmax = s->Lmax;
+  p.noise_k = s->noise_k;
+  p.cond = s->cond;
+  p.noise = s->noise;
+  p.kc = s->kc;
+  p.vc = s->vc;
+  p.text_len = s->text_len;
+  p.ring = s->ring;
+  p.xa = s->xa;
+  p.xb = s->xb;
+  p.hbuf = s->hbuf;
+  p.qbuf = s->qbuf;
+  p.abuf = s->abuf;
+  p.logits = s->logits;
+  p.tokens = s->tokens;
+  p.sampled = s->sampled;
+  p.n_tokens = s->n_tokens;
+  p.done = s->done;
+  p.forced = s->forced;
+  p.st = s->st;
+  p.samp = s->samp;
+  p.trace_blocks = s->trace_blocks;
+  p.trace_logits = s->trace_logits;
+  p.barrier = s->barrier;
+  // ---- team geometry
+  int Bt = s->utts_per_team;
+  if (Bt <= 0) {
+    if (const char* env = getenv("SOPRO_AR_UTTS_PER_TEAM")) Bt = atoi(env);
+  }
+  if (Bt <= 0) Bt = s->B <= 8 ? s->B : (s->B <= 16 * e->n_sms / 8 ? 16 : kMaxUttPerTeam);
+  Bt = std::min(Bt, kMaxUttPerTeam);
+  int g = (s->B + Bt - 1) / Bt;
+  if (g > e->n_sms) {
+    Bt = kMaxUttPerTeam;
+    g = (s->B + Bt - 1) / Bt;
+  }
+  if (g > e->n_sms) return fail(SOPRO_ERR_INVALID, "batch %d needs %d teams > %d SMs", s->B, g, e->n_sms);
+  Bt = (s->B + g - 1) / g;  // balance
+  g = (s->B + Bt - 1) / Bt;
+  const int P = e->n_sms / g;
+  p.g = g;
+  p.P = P;
+  p.Bt = Bt;
+  p.t_begin = t_begin;
+  p.t_end = t_end;
+  const size_t need_act = (size_t)Bt * std::max(2 * e->D, e->F) * 4;
+  const size_t need_att = (size_t)kWarps * (s->Lmax + e->Dh) * 4;
+  const size_t need_smp = (size_t)e->Vpad * 4 + e->Vpad + 16;
+  const size_t smem = align_up(std::max(need_act, std::max(need_att, need_smp)), 16);
+  if (smem > 227 * 1024)
+    return fail(SOPRO_ERR_INVALID, "shared memory need %zu B > 227 KB (Bt=%d, Lmax=%d)", smem, Bt, s->Lmax);
+  CK(cudaFuncSetAttribute(ar_persistent_kernel<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ar_persistent_kernel<WT>, kThreads, smem));
+  if (occ < 1) return fail(SOPRO_ERR_CUDA, "persistent kernel does not fit an SM (smem %zu)", smem);
+  CK(cudaMemsetAsync(s->barrier, 0, (size_t)e->n_sms * 32 * 4, st));
+  void* args[] = {(void*)&p};
+  CK(cudaLaunchCooperativeKernel((const void*)ar_persistent_kernel<WT>, dim3(g * P), dim3(kThreads), args, smem, st));
+  return SOPRO_OK;
+}
+
+extern "C" {
+
+int sopro_ar_run(sopro_ar_session_t* s, int n_steps, void* stream) {
+  if (!s) return fail(SOPRO_ERR_INVALID, "null session");
+  if (!s->begun) return fail(SOPRO_ERR_STATE, "sopro_ar_run before sopro_ar_begin");
+  if (n_steps < 1) return fail(SOPRO_ERR_INVALID, "n_steps must be >= 1");
+  sopro_engine* e = s->e;
+  CK(cudaSetDevice(e->device));
+  const int t0 = s->t_pos;
+  const int t1 = std::min(s->steps, t0 + n_steps);
+  if (t0 >= t1) return SOPRO_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = e->cfg.weight_dtype == SOPRO_W_F32 ? launch_ar<float>(s, t0, t1, st)
+                                               : launch_ar<__nv_bfloat16>(s, t0, t1, st);
+  if (rc != SOPRO_OK) return rc;
+  s->t_pos = t1;
+  return SOPRO_OK;
+}
+
+int sopro_ar_outputs(sopro_ar_session_t* s, const int32_t** tokens, const int32_t** n_tokens,
+                     const int32_t** done) {
+  if (!s) return fail(SOPRO_ERR_INVALID, "null session");
+  if (tokens) *tokens = s->tokens;
+  if (n_tokens) *n_tokens = s->n_tokens;
+  if (done) *done = s->done;
+  return SOPRO_OK;
+}
+
+int sopro_ar_read(sopro_ar_session_t* s, int32_t* tokens_host, int32_t* n_tokens_host, int32_t* done_host,
+                  void* stream) {
+  if (!s) return fail(SOPRO_ERR_INVALID, "null session");
+  if (!s->begun) return fail(SOPRO_ERR_STATE, "sopro_ar_read before sopro_ar_begin");
+  CK(cudaSetDevice(s->e->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (tokens_host)
+    CK(cudaMemcpyAsync(tokens_host, s->tokens, (size_t)s->B * s->steps * 4, cudaMemcpyDeviceToHost, st));
+  s->host_st.resize(s->B);
+  CK(cudaMemcpyAsync(s->host_st.data(), s->st, (size_t)s->B * sizeof(UttState), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int b = 0; b < s->B; ++b) {
+    if (n_tokens_host) n_tokens_host[b] = s->host_st[b].len;
+    if (done_host) done_host[b] = s->host_st[b].done;
+  }
+  return SOPRO_OK;
+}
+
+int sopro_ar_position(sopro_ar_session_t* s) { return s ? s->t_pos : -1; }
+
+static int ensure(float** p, size_t* cap, size_t bytes) {
+  if (*cap >= bytes) return SOPRO_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  cudaError_t e = cudaMalloc((void**)p, bytes);
+  if (e != cudaSuccess) return fail(SOPRO_ERR_CUDA, "staging alloc %zu failed: %s", bytes, cudaGetErrorString(e));
+  *cap = bytes;
+  return SOPRO_OK;
+}
+
+int sopro_ar_generate_host(sopro_ar_session_t* s, int batch, int steps, const float* cond_ar, const float* txt_seq,
+                           int text_stride, const int32_t* text_len, const float* noise, int noise_k,
+                           const sopro_ar_sampling_t* sampling, int32_t* tokens_out, int32_t* n_tokens_out,
+                           void* stream) {
+  if (!s || !cond_ar || !txt_seq || !text_len || !noise || !sampling || !tokens_out)
+    return fail(SOPRO_ERR_INVALID, "null argument");
+  if (batch < 1 || batch > s->max_batch || steps < 1 || steps > s->max_steps || text_stride < 1 || noise_k < 1)
+    return fail(SOPRO_ERR_INVALID, "bad batch/steps/text_stride/noise_k");
+  sopro_engine* e = s->e;
+  CK(cudaSetDevice(e->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t nc = (size_t)batch * steps * e->D * 4, nt = (size_t)batch * text_stride * e->D * 4,
+               nn = (size_t)batch * steps * noise_k * 4;
+  int rc;
+  if ((rc = ensure(&s->h_cond, &s->h_cond_cap, nc)) != SOPRO_OK) return rc;
+  if ((rc = ensure(&s->h_txt, &s->h_txt_cap, nt)) != SOPRO_OK) return rc;
+  if ((rc = ensure(&s->h_noise, &s->h_noise_cap, nn)) != SOPRO_OK) return rc;
+  CK(cudaMemcpyAsync(s->h_cond, cond_ar, nc, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s->h_txt, txt_seq, nt, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s->h_noise, noise, nn, cudaMemcpyHostToDevice, st));
+  rc = sopro_ar_begin(s, batch, steps, s->h_cond, s->h_txt, text_stride, text_len, s->h_noise, noise_k, sampling,
+                      stream);
+  if (rc != SOPRO_OK) return rc;
+  rc = sopro_ar_run(s, steps, stream);
+  if (rc != SOPRO_OK) return rc;
+  return sopro_ar_read(s, tokens_out, n_tokens_out, nullptr, stream);
+}
+
+int sopro_ar_set_forced_tokens(sopro_ar_session_t* s, const int32_t* forced) {
+  if (!s) return fail(SOPRO_ERR_INVALID, "null session");
+  s->forced = forced;
+  return SOPRO_OK;
+}
+
+int sopro_ar_set_trace(sopro_ar_session_t* s, float* trace_blocks, float* trace_logits) {
+  if (!s) return fail(SOPRO_ERR_INVALID, "null session");
+  s->trace_blocks = trace_blocks;
+  s->trace_logits = trace_logits;
+  return SOPRO_OK;
+}
+
+int sopro_ar_debug_sampled(sopro_ar_session_t* s, int32_t* dst, void* stream) {
+  if (!s || !dst) return fail(SOPRO_ERR_INVALID, "null argument");
+  CK(cudaMemcpyAsync(dst, s->sampled, (size_t)s->B * s->steps * 4, cudaMemcpyDeviceToDevice,
+                     reinterpret_cast<cudaStream_t>(stream)));
+  return SOPRO_OK;
+}
+
+int sopro_ar_debug_kv(sopro_ar_session_t* s, float* k_dst, float* v_dst, void* stream) {
+  if (!s) return fail(SOPRO_ERR_INVALID, "null argument");
+  const size_t n = (size_t)s->e->n_attn * s->B * s->Lmax * s->e->D * 4;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (k_dst) CK(cudaMemcpyAsync(k_dst, s->kc, n, cudaMemcpyDeviceToDevice, st));
+  if (v_dst) CK(cudaMemcpyAsync(v_dst, s->vc, n, cudaMemcpyDeviceToDevice, st));
+  return SOPRO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,967 @@
+// Persistent autoregressive codec-token kernel for sm_100a.
+//
+// One launch runs up to n_steps frames for a batch of independent utterances:
+// the body of SoproTTSModel.ar_stream's loop (reference model.py:265-305) —
+// embedding add, 6x SSMLiteBlock.forward_step (nn/blocks.py:150-162), 3x cached
+// TextXAttnBlock (nn/text.py:85-132), final RMSNorm + head (nn/generator.py:127-128),
+// sample_token (sampling.py:24-93) and the anti-loop / EOS bookkeeping
+// (model.py:274-305) — without returning to the host.
+//
+// Work decomposition: the grid is split into `g` TEAMS of `P`
+// CTAs (one CTA per SM, co-resident: cooperative launch).  A team owns a group
+// of <= 32 utterances.  Every stage of the step is a skinny GEMM
+// [utterances x K] . [K x N]; inside a team the N output features are
+// partitioned over the P CTAs, so each weight element is read from L2/HBM once
+// per team per step with coalesced 128-bit loads, and the [utterances x K]
+// activations are broadcast through L2.  Stages are separated by a team-scoped
+// barrier (one atomic counter per team, release/acquire at gpu scope).
+// All arithmetic is fp32 (FFMA2 packed pairs, warp-shuffle reductions); bf16
+// is a weight STORAGE format only.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace sopro {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxLayers = 16;
+constexpr int kMaxTopK = 64;
+constexpr int kMaxUttPerTeam = 32;
+constexpr int kSampNPT = 8;  // vocab entries per thread in the sampler: V <= 4096
+
+struct LayerDev {
+  const float* norm_w;
+  const void* glu_w;
+  const float* glu_b;
+  const float* dw_w;  // [D][k]
+  const float* dw_b;
+  const float* ffn_norm_w;
+  const void* w1;
+  const float* b1;
+  const void* w2;
+  const float* b2;
+  const float* nq_w;
+  const void* wq;
+  const void* wo;
+  float gate_tanh;
+  int has_attn;
+  int attn_slot;      // index into the K/V cache
+  int dil;
+  int ring_len;       // (k-1)*dil + 1
+  long long ring_off; // float offset of this layer's rings: [B][ring_len][D]
+};
+
+struct UttState {
+  int len;       // tokens produced so far
+  int last;      // last token (-1 = none)
+  int streak;    // same-token streak (model.py:296-299)
+  int recovery;  // next step samples with the recovery (top_p, temp) (model.py:274-279)
+  int done;
+  int pad[3];
+};
+
+struct SamplingDev {
+  float top_p, temperature, rec_top_p, rec_temp, rep_pen;
+  int top_k, anti_loop, loop_streak, min_gen, stop_on_first_eos;
+};
+
+struct ArParams {
+  int D, F, V, Vpad, H, Dh, Kc, n_layers, eos_id;
+  LayerDev layer[kMaxLayers];
+  const float* final_norm_w;
+  const void* head_w;
+  const float* head_b;
+  const float* emb;  // [V+1][D]; row V = BOS
+  // ---- session
+  int B, steps, Lmax, noise_k;
+  const float* cond;   // [B][steps][D]
+  const float* noise;  // [B][steps][noise_k]
+  const float* kc;     // [n_attn][B][H][Lmax][Dh]
+  const float* vc;
+  const int* text_len;
+  float* ring;
+  float* xa;      // [B][D]
+  float* xb;      // [B][D]
+  float* hbuf;    // [B][F]
+  float* qbuf;    // [B][D]
+  float* abuf;    // [B][D]
+  float* logits;  // [B][Vpad]
+  int* tokens;    // [B][steps]
+  int* sampled;   // [B][steps]
+  int* n_tokens;  // [B]
+  int* done;      // [B]
+  const int* forced;
+  UttState* st;
+  const SamplingDev* samp;
+  float* trace_blocks;
+  float* trace_logits;
+  unsigned* barrier;  // [g][32]
+  int g, P, Bt;
+  int t_begin, t_end;
+};
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// weights: read-only path, 4 consecutive k per lane
+__device__ __forceinline__ float4 ldw4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 ldw4(const __nv_bfloat16* p) {
+  uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  float4 r;
+  r.x = __uint_as_float(u.x << 16);
+  r.y = __uint_as_float(u.x & 0xffff0000u);
+  r.z = __uint_as_float(u.y << 16);
+  r.w = __uint_as_float(u.y & 0xffff0000u);
+  return r;
+}
+
+// activations written by other CTAs: L2 only (never a stale L1 line)
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float ldcg1(const float* p) { return __ldcg(p); }
+
+// team barrier: monotonically increasing arrival counter, host zeroes it before each launch
+__device__ __forceinline__ void team_barrier(unsigned* counter, unsigned P, unsigned& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += 1;
+    const unsigned target = epoch * P;
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// warp GEMV tile: out[r][u] = sum_k W[row_r][k] * act[u][k]
+// lanes split K (4 consecutive k per lane per 128-k chunk), FFMA2 accumulation,
+// butterfly reduction: every lane ends with all TR*TU totals.
+// ---------------------------------------------------------------------------
+template <int TR, int TU, typename WT>
+__device__ __forceinline__ void warp_rows(const WT* const (&wrow)[TR], const float* __restrict__ act, int lda,
+                                          int K, int lane, float (&out)[TR][TU]) {
+  float2 acc[TR][TU];
+#pragma unroll
+  for (int r = 0; r < TR; ++r)
+#pragma unroll
+    for (int u = 0; u < TU; ++u) acc[r][u] = make_float2(0.f, 0.f);
+
+#pragma unroll 2
+  for (int k = lane * 4; k < K; k += 128) {
+    float4 w[TR];
+#pragma unroll
+    for (int r = 0; r < TR; ++r) w[r] = ldw4(wrow[r] + k);
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      const float4 x = *reinterpret_cast<const float4*>(act + (size_t)u * lda + k);
+#pragma unroll
+      for (int r = 0; r < TR; ++r) {
+        acc[r][u] = __ffma2_rn(make_float2(w[r].x, w[r].y), make_float2(x.x, x.y), acc[r][u]);
+        acc[r][u] = __ffma2_rn(make_float2(w[r].z, w[r].w), make_float2(x.z, x.w), acc[r][u]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < TR; ++r)
+#pragma unroll
+    for (int u = 0; u < TU; ++u) out[r][u] = warp_sum(acc[r][u].x + acc[r][u].y);
+}
+
+// pick element [i] of a register array with a runtime index without spilling
+template <int N>
+__device__ __forceinline__ float pick(const float (&a)[N], int i) {
+  float v = a[0];
+#pragma unroll
+  for (int j = 1; j < N; ++j) v = (i == j) ? a[j] : v;
+  return v;
+}
+template <int TR, int TU>
+__device__ __forceinline__ float pick2(const float (&a)[TR][TU], int r, int u) {
+  float v = a[0][0];
+#pragma unroll
+  for (int i = 0; i < TR; ++i)
+#pragma unroll
+    for (int j = 0; j < TU; ++j) v = (i == r && j == u) ? a[i][j] : v;
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// activation staging: global [nb][K] -> smem, optionally RMS-normalised
+// (nn/blocks.py:32-37: y = (x * rsqrt(mean(x^2) + eps)) * w, two roundings)
+// one warp per utterance row
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int ld_src, int nb, int K,
+                                           float* __restrict__ dst, const float* __restrict__ norm_w,
+                                           float* __restrict__ raw_copy) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int u = warp; u < nb; u += kWarps) {
+    const float* s = src + (size_t)u * ld_src;
+    float* d = dst + (size_t)u * K;
+    float ss = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 v = ldcg4(s + k);
+      *reinterpret_cast<float4*>(d + k) = v;
+      if (raw_copy) *reinterpret_cast<float4*>(raw_copy + (size_t)u * K + k) = v;
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    if (norm_w) {
+      ss = warp_sum(ss);
+      const float inv = 1.0f / sqrtf(ss / (float)K + 1e-6f);
+      for (int k = lane * 4; k < K; k += 128) {
+        float4 v = *reinterpret_cast<float4*>(d + k);
+        const float4 w = __ldg(reinterpret_cast<const float4*>(norm_w + k));
+        v.x = (v.x * inv) * w.x;
+        v.y = (v.y * inv) * w.y;
+        v.z = (v.z * inv) * w.z;
+        v.w = (v.w * inv) * w.w;
+        *reinterpret_cast<float4*>(d + k) = v;
+      }
+    }
+  }
+}
+
+// in-place RMSNorm of smem rows that were produced locally (layer 0: x = cond + emb)
+__device__ __forceinline__ void norm_rows_inplace(float* __restrict__ buf, int nb, int K,
+                                                  const float* __restrict__ norm_w) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int u = warp; u < nb; u += kWarps) {
+    float* d = buf + (size_t)u * K;
+    float ss = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 v = *reinterpret_cast<float4*>(d + k);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / sqrtf(ss / (float)K + 1e-6f);
+    for (int k = lane * 4; k < K; k += 128) {
+      float4 v = *reinterpret_cast<float4*>(d + k);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(norm_w + k));
+      v.x = (v.x * inv) * w.x;
+      v.y = (v.y * inv) * w.y;
+      v.z = (v.z * inv) * w.z;
+      v.w = (v.w * inv) * w.w;
+      *reinterpret_cast<float4*>(d + k) = v;
+    }
+  }
+}
+
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// Row partition of N outputs over the team's P CTAs.
+__device__ __forceinline__ void slice(int N, int rank, int P, int& lo, int& hi) {
+  lo = (int)(((long long)N * rank) / P);
+  hi = (int)(((long long)N * (rank + 1)) / P);
+}
+
+struct TeamCtx {
+  int team, rank, P;
+  int b0, nb;  // utterances [b0, b0+nb)
+};
+
+// ---------------------------------------------------------------------------
+// Stage 1 of a block: h = GLU(RMSNorm(x)); ring push; y = dwconv taps; x' = x + y
+// (nn/blocks.py:156-160, 92-106).  xraw/act: smem [nb][D].
+// ---------------------------------------------------------------------------
+template <int TU, typename WT>
+__device__ __forceinline__ void stage_glu_conv(const ArParams& p, const LayerDev& L, const TeamCtx& tc, int t,
+                                               const float* __restrict__ act, const float* __restrict__ xraw,
+                                               float* __restrict__ xout) {
+  const int D = p.D, Kc = p.Kc;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int c0, c1;
+  slice(D, tc.rank, tc.P, c0, c1);
+  const int n_ut = (tc.nb + TU - 1) / TU;
+  const int n_task = (c1 - c0) * n_ut;
+  const WT* W = reinterpret_cast<const WT*>(L.glu_w);
+  float* ring = p.ring + L.ring_off;
+  const int RL = L.ring_len;
+  for (int task = warp; task < n_task; task += kWarps) {
+    const int c = c0 + task / n_ut;
+    const int u0 = (task % n_ut) * TU;
+    const WT* rows[2] = {W + (size_t)c * D, W + (size_t)(c + D) * D};
+    // clamp the utterance tile to valid smem rows (results of clamped rows are dropped)
+    const int ub = min(u0, max(tc.nb - TU, 0));
+    float out[2][TU];
+    warp_rows<2, TU, WT>(rows, act + (size_t)ub * D, D, D, lane, out);
+    const int u = ub + lane;  // lane < TU handles utterance u
+    if (lane < TU && u >= u0 && u < tc.nb) {
+      const float a = pick2<2, TU>(out, 0, lane) + __ldg(L.glu_b + c);
+      const float gt = pick2<2, TU>(out, 1, lane) + __ldg(L.glu_b + c + D);
+      const float h = a * sigmoid_ref(gt);
+      const int b = tc.b0 + u;
+      float* rb = ring + ((size_t)b * RL) * D + c;
+      // slot of frame tau is tau mod RL; frames before 0 are the zero-initialised ring
+      const int slot_now = t % RL;
+      rb[(size_t)slot_now * D] = h;
+      const float* wt = L.dw_w + (size_t)c * Kc;
+      float y = 0.f;
+      for (int j = 0; j < Kc - 1; ++j) {
+        const int tau = t - (Kc - 1 - j) * L.dil;
+        int sl = tau % RL;
+        if (sl < 0) sl += RL;
+        const float tap = rb[(size_t)sl * D];  // own writes only: plain load
+        y += tap * __ldg(wt + j);
+      }
+      y += h * __ldg(wt + Kc - 1);
+      y += __ldg(L.dw_b + c);
+      xout[(size_t)b * D + c] = xraw[(size_t)u * D + c] + y;
+    }
+  }
+}
+
+// generic epilogue kinds
+enum { EPI_FFN1 = 0, EPI_FFN2 = 1, EPI_Q = 2, EPI_O = 3, EPI_HEAD = 4 };
+
+// out-feature rows [n0,n1) of a [N][K] matrix times the staged activations.
+template <int EPI, int TU, typename WT>
+__device__ __forceinline__ void stage_rows_gemv(const ArParams& p, const TeamCtx& tc, const void* Wv, int N, int K,
+                                                const float* __restrict__ bias, const float* __restrict__ act,
+                                                float* __restrict__ dst, int ld_dst, float scale,
+                                                float* __restrict__ trace) {
+  constexpr int TR = 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int n0, n1;
+  slice(N, tc.rank, tc.P, n0, n1);
+  const int n_rt = (n1 - n0 + TR - 1) / TR;
+  const int n_ut = (tc.nb + TU - 1) / TU;
+  const WT* W = reinterpret_cast<const WT*>(Wv);
+  for (int task = warp; task < n_rt * n_ut; task += kWarps) {
+    const int r0 = n0 + (task / n_ut) * TR;
+    const int u0 = (task % n_ut) * TU;
+    const WT* rows[TR];
+#pragma unroll
+    for (int i = 0; i < TR; ++i) rows[i] = W + (size_t)min(r0 + i, n1 - 1) * K;
+    const int ub = min(u0, max(tc.nb - TU, 0));
+    float out[TR][TU];
+    warp_rows<TR, TU, WT>(rows, act + (size_t)ub * K, K, K, lane, out);
+    const int i = lane / TU, uu = lane % TU;
+    const int r = r0 + i, u = ub + uu;
+    if (lane < TR * TU && r < n1 && u >= u0 && u < tc.nb) {
+      float v = pick2<TR, TU>(out, i, uu);
+      const int b = tc.b0 + u;
+      float* d = dst + (size_t)b * ld_dst + r;
+      if (EPI == EPI_FFN1) {
+        *d = gelu_erf(v + __ldg(bias + r));
+      } else if (EPI == EPI_FFN2) {
+        const float nv = ldcg1(d) + (v + __ldg(bias + r));
+        *d = nv;
+        if (trace) trace[(size_t)b * ld_dst + r] = nv;
+      } else if (EPI == EPI_Q) {
+        *d = v;
+      } else if (EPI == EPI_O) {
+        const float nv = ldcg1(d) + scale * v;
+        *d = nv;
+        if (trace) trace[(size_t)b * ld_dst + r] = nv;
+      } else {  // EPI_HEAD
+        v += __ldg(bias + r);
+        *d = v;
+        if (trace) trace[(size_t)b * p.V + r] = v;
+      }
+    }
+  }
+}
+
+// dispatch on the utterance-tile width
+template <int EPI, typename WT>
+__device__ __forceinline__ void gemv_dispatch(const ArParams& p, const TeamCtx& tc, const void* W, int N, int K,
+                                              const float* bias, const float* act, float* dst, int ld_dst,
+                                              float scale, float* trace) {
+  if (tc.nb >= 8)
+    stage_rows_gemv<EPI, 8, WT>(p, tc, W, N, K, bias, act, dst, ld_dst, scale, trace);
+  else if (tc.nb >= 4)
+    stage_rows_gemv<EPI, 4, WT>(p, tc, W, N, K, bias, act, dst, ld_dst, scale, trace);
+  else if (tc.nb >= 2)
+    stage_rows_gemv<EPI, 2, WT>(p, tc, W, N, K, bias, act, dst, ld_dst, scale, trace);
+  else
+    stage_rows_gemv<EPI, 1, WT>(p, tc, W, N, K, bias, act, dst, ld_dst, scale, trace);
+}
+
+// ---------------------------------------------------------------------------
+// Cached text cross-attention core (nn/text.py:101-128): one warp per
+// (utterance, head).  scores in smem (per-warp slice of Lmax floats).
+// softmax(q.K^T / sqrt(Dh)) . V, fp32, keys l < text_len only.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void stage_attention(const ArParams& p, const LayerDev& L, const TeamCtx& tc,
+                                                float* __restrict__ smem_scores) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int H = p.H, Dh = p.Dh, D = p.D, Lmax = p.Lmax;
+  float* sc = smem_scores + (size_t)warp * (Lmax + Dh);
+  float* qs = sc + Lmax;
+  const float scale = 1.0f / sqrtf((float)Dh);
+  const int n_items = tc.nb * H;
+  for (int item = tc.rank * kWarps + warp; item < n_items; item += tc.P * kWarps) {
+    const int u = item / H, h = item % H;
+    const int b = tc.b0 + u;
+    const int len = p.text_len[b];
+    const float* q = p.qbuf + (size_t)b * D + (size_t)h * Dh;
+    const size_t kv_off = ((((size_t)L.attn_slot * p.B + b) * H + h) * Lmax) * Dh;
+    const float* Kp = p.kc + kv_off;
+    const float* Vp = p.vc + kv_off;
+    for (int d = lane; d < Dh; d += 32) qs[d] = ldcg1(q + d);
+    __syncwarp();
+    // scores: lane handles keys lane, lane+32, ...
+    float mx = -INFINITY;
+    for (int l = lane; l < len; l += 32) {
+      const float* kr = Kp + (size_t)l * Dh;
+      float s = 0.f;
+      for (int d = 0; d < Dh; d += 4) {
+        const float4 kk = __ldg(reinterpret_cast<const float4*>(kr + d));
+        const float4 qq = *reinterpret_cast<const float4*>(qs + d);
+        s += kk.x * qq.x + kk.y * qq.y + kk.z * qq.z + kk.w * qq.w;
+      }
+      s *= scale;
+      sc[l] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int l = lane; l < len; l += 32) {
+      const float e = expf(sc[l] - mx);
+      sc[l] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    // out[d] = sum_l p_l V[l][d] / sum ; lane handles d = lane, lane+32, ...
+    for (int d = lane; d < Dh; d += 32) {
+      float o = 0.f;
+      for (int l = 0; l < len; ++l) o += sc[l] * __ldg(Vp + (size_t)l * Dh + d);
+      o = o / sum;
+      if (!isfinite(o)) o = 0.f;  // nan_to_num(nan=0, posinf=0, neginf=0), nn/text.py:128
+      p.abuf[(size_t)b * D + (size_t)h * Dh + d] = o;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Sampler (sampling.py:24-93) + bookkeeping (model.py:293-305), one CTA per utterance.
+// ---------------------------------------------------------------------------
+struct SamplerSmem {
+  float red_v[kWarps];
+  int red_i[kWarps];
+  float topv[kMaxTopK];
+  int topi[kMaxTopK];
+  float bc_f;
+  int bc_i;
+  int fallback;
+};
+
+__device__ __forceinline__ void argmax_pair(float& v, int& i, float ov, int oi) {
+  // larger value wins; ties -> lower index (torch.argmax / topk / sort keep the first)
+  if (ov > v || (ov == v && oi < i)) {
+    v = ov;
+    i = oi;
+  }
+}
+__device__ __forceinline__ void warp_argmax(float& v, int& i) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+    argmax_pair(v, i, ov, oi);
+  }
+}
+
+// block-wide argmax; result valid in every thread
+__device__ __forceinline__ void block_argmax(float& v, int& i, SamplerSmem& sm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  warp_argmax(v, i);
+  if (lane == 0) {
+    sm.red_v[warp] = v;
+    sm.red_i[warp] = i;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float bv = lane < kWarps ? sm.red_v[lane] : -INFINITY;
+    int bi = lane < kWarps ? sm.red_i[lane] : 0x7fffffff;
+    warp_argmax(bv, bi);
+    if (lane == 0) {
+      sm.bc_f = bv;
+      sm.bc_i = bi;
+    }
+  }
+  __syncthreads();
+  v = sm.bc_f;
+  i = sm.bc_i;
+}
+
+__device__ __forceinline__ float block_max(float v, SamplerSmem& sm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_max(v);
+  if (lane == 0) sm.red_v[warp] = v;
+  __syncthreads();
+  float r = lane < kWarps ? sm.red_v[lane] : -INFINITY;
+  r = warp_max(r);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, SamplerSmem& sm) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_sum(v);
+  if (lane == 0) sm.red_v[warp] = v;
+  __syncthreads();
+  float r = lane < kWarps ? sm.red_v[lane] : 0.f;
+  r = warp_sum(r);
+  __syncthreads();
+  return r;
+}
+
+// sx: smem [Vpad] floats, flags: smem [Vpad] bytes
+__device__ __forceinline__ void sample_utterance(const ArParams& p, int b, int t, float* __restrict__ sx,
+                                                 unsigned char* __restrict__ flags, SamplerSmem& sm) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int V = p.V;
+  UttState st = p.st[b];
+  const SamplingDev sp = p.samp[b];
+  if (st.done) return;  // CTA-uniform
+  const float top_p = st.recovery ? sp.rec_top_p : sp.top_p;
+  const float temp = st.recovery ? sp.rec_temp : sp.temperature;
+  const float rep = sp.rep_pen;
+  const int* hist = p.tokens + (size_t)b * p.steps;
+  const int hlen = st.len;
+
+  // 1. logits -> nan_to_num -> /T ; repetition-penalty flags from set(hist[-50:])
+  for (int v = tid; v < p.Vpad; v += kThreads) flags[v] = 0;
+  __syncthreads();
+  if (rep != 1.0f && tid < 50 && tid < hlen) {
+    const int tok = hist[hlen - 1 - tid];
+    if (tok >= 0 && tok < V) flags[tok] = 1;
+  }
+  __syncthreads();
+  const float* lg = p.logits + (size_t)b * p.Vpad;
+  float xv[kSampNPT];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kSampNPT; ++i) {
+    const int v = tid + i * kThreads;
+    float x = -INFINITY;
+    if (v < V) {
+      x = ldcg1(lg + v);
+      if (isnan(x)) x = -1e9f;
+      else if (isinf(x)) x = x > 0.f ? 1e9f : -1e9f;
+      if (temp != 0.0f && temp != 1.0f) x = x / temp;
+      if (flags[v]) x = (x < 0.f) ? x * rep : x / rep;
+      sx[v] = x;
+      mx = fmaxf(mx, x);
+    }
+    xv[i] = x;
+  }
+  // 2. softmax + nan_to_num
+  mx = block_max(mx, sm);
+  float pv[kSampNPT];
+  float se = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSampNPT; ++i) {
+    const int v = tid + i * kThreads;
+    pv[i] = (v < V) ? expf(xv[i] - mx) : 0.f;
+    se += pv[i];
+  }
+  se = block_sum(se, sm);
+#pragma unroll
+  for (int i = 0; i < kSampNPT; ++i) {
+    const int v = tid + i * kThreads;
+    float q = pv[i] / se;
+    if (!isfinite(q)) q = 0.f;
+    pv[i] = (v < V) ? q : -1.f;  // -1 = not a candidate
+  }
+  // 3. top-k: kk passes of block argmax over the remaining candidates, value desc, index asc
+  const int kk = min(min(sp.top_k, V), kMaxTopK);
+  for (int j = 0; j < kk; ++j) {
+    float bv = -1.f;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kSampNPT; ++i) {
+      if (pv[i] > bv) {
+        bv = pv[i];
+        bi = tid + i * kThreads;
+      }
+    }
+    block_argmax(bv, bi, sm);
+    if (tid == 0) {
+      sm.topv[j] = bv;
+      sm.topi[j] = bi;
+    }
+    if ((bi % kThreads) == tid) {
+      const int slot = bi / kThreads;
+#pragma unroll
+      for (int i = 0; i < kSampNPT; ++i)
+        if (i == slot) pv[i] = -1.f;
+    }
+  }
+  __syncthreads();
+  // 4. renormalise, top-p, draw: warp 0, two candidates per lane (j = lane, lane + 32)
+  if (warp == 0) {
+    const int j0 = lane, j1 = lane + 32;
+    float a0 = j0 < kk ? sm.topv[j0] : 0.f;
+    float a1 = j1 < kk ? sm.topv[j1] : 0.f;
+    const int i0 = j0 < kk ? sm.topi[j0] : 0x7fffffff;
+    const int i1 = j1 < kk ? sm.topi[j1] : 0x7fffffff;
+    const float s1 = (float)warp_sum_d((double)a0 + (double)a1);
+    int fallback = 0;
+    int token = 0;
+    if (s1 <= 1e-12f) {
+      fallback = 1;
+    } else {
+      a0 = a0 / s1;
+      a1 = a1 / s1;
+      const float* nz = p.noise + ((size_t)b * p.steps + t) * p.noise_k;
+      float r0 = 0.f, r1 = 0.f;
+      int t0 = 0x7fffffff, t1 = 0x7fffffff;  // tie-break keys
+      if (top_p < 1.0f) {
+        // cumsum in double, rounded to float at each position (ATen CPU cumsum accumulates in
+        // acc_type<float> = double); inclusive scan over lanes, first the low 32, then the high 32
+        double c0 = (double)a0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double n = __shfl_up_sync(0xffffffffu, c0, o);
+          if (lane >= o) c0 += n;
+        }
+        const double tot0 = __shfl_sync(0xffffffffu, c0, 31);
+        double c1 = (double)a1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double n = __shfl_up_sync(0xffffffffu, c1, o);
+          if (lane >= o) c1 += n;
+        }
+        c1 += tot0;
+        const float cf0 = (float)c0, cf1 = (float)c1;
+        // remove[j] = cum[j-1] > top_p, remove[0] = False (sampling.py:72-74)
+        float prev0 = __shfl_up_sync(0xffffffffu, cf0, 1);
+        float prev1 = __shfl_up_sync(0xffffffffu, cf1, 1);
+        const float last0 = __shfl_sync(0xffffffffu, cf0, 31);
+        if (lane == 0) prev1 = last0;
+        const bool keep0 = (lane == 0) || !(prev0 > top_p);
+        const bool keep1 = !(prev1 > top_p);
+        a0 = (j0 < kk && keep0) ? a0 : 0.f;
+        a1 = (j1 < kk && keep1) ? a1 : 0.f;
+        const float s2 = (float)warp_sum_d((double)a0 + (double)a1);
+        if (s2 <= 1e-12f) {
+          fallback = 1;
+        } else {
+          a0 = a0 / s2;
+          a1 = a1 / s2;
+          // multinomial == argmax(p_sorted[j] / q[j]), noise index = sorted rank (sampling.py:83-84)
+          r0 = j0 < kk ? a0 / __ldg(nz + j0) : 0.f;
+          r1 = j1 < kk ? a1 / __ldg(nz + j1) : 0.f;
+          t0 = j0;
+          t1 = j1;
+        }
+      } else {
+        // no top-p: probs stay in vocabulary order, noise index = token id (sampling.py:88-93)
+        const float s2 = (float)warp_sum_d((double)a0 + (double)a1);
+        if (s2 <= 1e-12f) {
+          fallback = 1;
+        } else {
+          a0 = a0 / s2;
+          a1 = a1 / s2;
+          r0 = j0 < kk ? a0 / __ldg(nz + i0) : 0.f;
+          r1 = j1 < kk ? a1 / __ldg(nz + i1) : 0.f;
+          t0 = i0;
+          t1 = i1;
+        }
+      }
+      if (!fallback) {
+        float bv = r0;
+        int bk = t0, bt = i0;
+        if (j1 < kk && (r1 > bv || (r1 == bv && t1 < bk))) {
+          bv = r1;
+          bk = t1;
+          bt = i1;
+        }
+        if (j0 >= kk) {
+          bv = -1.f;
+          bk = 0x7fffffff;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
+          const int ot = __shfl_xor_sync(0xffffffffu, bt, o);
+          if (ov > bv || (ov == bv && ok < bk)) {
+            bv = ov;
+            bk = ok;
+            bt = ot;
+          }
+        }
+        token = bt;
+      }
+    }
+    if (lane == 0) {
+      sm.fallback = fallback;
+      sm.bc_i = token;
+    }
+  }
+  __syncthreads();
+  int token = sm.bc_i;
+  if (sm.fallback) {
+    // argmax of the penalised, temperature-scaled logits (sampling.py:65,80,90)
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int i = 0; i < kSampNPT; ++i) {
+      const int v = tid + i * kThreads;
+      if (v < V) argmax_pair(bv, bi, xv[i], v);
+    }
+    __syncthreads();
+    block_argmax(bv, bi, sm);
+    token = bi;
+  }
+  // 5. bookkeeping: one warp (repeated_tail needs lanes 3..16)
+  if (warp == 0) {
+    int* toks = p.tokens + (size_t)b * p.steps;
+    if (lane == 0) p.sampled[(size_t)b * p.steps + t] = token;
+    if (p.forced) token = p.forced[(size_t)b * p.steps + t];
+    if (lane == 0) toks[t] = token;
+    __syncwarp();
+    const int len = hlen + 1;  // == t + 1
+    // repeated_tail(hist, 16): any n in [3, min(16, len/2)] with hist[-n:] == hist[-2n:-n]
+    bool rep_n = false;
+    {
+      const int n = lane;
+      if (n >= 3 && n <= 16 && n <= len / 2) {
+        rep_n = true;
+        for (int i = 0; i < n; ++i) {
+          const int a = (len - n + i == t) ? token : toks[len - n + i];
+          const int c = toks[len - 2 * n + i];
+          if (a != c) {
+            rep_n = false;
+            break;
+          }
+        }
+      }
+    }
+    const bool any_rep = __any_sync(0xffffffffu, rep_n);
+    if (lane == 0) {
+      const int streak = (st.last >= 0 && token == st.last) ? st.streak + 1 : 0;
+      int recovery = 0;
+      if (sp.anti_loop && (any_rep || streak >= sp.loop_streak)) recovery = 1;
+      const bool is_eos = token == p.eos_id;
+      int done = 0;
+      if (is_eos && (sp.stop_on_first_eos || len >= sp.min_gen)) done = 1;
+      if (len >= p.steps) done = 1;
+      UttState ns;
+      ns.len = len;
+      ns.last = token;
+      ns.streak = streak;
+      ns.recovery = recovery;
+      ns.done = done;
+      ns.pad[0] = ns.pad[1] = ns.pad[2] = 0;
+      p.st[b] = ns;
+      p.n_tokens[b] = len;
+      p.done[b] = done;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the persistent kernel
+// ---------------------------------------------------------------------------
+template <int TU, typename WT>
+__device__ __forceinline__ void glu_dispatch_one(const ArParams& p, const LayerDev& L, const TeamCtx& tc, int t,
+                                                 const float* act, const float* xraw, float* xout) {
+  stage_glu_conv<TU, WT>(p, L, tc, t, act, xraw, xout);
+}
+
+template <typename WT>
+__global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid_constant__ ArParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ SamplerSmem ssm;
+  float* act = reinterpret_cast<float*>(smem_raw);  // [nb][max(D,F)] (or 2 x [nb][D])
+  TeamCtx tc;
+  tc.team = blockIdx.x / p.P;
+  tc.rank = blockIdx.x % p.P;
+  tc.P = p.P;
+  if (tc.team >= p.g) return;
+  tc.b0 = tc.team * p.Bt;
+  tc.nb = min(p.Bt, p.B - tc.b0);
+  if (tc.nb <= 0) return;
+  unsigned* bar = p.barrier + (size_t)tc.team * 32;
+  unsigned epoch = 0;
+  const int D = p.D, F = p.F;
+  float* xraw = act + (size_t)tc.nb * D;  // second [nb][D] buffer (stage 1 only)
+
+  for (int t = p.t_begin; t < p.t_end; ++t) {
+    // team-uniform early exit: all utterances of the team finished
+    {
+      int live = 0;
+      for (int u = 0; u < tc.nb; ++u) live |= (__ldcg(&p.st[tc.b0 + u].done) == 0);
+      if (!live) break;
+    }
+    float* cur = p.xa;
+    float* nxt = p.xb;
+    for (int li = 0; li < p.n_layers; ++li) {
+      const LayerDev& L = p.layer[li];
+      // ---- stage 1: x (or cond+emb) -> RMSNorm -> GLU -> ring/dwconv -> nxt
+      if (li == 0) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int u = warp; u < tc.nb; u += kWarps) {
+          const int b = tc.b0 + u;
+          const int row = (t == 0) ? p.V : __ldcg(&p.tokens[(size_t)b * p.steps + t - 1]);
+          const float* cr = p.cond + ((size_t)b * p.steps + t) * D;
+          const float* er = p.emb + (size_t)row * D;
+          for (int k = lane * 4; k < D; k += 128) {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(cr + k));
+            const float4 e = __ldg(reinterpret_cast<const float4*>(er + k));
+            const float4 x = make_float4(c.x + e.x, c.y + e.y, c.z + e.z, c.w + e.w);
+            *reinterpret_cast<float4*>(act + (size_t)u * D + k) = x;
+            *reinterpret_cast<float4*>(xraw + (size_t)u * D + k) = x;
+          }
+        }
+        __syncthreads();
+        norm_rows_inplace(act, tc.nb, D, L.norm_w);
+      } else {
+        stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, L.norm_w, xraw);
+      }
+      __syncthreads();
+      if (tc.nb >= 8)
+        stage_glu_conv<8, WT>(p, L, tc, t, act, xraw, nxt);
+      else if (tc.nb >= 4)
+        stage_glu_conv<4, WT>(p, L, tc, t, act, xraw, nxt);
+      else if (tc.nb >= 2)
+        stage_glu_conv<2, WT>(p, L, tc, t, act, xraw, nxt);
+      else
+        stage_glu_conv<1, WT>(p, L, tc, t, act, xraw, nxt);
+      {
+        float* tmp = cur;
+        cur = nxt;
+        nxt = tmp;
+      }
+      team_barrier(bar, tc.P, epoch);
+      // ---- stage 2: FFN up + GELU
+      stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, L.ffn_norm_w, nullptr);
+      __syncthreads();
+      gemv_dispatch<EPI_FFN1, WT>(p, tc, L.w1, F, D, L.b1, act, p.hbuf, F, 0.f, nullptr);
+      team_barrier(bar, tc.P, epoch);
+      // ---- stage 3: FFN down + residual (in place on this CTA's slice of cur)
+      stage_rows(p.hbuf + (size_t)tc.b0 * F, F, tc.nb, F, act, nullptr, nullptr);
+      __syncthreads();
+      {
+        float* tr = (p.trace_blocks && !L.has_attn)
+                        ? p.trace_blocks + (((size_t)t * p.n_layers + li) * p.B) * D
+                        : nullptr;
+        gemv_dispatch<EPI_FFN2, WT>(p, tc, L.w2, D, F, L.b2, act, cur, D, 0.f, tr);
+      }
+      team_barrier(bar, tc.P, epoch);
+      if (L.has_attn) {
+        // ---- q projection
+        stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, L.nq_w, nullptr);
+        __syncthreads();
+        gemv_dispatch<EPI_Q, WT>(p, tc, L.wq, D, D, nullptr, act, p.qbuf, D, 0.f, nullptr);
+        team_barrier(bar, tc.P, epoch);
+        // ---- attention core
+        stage_attention(p, L, tc, act);
+        team_barrier(bar, tc.P, epoch);
+        // ---- out projection + gated residual
+        stage_rows(p.abuf + (size_t)tc.b0 * D, D, tc.nb, D, act, nullptr, nullptr);
+        __syncthreads();
+        {
+          float* tr = p.trace_blocks ? p.trace_blocks + (((size_t)t * p.n_layers + li) * p.B) * D : nullptr;
+          gemv_dispatch<EPI_O, WT>(p, tc, L.wo, D, D, nullptr, act, cur, D, L.gate_tanh, tr);
+        }
+        team_barrier(bar, tc.P, epoch);
+      }
+    }
+    // ---- head
+    stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, p.final_norm_w, nullptr);
+    __syncthreads();
+    {
+      float* tr = p.trace_logits ? p.trace_logits + ((size_t)t * p.B) * p.V : nullptr;
+      gemv_dispatch<EPI_HEAD, WT>(p, tc, p.head_w, p.V, D, p.head_b, act, p.logits, p.Vpad, 0.f, tr);
+    }
+    team_barrier(bar, tc.P, epoch);
+    // ---- sampler: utterances round-robin over the team's CTAs
+    {
+      float* sx = act;
+      unsigned char* flags = reinterpret_cast<unsigned char*>(act + p.Vpad);
+      for (int u = tc.rank; u < tc.nb; u += tc.P) {
+        sample_utterance(p, tc.b0 + u, t, sx, flags, ssm);
+        __syncthreads();
+      }
+    }
+    team_barrier(bar, tc.P, epoch);
+    // x ping-pong parity: after an even number of swaps per step cur == xa again only if
+    // n_layers is even; keep it simple and copy nothing: the next step's layer 0 reads
+    // cond/emb, never cur.
+  }
+}
+
+// ---------------------------------------------------------------------------
+// text K/V cache builder (nn/text.py:75-83): K,V = W . RMSNorm_kv(txt) -> [slot][B][H][Lmax][Dh]
+// grid = (ceil(Lmax/16), B, n_attn)
+// ---------------------------------------------------------------------------
+struct KvParams {
+  int D, H, Dh, B, Lmax, text_stride, n_attn;
+  const float* txt;      // [B][text_stride][D]
+  const int* text_len;
+  const float* nkv_w[kMaxLayers];
+  const void* wk[kMaxLayers];
+  const void* wv[kMaxLayers];
+  float* kc;
+  float* vc;
+};
+
+template <typename WT>
+__global__ void __launch_bounds__(kThreads, 1) kv_build_kernel(const __grid_constant__ KvParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* act = reinterpret_cast<float*>(smem_raw);  // [16][D]
+  constexpr int TL = 16, TU = 8, TR = 2;
+  const int l0 = blockIdx.x * TL, b = blockIdx.y, slot = blockIdx.z;
+  const int len = p.text_len[b];
+  if (l0 >= len) return;
+  const int nl = min(TL, len - l0);
+  const int D = p.D;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // positions beyond nl: fill with zeros so the tiles stay in-bounds
+  for (int i = threadIdx.x; i < TL * D; i += kThreads) act[i] = 0.f;
+  __syncthreads();
+  stage_rows(p.txt + ((size_t)b * p.text_stride + l0) * D, D, nl, D, act, p.nkv_w[slot], nullptr);
+  __syncthreads();
+  const WT* Wk = reinterpret_cast<const WT*>(p.wk[slot]);
+  const WT* Wv = reinterpret_cast<const WT*>(p.wv[slot]);
+  const int n_rt = (2 * D) / TR, n_ut = TL / TU;
+  for (int task = warp; task < n_rt * n_ut; task += kWarps) {
+    const int r0 = (task / n_ut) * TR, u0 = (task % n_ut) * TU;
+    if (u0 >= nl) continue;
+    const WT* rows[TR];
+#pragma unroll
+    for (int i = 0; i < TR; ++i) {
+      const int r = r0 + i;
+      rows[i] = (r < D) ? Wk + (size_t)r * D : Wv + (size_t)(r - D) * D;
+    }
+    float out[TR][TU];
+    warp_rows<TR, TU, WT>(rows, act + (size_t)u0 * D, D, D, lane, out);
+    const int i = lane / TU, uu = lane % TU;
+    const int r = r0 + i, l = u0 + uu;
+    if (lane < TR * TU && l < nl) {
+      const float v = pick2<TR, TU>(out, i, uu);
+      const int rr = r < D ? r : r - D;
+      const int h = rr / p.Dh, dh = rr % p.Dh;
+      float* dst = (r < D ? p.kc : p.vc) + ((((size_t)slot * p.B + b) * p.H + h) * p.Lmax + (l0 + l)) * p.Dh + dh;
+      *dst = v;
+    }
+  }
+}
+
+}  // namespace sopro

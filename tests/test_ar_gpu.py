@@ -1,0 +1,205 @@
+"""GPU parity tests of the persistent AR kernel, through the C-ABI, against
+(a) the golden fixtures written from the reference and (b) the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ar_oracle as O
+from tests.cases import AR_CASES, _unit, ar_case_inputs, ar_weights
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+torch.set_grad_enabled(False)
+
+_ENGINES = {}
+
+
+def _engine(cfg, sd, wdtype, key):
+    from sopro_b200.engine import ArEngine
+
+    k = (key, wdtype)
+    if k not in _ENGINES:
+        _ENGINES[k] = ArEngine(cfg, sd, device=0, weight_dtype=wdtype)
+    return _ENGINES[k]
+
+
+def _wkey(spec):
+    return (str(sorted(spec["cfg"].items())), spec["head_gain"], spec["bf16"], spec.get("eos_bias", 0.0))
+
+
+def _sampling(samp, cfg, **over):
+    from sopro_b200.engine import Sampling
+
+    mg = samp.min_gen_frames if samp.min_gen_frames is not None else cfg.min_gen_frames
+    d = dict(top_p=samp.top_p, temperature=samp.temperature, recovery_top_p=samp.recovery_top_p,
+             recovery_temp=samp.recovery_temp, repetition_penalty=samp.repetition_penalty, top_k=samp.top_k,
+             anti_loop=samp.anti_loop, loop_streak=samp.loop_streak, min_gen_frames=int(min(mg, 2 ** 31 - 1)),
+             stop_on_first_eos=False)
+    d.update(over)
+    return Sampling(**d)
+
+
+def _case(name):
+    spec = AR_CASES[name]
+    cfg, sd, inp = ar_case_inputs(spec)
+    g = np.load(os.path.join(GOLD, f"ar_{name}.npz"))
+    eng = _engine(cfg, sd, "bf16" if spec["bf16"] else "fp32", _wkey(spec))
+    steps = inp["max_frames"] + 1
+    tape = O.noise_tape(spec["noise_seed"], steps, cfg.ar_vocab())[:, :50].contiguous()
+    return spec, cfg, sd, inp, g, eng, steps, tape
+
+
+def _run_case(name, **samp_over):
+    spec, cfg, sd, inp, g, eng, steps, tape = _case(name)
+    ses = eng.session(1, steps, inp["txt_seq"].shape[1])
+    ses.begin(inp["cond_ar"], inp["txt_seq"], [inp["txt_seq"].shape[1]], tape.unsqueeze(0), _sampling(inp["sampling"], cfg, **samp_over))
+    ses.run()
+    toks, n, done = ses.read()
+    return toks[0, : n[0]].tolist(), g, ses
+
+
+@pytest.mark.parametrize("name", list(AR_CASES))
+def test_free_running_tokens_match_reference(name):
+    """Sampled ids are bit-identical to the reference's ar_stream under the same seed."""
+    toks, g, _ = _run_case(name)
+    gold = g["tokens"].tolist()
+    if toks != gold:
+        first = next((i for i, (a, b) in enumerate(zip(toks, gold)) if a != b), min(len(toks), len(gold)))
+        pytest.fail(f"{name}: diverges at step {first}: got {toks[first:first+4]} want {gold[first:first+4]} (len {len(toks)} vs {len(gold)})")
+
+
+@pytest.mark.parametrize("name", ["default_fp32", "default_bf16", "peaked_fp32", "small_fp32"])
+def test_teacher_forced_logits_and_blocks(name):
+    """With the reference's tokens forced, every step's logits and the per-block residual
+    stream match the reference within fp32 round-off (tolerance stated below)."""
+    spec, cfg, sd, inp, g, eng, steps, tape = _case(name)
+    gold = torch.from_numpy(g["tokens"].astype(np.int32))
+    n = gold.numel()
+    forced = torch.zeros(1, steps, dtype=torch.int32)
+    forced[0, :n] = gold
+    dev = eng.device
+    tr_b = torch.zeros(steps, int(cfg.n_layers_ar), 1, int(cfg.d_model), device=dev)
+    tr_l = torch.zeros(steps, 1, cfg.ar_vocab(), device=dev)
+    ses = eng.session(1, steps, inp["txt_seq"].shape[1])
+    ses.set_forced(forced)
+    ses.set_trace(tr_b, tr_l)
+    ses.begin(inp["cond_ar"], inp["txt_seq"], [inp["txt_seq"].shape[1]], tape.unsqueeze(0), _sampling(inp["sampling"], cfg))
+    ses.run()
+    toks, nn, done = ses.read()
+    sampled = ses.sampled().cpu()[0, :n].tolist()
+    torch.cuda.synchronize()
+    # block traces at steps 0 and 1: |err| <= 2e-5 * max|ref| (fp32 accumulation-order noise)
+    bt = g["block_trace"]  # [2, n_layers, D]
+    got = tr_b[:2, :, 0].cpu().numpy()
+    for t in range(2):
+        for i in range(bt.shape[1]):
+            tol = 2e-5 * max(1.0, float(np.abs(bt[t, i]).max()))
+            np.testing.assert_allclose(got[t, i], bt[t, i], rtol=0, atol=tol, err_msg=f"step {t} block {i}")
+    # logits at the fixture's steps
+    lg = tr_l[:, 0].cpu().numpy()
+    for row, t in zip(g["logits"], g["logit_steps"].tolist()):
+        tol = 3e-5 * max(1.0, float(np.abs(row).max()))
+        np.testing.assert_allclose(lg[t], row, rtol=0, atol=tol, err_msg=f"logits step {t}")
+    # the token sampled at every step (given the reference history) is the reference's
+    assert sampled == gold.tolist()
+
+
+def test_kv_cache_matches_oracle():
+    spec, cfg, sd, inp, g, eng, steps, tape = _case("default_fp32")
+    L = inp["txt_seq"].shape[1]
+    ses = eng.session(1, steps, L)
+    ses.begin(inp["cond_ar"], inp["txt_seq"], [L], tape.unsqueeze(0), _sampling(inp["sampling"], cfg))
+    k, v = ses.kv()
+    torch.cuda.synchronize()
+    for slot, li in enumerate(cfg.ar_attn_layers()):
+        ko, vo = O.text_kv_cache(sd, f"ar.x_attns.{li}.", inp["txt_seq"], cfg.AR_HEADS)
+        np.testing.assert_allclose(k[slot, 0, :, :L].cpu().numpy(), ko[0].numpy(), rtol=0, atol=2e-5)
+        np.testing.assert_allclose(v[slot, 0, :, :L].cpu().numpy(), vo[0].numpy(), rtol=0, atol=2e-5)
+
+
+def _batch_inputs(cfg, n, steps, lens):
+    D = int(cfg.d_model)
+    Ls = max(lens)
+    cond = torch.stack([_unit(steps * D, 9000 + i).view(steps, D) for i in range(n)])
+    txt = torch.zeros(n, Ls, D)
+    for i, L in enumerate(lens):
+        txt[i, :L] = _unit(L * D, 9500 + i).view(L, D)
+    tapes = torch.stack([O.noise_tape(100 + i, steps, cfg.ar_vocab()) for i in range(n)])
+    return cond, txt, tapes
+
+
+def _oracle_batch(sd, cfg, cond, txt, tapes, lens, samp, steps):
+    out = []
+    for i, L in enumerate(lens):
+        out.append(O.ar_generate(sd, cfg, cond[i:i + 1], txt[i:i + 1, :L], torch.ones(1, L, dtype=torch.bool),
+                                 max_frames=steps - 1, sampling=samp, noise_tv=tapes[i]))
+    return out
+
+
+@pytest.mark.parametrize("team", [0, 1, 2, 3])
+def test_batch_equals_each_utterance_alone(team):
+    """Utterance i of a ragged batch == the oracle run alone on utterance i,
+    for every team geometry (1 team, several teams, uneven last team)."""
+    spec = AR_CASES["peaked_fp32"]
+    cfg, sd, _ = ar_case_inputs(spec)
+    eng = _engine(cfg, sd, "fp32", _wkey(spec))
+    lens = [52, 7, 23, 33, 1, 12, 5]
+    n, steps = len(lens), 40
+    cond, txt, tapes = _batch_inputs(cfg, n, steps, lens)
+    samp = O.ArSampling(min_gen_frames=10 ** 9)
+    want = _oracle_batch(sd, cfg, cond, txt, tapes, lens, samp, steps)
+    ses = eng.session(n, steps, max(lens))
+    ses.set_team(team)
+    ses.begin(cond, txt, lens, tapes[:, :, :50].contiguous(), _sampling(samp, cfg))
+    ses.run()
+    toks, nn, done = ses.read()
+    for i in range(n):
+        assert toks[i, : nn[i]].tolist() == want[i], f"utterance {i} (L={lens[i]})"
+
+
+def test_resume_in_chunks_equals_one_launch():
+    """Streaming drives the kernel chunk by chunk (stream(): 6 frames); state lives in HBM."""
+    spec, cfg, sd, inp, g, eng, steps, tape = _case("peaked_fp32")
+    L = inp["txt_seq"].shape[1]
+    ses = eng.session(1, steps, L)
+    ses.begin(inp["cond_ar"], inp["txt_seq"], [L], tape.unsqueeze(0), _sampling(inp["sampling"], cfg))
+    while ses.position < steps:
+        ses.run(6)
+    toks, n, done = ses.read()
+    assert toks[0, : n[0]].tolist() == g["tokens"].tolist()
+
+
+def test_host_buffer_path():
+    spec, cfg, sd, inp, g, eng, steps, tape = _case("eos_mingen40")
+    L = inp["txt_seq"].shape[1]
+    ses = eng.session(1, steps, L)
+    toks, n = ses.generate_host(inp["cond_ar"].numpy(), inp["txt_seq"].numpy(), [L], tape.unsqueeze(0).numpy(),
+                                _sampling(inp["sampling"], cfg))
+    assert toks[0, : n[0]].tolist() == g["tokens"].tolist()
+
+
+def test_stop_on_first_eos_mode():
+    """generate_tokens()/stream() consumers break at the first EOS (model.py:382-383)."""
+    toks, g, _ = _run_case("eos_mingen40", stop_on_first_eos=True)
+    gold = g["tokens"].tolist()
+    eos = 2048
+    first = gold.index(eos)
+    assert toks == gold[: first + 1]
+
+
+def test_errors_are_loud():
+    from sopro_b200 import _lib
+    from sopro_b200.engine import Sampling
+
+    spec, cfg, sd, inp, g, eng, steps, tape = _case("default_fp32")
+    ses = eng.session(1, 8, 8)
+    with pytest.raises(_lib.SoproError):
+        ses.run(1)  # before begin
+    with pytest.raises(_lib.SoproError):
+        ses.begin(inp["cond_ar"][:, :8], inp["txt_seq"][:, :8], [0], tape[:8].unsqueeze(0), Sampling())  # text_len 0
+    with pytest.raises(_lib.SoproError):
+        ses.begin(inp["cond_ar"][:, :8], inp["txt_seq"][:, :8], [8], tape[:8].unsqueeze(0), Sampling(top_k=0))
+    with pytest.raises(_lib.SoproError):
+        ses.begin(inp["cond_ar"][:, :8], inp["txt_seq"][:, :8], [8], tape[:8, :10].unsqueeze(0).contiguous(), Sampling())
