@@ -71,6 +71,7 @@ SYMBOLS = {
     "sopro_ar_generate_host": (_I, [_VP, _I, _I, _VP, _VP, _I, _I32P, _VP, _I, C.POINTER(ArSampling), _VP, _VP, _VP]),
     "sopro_ar_set_forced_tokens": (_I, [_VP, _VP]),
     "sopro_ar_set_trace": (_I, [_VP, _VP, _VP]),
+    "sopro_ar_set_timing": (_I, [_VP, _VP, _I]),
     "sopro_ar_debug_sampled": (_I, [_VP, _VP, _VP]),
     "sopro_ar_debug_kv": (_I, [_VP, _VP, _VP, _VP]),
 }

@@ -109,6 +109,8 @@ struct sopro_ar_session {
   const int* forced = nullptr;
   float* trace_blocks = nullptr;
   float* trace_logits = nullptr;
+  long long* timing = nullptr;
+  int timing_step = -1;
   bool begun = false;
   std::vector<UttState> host_st;
 };
@@ -515,6 +517,8 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.trace_blocks = s->trace_blocks;
   p.trace_logits = s->trace_logits;
   p.barrier = s->barrier;
+  p.timing = s->timing;
+  p.timing_step = s->timing_step;
   // ---- team geometry
   int Bt = s->utts_per_team;
   if (Bt <= 0) {
@@ -649,6 +653,13 @@ int sopro_ar_set_trace(sopro_ar_session_t* s, float* trace_blocks, float* trace_
   if (!s) return fail(SOPRO_ERR_INVALID, "null session");
   s->trace_blocks = trace_blocks;
   s->trace_logits = trace_logits;
+  return SOPRO_OK;
+}
+
+int sopro_ar_set_timing(sopro_ar_session_t* s, int64_t* buf, int step) {
+  if (!s) return fail(SOPRO_ERR_INVALID, "null session");
+  s->timing = reinterpret_cast<long long*>(buf);
+  s->timing_step = step;
   return SOPRO_OK;
 }
 

@@ -30,6 +30,7 @@ constexpr int kMaxLayers = 16;
 constexpr int kMaxTopK = 64;
 constexpr int kMaxUttPerTeam = 32;
 constexpr int kSampNPT = 8;  // vocab entries per thread in the sampler: V <= 4096
+constexpr int kTimingSlots = 128;
 
 struct LayerDev {
   const float* norm_w;
@@ -98,6 +99,8 @@ struct ArParams {
   float* trace_blocks;
   float* trace_logits;
   unsigned* barrier;  // [g][32]
+  long long* timing;  // debug: [grid][kTimingSlots] clock64 stamps of step `timing_step` (null = off)
+  int timing_step;
   int g, P, Bt;
   int t_begin, t_end;
 };
@@ -138,16 +141,27 @@ __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterp
 __device__ __forceinline__ float ldcg1(const float* p) { return __ldcg(p); }
 
 // team barrier: monotonically increasing arrival counter, host zeroes it before each launch
-__device__ __forceinline__ void team_barrier(unsigned* counter, unsigned P, unsigned& epoch) {
+struct Stamp {
+  long long* buf;  // this CTA's slots, or null
+  int n;
+  __device__ __forceinline__ void mark() {
+    if (buf && n < kTimingSlots) buf[n++] = clock64();
+  }
+};
+
+__device__ __forceinline__ void team_barrier(unsigned* counter, unsigned P, unsigned& epoch, Stamp& ts) {
   __syncthreads();
   if (threadIdx.x == 0) {
+    ts.mark();  // whole CTA finished the stage
     epoch += 1;
     const unsigned target = epoch * P;
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+    ts.mark();  // arrival posted
     unsigned v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
     } while (v < target);
+    ts.mark();  // released
   }
   __syncthreads();
 }
@@ -811,6 +825,10 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
     }
     float* cur = p.xa;
     float* nxt = p.xb;
+    Stamp ts;
+    ts.buf = (p.timing && t == p.timing_step && threadIdx.x == 0) ? p.timing + (size_t)blockIdx.x * kTimingSlots : nullptr;
+    ts.n = 0;
+    ts.mark();
     for (int li = 0; li < p.n_layers; ++li) {
       const LayerDev& L = p.layer[li];
       // ---- stage 1: x (or cond+emb) -> RMSNorm -> GLU -> ring/dwconv -> nxt
@@ -848,12 +866,12 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
         cur = nxt;
         nxt = tmp;
       }
-      team_barrier(bar, tc.P, epoch);
+      team_barrier(bar, tc.P, epoch, ts);
       // ---- stage 2: FFN up + GELU
       stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, L.ffn_norm_w, nullptr);
       __syncthreads();
       gemv_dispatch<EPI_FFN1, WT>(p, tc, L.w1, F, D, L.b1, act, p.hbuf, F, 0.f, nullptr);
-      team_barrier(bar, tc.P, epoch);
+      team_barrier(bar, tc.P, epoch, ts);
       // ---- stage 3: FFN down + residual (in place on this CTA's slice of cur)
       stage_rows(p.hbuf + (size_t)tc.b0 * F, F, tc.nb, F, act, nullptr, nullptr);
       __syncthreads();
@@ -863,16 +881,16 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
                         : nullptr;
         gemv_dispatch<EPI_FFN2, WT>(p, tc, L.w2, D, F, L.b2, act, cur, D, 0.f, tr);
       }
-      team_barrier(bar, tc.P, epoch);
+      team_barrier(bar, tc.P, epoch, ts);
       if (L.has_attn) {
         // ---- q projection
         stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, L.nq_w, nullptr);
         __syncthreads();
         gemv_dispatch<EPI_Q, WT>(p, tc, L.wq, D, D, nullptr, act, p.qbuf, D, 0.f, nullptr);
-        team_barrier(bar, tc.P, epoch);
+        team_barrier(bar, tc.P, epoch, ts);
         // ---- attention core
         stage_attention(p, L, tc, act);
-        team_barrier(bar, tc.P, epoch);
+        team_barrier(bar, tc.P, epoch, ts);
         // ---- out projection + gated residual
         stage_rows(p.abuf + (size_t)tc.b0 * D, D, tc.nb, D, act, nullptr, nullptr);
         __syncthreads();
@@ -880,7 +898,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
           float* tr = p.trace_blocks ? p.trace_blocks + (((size_t)t * p.n_layers + li) * p.B) * D : nullptr;
           gemv_dispatch<EPI_O, WT>(p, tc, L.wo, D, D, nullptr, act, cur, D, L.gate_tanh, tr);
         }
-        team_barrier(bar, tc.P, epoch);
+        team_barrier(bar, tc.P, epoch, ts);
       }
     }
     // ---- head
@@ -890,7 +908,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
       float* tr = p.trace_logits ? p.trace_logits + ((size_t)t * p.B) * p.V : nullptr;
       gemv_dispatch<EPI_HEAD, WT>(p, tc, p.head_w, p.V, D, p.head_b, act, p.logits, p.Vpad, 0.f, tr);
     }
-    team_barrier(bar, tc.P, epoch);
+    team_barrier(bar, tc.P, epoch, ts);
     // ---- sampler: utterances round-robin over the team's CTAs
     {
       float* sx = act;
@@ -900,7 +918,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
         __syncthreads();
       }
     }
-    team_barrier(bar, tc.P, epoch);
+    team_barrier(bar, tc.P, epoch, ts);
     // x ping-pong parity: after an even number of swaps per step cur == xa again only if
     // n_layers is even; keep it simple and copy nothing: the next step's layer 0 reads
     // cond/emb, never cur.

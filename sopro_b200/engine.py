@@ -214,6 +214,10 @@ class ArSession:
         _lib.check(self.lib.sopro_ar_set_trace(self._h, blocks.data_ptr() if blocks is not None else None,
                                                logits.data_ptr() if logits is not None else None))
 
+    def set_timing(self, buf: Optional[torch.Tensor], step: int = -1) -> None:
+        self._timing = buf
+        _lib.check(self.lib.sopro_ar_set_timing(self._h, buf.data_ptr() if buf is not None else None, int(step)))
+
     def sampled(self) -> torch.Tensor:
         out = torch.empty((self.batch, self.steps), dtype=torch.int32, device=self.engine.device)
         _lib.check(self.lib.sopro_ar_debug_sampled(self._h, out.data_ptr(), _stream_ptr(self.engine.device)))

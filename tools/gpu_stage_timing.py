@@ -1,0 +1,57 @@
+"""Per-stage timeline of one AR step from the kernel's own clock64 stamps."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+from tests.cases import AR_CASES, ar_case_inputs, _unit
+from sopro_b200.engine import ArEngine, Sampling
+
+torch.set_grad_enabled(False)
+
+
+def stage_names(cfg):
+    names = []
+    attn = set(cfg.ar_attn_layers())
+    for i in range(int(cfg.n_layers_ar)):
+        names += [f"L{i}.glu", f"L{i}.ffn1", f"L{i}.ffn2"]
+        if i in attn:
+            names += [f"L{i}.q", f"L{i}.att", f"L{i}.o"]
+    return names + ["head", "sample"]
+
+
+def run(B, wdtype, team=0, steps=64, L=52, step=40):
+    spec = AR_CASES["default_bf16" if wdtype == "bf16" else "default_fp32"]
+    cfg, sd, _ = ar_case_inputs(spec)
+    eng = ArEngine(cfg, sd, 0, wdtype)
+    D = int(cfg.d_model)
+    cond = (_unit(steps * D, 1).view(1, steps, D).expand(B, steps, D) + 0.01 * torch.arange(B).view(B, 1, 1)).contiguous()
+    txt = _unit(L * D, 2).view(1, L, D).expand(B, L, D).contiguous()
+    noise = torch.empty(B, steps, 50).exponential_(1.0, generator=torch.Generator().manual_seed(0))
+    ses = eng.session(B, steps, L)
+    if team: ses.set_team(team)
+    buf = torch.zeros(eng.num_sms, 128, dtype=torch.int64, device="cuda")
+    ses.set_timing(buf, step)
+    ses.begin(cond, txt, [L] * B, noise, Sampling(min_gen_frames=2**31 - 1))
+    ses.run(); torch.cuda.synchronize()
+    t = buf.cpu().numpy()
+    names = stage_names(cfg)
+    ns = len(names)
+    clk = 1.0  # cycles
+    print(f"== B={B} {wdtype} team={team}: per-stage cycles (median / max over CTAs): work = start->stage done, "
+          f"post = done->arrival posted, wait = arrival->released")
+    tot = np.zeros(3)
+    for s_i, nm in enumerate(names):
+        t0 = t[:, 0] if s_i == 0 else t[:, 3 * s_i]      # previous release (or step start)
+        done, arr, rel = t[:, 1 + 3 * s_i], t[:, 2 + 3 * s_i], t[:, 3 + 3 * s_i]
+        ok = rel > 0
+        w, p_, q = (done - t0)[ok], (arr - done)[ok], (rel - arr)[ok]
+        tot += [np.median(w), np.median(p_), np.median(q)]
+        print(f"  {nm:9s} work {np.median(w):7.0f}/{w.max():7.0f}  post {np.median(p_):6.0f}/{p_.max():6.0f}  "
+              f"wait {np.median(q):7.0f}/{q.max():7.0f}  (min wait {q.min():6.0f})")
+    span = (t[:, 3 * ns] - t[:, 0])
+    print(f"  step span cycles median {np.median(span[span>0]):.0f}; sums of medians work {tot[0]:.0f} post {tot[1]:.0f} wait {tot[2]:.0f}")
+
+
+if __name__ == "__main__":
+    for B, wd, team in [(1, "fp32", 0), (64, "bf16", 0)]:
+        run(B, wd, team)
