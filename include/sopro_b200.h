@@ -167,8 +167,9 @@ int sopro_ar_set_forced_tokens(sopro_ar_session_t* s, const int32_t* forced);
 /* trace_blocks [steps, n_layers, batch, D] f32 (residual stream after block i incl. its
  * cross-attention), trace_logits [steps, batch, V] f32; NULL disables. device. */
 int sopro_ar_set_trace(sopro_ar_session_t* s, float* trace_blocks, float* trace_logits);
-/* clock64 stamps of one step: buf [grid, 128] i64 device (grid = SM count); per barrier three
- * stamps (stage done, arrival posted, released), preceded by one stamp at step start. NULL = off */
+/* clock64 stamps of one step: buf [grid, 224] i64 device (grid = SM count): one stamp at step
+ * start, then five per stage (activations staged, weight tiles done, whole CTA done, barrier
+ * arrival posted, barrier released). NULL = off */
 int sopro_ar_set_timing(sopro_ar_session_t* s, int64_t* buf, int step);
 /* copy the sampled (pre-forcing) tokens into dst [batch, steps] i32 (device) */
 int sopro_ar_debug_sampled(sopro_ar_session_t* s, int32_t* dst, void* stream);

@@ -85,6 +85,8 @@ struct sopro_engine {
   const void* head_w = nullptr;
   const float* head_b = nullptr;
   const float* emb = nullptr;
+  const float* epi[kMaxLayers]{};  // packed [D][KcE]: dwconv taps, dwconv bias, GLU value bias, GLU gate bias
+  int KcP = 0, KcE = 0;
   long long ring_floats_per_utt = 0;
 };
 
@@ -99,6 +101,13 @@ struct sopro_ar_session {
   UttState* st = nullptr;
   SamplingDev* samp = nullptr;
   unsigned* barrier = nullptr;
+  TileDesc* tiles = nullptr;  // [n_sms][kMaxTilesPerStep]
+  int* n_tiles = nullptr;     // [n_sms]
+  unsigned char* stage_tiles = nullptr;  // [n_sms][kMaxStages]
+  std::vector<unsigned char> h_stage_tiles;
+  int tile_P = -1, tile_wbuf = -1;
+  std::vector<TileDesc> h_tiles;
+  std::vector<int> h_ntiles;
   // staging for the host-buffer path
   float *h_cond = nullptr, *h_txt = nullptr, *h_noise = nullptr;
   size_t h_cond_cap = 0, h_txt_cap = 0, h_noise_cap = 0;
@@ -138,9 +147,10 @@ int sopro_engine_create(const sopro_ar_config_t* cfg, const sopro_ar_weights_t* 
   const int D = cfg->d_model, NL = cfg->n_layers, Kc = cfg->kernel, H = cfg->n_heads, V = cfg->vocab;
   if (D <= 0 || D % 4 != 0) return fail(SOPRO_ERR_INVALID, "d_model must be a positive multiple of 4 (got %d)", D);
   if (NL <= 0 || NL > kMaxLayers) return fail(SOPRO_ERR_INVALID, "n_layers must be in [1,%d]", kMaxLayers);
-  if (H <= 0 || D % H != 0 || (D / H) % 4 != 0) return fail(SOPRO_ERR_INVALID, "bad head geometry D=%d H=%d", D, H);
+  if (H <= 0 || D % H != 0 || (D / H) % 4 != 0 || D / H > 128)
+    return fail(SOPRO_ERR_INVALID, "bad head geometry D=%d H=%d (head_dim must be a multiple of 4, <= 128)", D, H);
   if (Kc < 1 || Kc > 64) return fail(SOPRO_ERR_INVALID, "kernel must be in [1,64]");
-  if (V < 2 || V > kSampNPT * kThreads) return fail(SOPRO_ERR_INVALID, "vocab must be in [2,%d]", kSampNPT * kThreads);
+  if (V < 2 || V > kMaxVocab) return fail(SOPRO_ERR_INVALID, "vocab must be in [2,%d]", kMaxVocab);
   if (cfg->eos_id < 0 || cfg->eos_id >= V) return fail(SOPRO_ERR_INVALID, "eos_id out of range");
   if (cfg->weight_dtype != SOPRO_W_F32 && cfg->weight_dtype != SOPRO_W_BF16)
     return fail(SOPRO_ERR_INVALID, "weight_dtype must be 0 (f32) or 1 (bf16)");
@@ -161,12 +171,14 @@ int sopro_engine_create(const sopro_ar_config_t* cfg, const sopro_ar_weights_t* 
   e->Dh = D / H;
   e->Kc = Kc;
   e->n_layers = NL;
+  e->KcP = (int)align_up((size_t)Kc, 4);
+  e->KcE = (int)align_up((size_t)Kc + 3, 4);
   const int wd = cfg->weight_dtype;
   const size_t wsz = wd == SOPRO_W_F32 ? 4 : 2;
 
   Arena A;
   struct Off {
-    size_t norm_w, glu_w, glu_b, dw_w, dw_b, ffn_norm_w, w1, b1, w2, b2, nq_w, nkv_w, wq, wk, wv, wo;
+    size_t norm_w, glu_w, glu_b, dw_w, dw_b, ffn_norm_w, w1, b1, w2, b2, nq_w, nkv_w, wq, wk, wv, wo, epi;
   } off[kMaxLayers];
   int64_t step_bytes = 0;
   int n_attn = 0;
@@ -192,6 +204,17 @@ int sopro_engine_create(const sopro_ar_config_t* cfg, const sopro_ar_weights_t* 
     off[i].b1 = A.add_f32(L.ffn_b1, 4 * D);
     off[i].w2 = A.add_mat(L.ffn_w2, (size_t)4 * D * D, wd);
     off[i].b2 = A.add_f32(L.ffn_b2, D);
+    {
+      std::vector<float> er((size_t)D * e->KcE, 0.f);
+      for (int c = 0; c < D; ++c) {
+        float* r = er.data() + (size_t)c * e->KcE;
+        for (int j = 0; j < Kc; ++j) r[j] = L.dw_w[(size_t)c * Kc + j];
+        r[Kc] = L.dw_b[c];
+        r[Kc + 1] = L.glu_b[c];
+        r[Kc + 2] = L.glu_b[c + D];
+      }
+      off[i].epi = A.add_f32(er.data(), er.size());
+    }
     step_bytes += (int64_t)(D + 2 * D + (size_t)D * Kc + D + D + 4 * D + D) * 4 + (int64_t)(2 + 4 + 4) * D * D * wsz;
     if (cfg->has_attn[i]) {
       if (!L.nq_w || !L.nkv_w || !L.q_w || !L.k_w || !L.v_w || !L.o_w) {
@@ -243,6 +266,7 @@ int sopro_engine_create(const sopro_ar_config_t* cfg, const sopro_ar_weights_t* 
     L.b1 = F32(off[i].b1);
     L.w2 = PTR(off[i].w2);
     L.b2 = F32(off[i].b2);
+    e->epi[i] = F32(off[i].epi);
     L.dil = cfg->dilation[i];
     L.ring_len = (Kc - 1) * L.dil + 1;
     L.has_attn = cfg->has_attn[i] ? 1 : 0;
@@ -258,7 +282,7 @@ int sopro_engine_create(const sopro_ar_config_t* cfg, const sopro_ar_weights_t* 
       e->wv[n_attn] = PTR(off[i].wv);
       ++n_attn;
     }
-    ring_off += (long long)L.ring_len * D;  // per utterance; scaled by batch at session time
+    ring_off += (long long)D * L.dil * e->KcP;  // conv state per utterance: [D][dil][KcP]
   }
   e->n_attn = n_attn;
   e->ring_floats_per_utt = ring_off;
@@ -300,6 +324,9 @@ static void session_free(sopro_ar_session* s) {
   cudaFree(s->st);
   cudaFree(s->samp);
   cudaFree(s->barrier);
+  cudaFree(s->tiles);
+  cudaFree(s->n_tiles);
+  cudaFree(s->stage_tiles);
   cudaFree(s->h_cond);
   cudaFree(s->h_txt);
   cudaFree(s->h_noise);
@@ -311,9 +338,9 @@ int sopro_ar_session_create(sopro_engine_t* e, int max_batch, int max_steps, int
   *out = nullptr;
   if (max_batch < 1 || max_steps < 1 || max_text_len < 1)
     return fail(SOPRO_ERR_INVALID, "max_batch, max_steps, max_text_len must be >= 1");
-  if (max_batch > e->n_sms * kMaxUttPerTeam)
+  if (max_batch > e->n_sms * 16)
     return fail(SOPRO_ERR_INVALID, "max_batch %d exceeds %d (SMs x %d utterances per team)", max_batch,
-                e->n_sms * kMaxUttPerTeam, kMaxUttPerTeam);
+                e->n_sms * 16, 16);
   CK(cudaSetDevice(e->device));
   sopro_ar_session* s = new sopro_ar_session();
   s->e = e;
@@ -343,6 +370,9 @@ int sopro_ar_session_create(sopro_engine_t* e, int max_batch, int max_steps, int
   A((void**)&s->st, B * sizeof(UttState));
   A((void**)&s->samp, B * sizeof(SamplingDev));
   A((void**)&s->barrier, (size_t)e->n_sms * 32 * 4);
+  A((void**)&s->tiles, (size_t)e->n_sms * kMaxTilesPerStep * sizeof(TileDesc));
+  A((void**)&s->n_tiles, (size_t)e->n_sms * 4);
+  A((void**)&s->stage_tiles, (size_t)e->n_sms * kMaxStages);
   if (err != cudaSuccess) {
     session_free(s);
     delete s;
@@ -468,6 +498,94 @@ int sopro_ar_begin(sopro_ar_session_t* s, int batch, int steps, const float* con
 
 }  // extern "C"
 
+// ---- weight-tile schedule of one AR step for every team rank (consumption order of the kernel)
+struct StageW {
+  int stage;          // index in the kernel's stage program
+  const void* w;
+  int N, K, parts;    // parts = 2 for the GLU (value rows + gate rows of the same channels)
+  const float* epi;   // GLU: packed [D][KcE] epilogue rows; else the bias vector [N] (or null)
+};
+
+static int build_tiles(sopro_ar_session* s, int P, int wbuf, cudaStream_t st) {
+  sopro_engine* e = s->e;
+  if (s->tile_P == P && s->tile_wbuf == wbuf) return SOPRO_OK;
+  const size_t wsz = e->cfg.weight_dtype == SOPRO_W_F32 ? 4 : 2;
+  std::vector<StageW> prog;
+  int si = 0;  // must mirror the stage program built in launch_ar
+  for (int i = 0; i < e->n_layers; ++i) {
+    const LayerDev& L = e->layer[i];
+    prog.push_back({si++, L.glu_w, e->D, e->D, 2, e->epi[i]});
+    prog.push_back({si++, L.w1, e->F, e->D, 1, L.b1});
+    prog.push_back({si++, L.w2, e->D, e->F, 1, L.b2});
+    if (L.has_attn) {
+      prog.push_back({si++, L.wq, e->D, e->D, 1, nullptr});
+      si++;  // attention core: no weights
+      prog.push_back({si++, L.wo, e->D, e->D, 1, nullptr});
+    }
+  }
+  prog.push_back({si++, e->head_w, e->V, e->D, 1, e->head_b});
+  s->h_stage_tiles.assign((size_t)P * kMaxStages, 0);
+  s->h_tiles.assign((size_t)P * kMaxTilesPerStep, TileDesc{});
+  s->h_ntiles.assign(P, 0);
+  for (int r = 0; r < P; ++r) {
+    int n = 0;
+    for (const StageW& sw : prog) {
+      const int n0 = (int)(((long long)sw.N * r) / P), n1 = (int)(((long long)sw.N * (r + 1)) / P);
+      const size_t row_bytes = (size_t)sw.K * wsz;
+      // per row: weights (x parts) + epilogue constants (GLU: KcE floats; else 1 bias float, +32 B span slack)
+      const size_t epi_row = sw.parts == 2 ? (size_t)e->KcE * 4 : (sw.epi ? 4 : 0);
+      const int rpt = (int)(((size_t)wbuf - 32) / (row_bytes * sw.parts + epi_row));
+      if (rpt < 1) return fail(SOPRO_ERR_INVALID, "weight buffer %d B cannot hold one row (%zu B x %d)", wbuf, row_bytes, sw.parts);
+      for (int a = n0; a < n1; a += rpt) {
+        const int nr = std::min(rpt, n1 - a);
+        if (n >= kMaxTilesPerStep) return fail(SOPRO_ERR_INVALID, "more than %d weight tiles per step (P=%d, wbuf=%d)", kMaxTilesPerStep, P, wbuf);
+        TileDesc& t = s->h_tiles[(size_t)r * kMaxTilesPerStep + n++];
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(sw.w);
+        t.src0 = reinterpret_cast<unsigned long long>(base + (size_t)a * row_bytes);
+        t.bytes0 = (unsigned)((size_t)nr * row_bytes);
+        t.src1 = sw.parts == 2 ? reinterpret_cast<unsigned long long>(base + (size_t)(a + sw.N) * row_bytes) : 0ull;
+        t.bytes1 = sw.parts == 2 ? t.bytes0 : 0u;
+        t.src2 = 0;
+        t.bytes2 = 0;
+        t.off2 = 0;
+        if (sw.parts == 2) {
+          t.src2 = reinterpret_cast<unsigned long long>(sw.epi + (size_t)a * e->KcE);
+          t.bytes2 = (unsigned)((size_t)nr * e->KcE * 4);
+        } else if (sw.epi) {
+          const int lo = a / 4 * 4, hi = (a + nr + 3) / 4 * 4;  // 16-byte aligned span (vectors are padded)
+          t.src2 = reinterpret_cast<unsigned long long>(sw.epi + lo);
+          t.bytes2 = (unsigned)((hi - lo) * 4);
+          t.off2 = a - lo;
+        }
+        t.row0 = a;
+        t.nrows = nr;
+        t.pad = 0;
+        if (++s->h_stage_tiles[(size_t)r * kMaxStages + sw.stage] == 255)
+          return fail(SOPRO_ERR_INVALID, "more than 254 weight tiles in one stage");
+      }
+    }
+    s->h_ntiles[r] = n;
+  }
+  CK(cudaMemcpyAsync(s->tiles, s->h_tiles.data(), s->h_tiles.size() * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s->n_tiles, s->h_ntiles.data(), (size_t)P * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(s->stage_tiles, s->h_stage_tiles.data(), s->h_stage_tiles.size(), cudaMemcpyHostToDevice, st));
+  s->tile_P = P;
+  s->tile_wbuf = wbuf;
+  return SOPRO_OK;
+}
+
+template <typename WT, int TU>
+static int launch_ar_tu(sopro_ar_session* s, ArParams& p, size_t smem, int grid, cudaStream_t st) {
+  CK(cudaFuncSetAttribute(ar_persistent_kernel<WT, TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ar_persistent_kernel<WT, TU>, kThreads, smem));
+  if (occ < 1) return fail(SOPRO_ERR_CUDA, "persistent kernel does not fit an SM (smem %zu)", smem);
+  CK(cudaMemsetAsync(s->barrier, 0, (size_t)s->e->n_sms * 32 * 4, st));
+  void* args[] = {(void*)&p};
+  CK(cudaLaunchCooperativeKernel((const void*)ar_persistent_kernel<WT, TU>, dim3(grid), dim3(kThreads), args, smem, st));
+  return SOPRO_OK;
+}
+
 template <typename WT>
 static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t st) {
   sopro_engine* e = s->e;
@@ -479,13 +597,15 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.H = e->H;
   p.Dh = e->Dh;
   p.Kc = e->Kc;
+  p.KcP = e->KcP;
+  p.KcE = e->KcE;
   p.n_layers = e->n_layers;
   p.eos_id = e->cfg.eos_id;
   long long roff = 0;
   for (int i = 0; i < e->n_layers; ++i) {
     p.layer[i] = e->layer[i];
     p.layer[i].ring_off = roff;
-    roff += (long long)e->layer[i].ring_len * e->D * s->B;
+    roff += (long long)e->D * e->layer[i].dil * e->KcP * s->B;
   }
   p.final_norm_w = e->final_norm_w;
   p.head_w = e->head_w;
@@ -519,16 +639,18 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.barrier = s->barrier;
   p.timing = s->timing;
   p.timing_step = s->timing_step;
-  // ---- team geometry
+  // ---- team geometry: g teams x P CTAs, Bt utterances per team
   int Bt = s->utts_per_team;
   if (Bt <= 0) {
     if (const char* env = getenv("SOPRO_AR_UTTS_PER_TEAM")) Bt = atoi(env);
   }
-  if (Bt <= 0) Bt = s->B <= 8 ? s->B : (s->B <= 16 * e->n_sms / 8 ? 16 : kMaxUttPerTeam);
-  Bt = std::min(Bt, kMaxUttPerTeam);
+  if (Bt <= 0) Bt = s->B <= 8 ? s->B : 16;
+  // activations ([Bt][F] fp32) may use at most ~120 KB of shared memory; the rest is the weight ring
+  const int bt_cap = std::min(kMaxUttPerTeam, std::max(1, (int)((120 * 1024) / ((size_t)e->F * 4))));
+  Bt = std::min(Bt, bt_cap);
   int g = (s->B + Bt - 1) / Bt;
   if (g > e->n_sms) {
-    Bt = kMaxUttPerTeam;
+    Bt = bt_cap;
     g = (s->B + Bt - 1) / Bt;
   }
   if (g > e->n_sms) return fail(SOPRO_ERR_INVALID, "batch %d needs %d teams > %d SMs", s->B, g, e->n_sms);
@@ -540,20 +662,64 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.Bt = Bt;
   p.t_begin = t_begin;
   p.t_end = t_end;
-  const size_t need_act = (size_t)Bt * std::max(2 * e->D, e->F) * 4;
-  const size_t need_att = (size_t)kWarps * (s->Lmax + e->Dh) * 4;
-  const size_t need_smp = (size_t)e->Vpad * 4 + e->Vpad + 16;
-  const size_t smem = align_up(std::max(need_act, std::max(need_att, need_smp)), 16);
-  if (smem > 227 * 1024)
-    return fail(SOPRO_ERR_INVALID, "shared memory need %zu B > 227 KB (Bt=%d, Lmax=%d)", smem, Bt, s->Lmax);
-  CK(cudaFuncSetAttribute(ar_persistent_kernel<WT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ar_persistent_kernel<WT>, kThreads, smem));
-  if (occ < 1) return fail(SOPRO_ERR_CUDA, "persistent kernel does not fit an SM (smem %zu)", smem);
-  CK(cudaMemsetAsync(s->barrier, 0, (size_t)e->n_sms * 32 * 4, st));
-  void* args[] = {(void*)&p};
-  CK(cudaLaunchCooperativeKernel((const void*)ar_persistent_kernel<WT>, dim3(g * P), dim3(kThreads), args, smem, st));
-  return SOPRO_OK;
+  const size_t need_act = std::max((size_t)Bt * e->F * 4, (size_t)2 * Bt * e->D * 4 + (size_t)kWarps * 8 * e->KcP * 4);
+  const size_t need_att = ((size_t)s->Lmax + (size_t)kWarps * e->Dh + (size_t)kWarps * 8 * e->Dh) * 4;
+  const size_t need_smp = (size_t)e->Vpad * 8 + e->Vpad + 16;
+  const size_t act_bytes = align_up(std::max(need_act, std::max(need_att, need_smp)), 128);
+  const size_t kSmemCap = 214 * 1024;  // 227 KB minus static shared memory (sampler scratch, mbarriers)
+  const size_t table_bytes = (size_t)kMaxTilesPerStep * sizeof(TileDesc);
+  if (act_bytes + table_bytes + 2 * 4096 > kSmemCap)
+    return fail(SOPRO_ERR_INVALID, "shared memory: activations need %zu B (Bt=%d, Lmax=%d), nothing left for weights",
+                act_bytes, Bt, s->Lmax);
+  const size_t avail = kSmemCap - act_bytes - table_bytes;
+  const size_t wsz = e->cfg.weight_dtype == SOPRO_W_F32 ? 4 : 2;
+  auto slice_bytes = [&](int N, int K, int parts) {
+    const size_t rows = (size_t)((N + P - 1) / P);
+    return rows * K * wsz * parts + (parts == 2 ? rows * e->KcE * 4 : rows * 4) + 32;
+  };
+  size_t full = std::max(std::max(slice_bytes(e->D, e->D, 2), slice_bytes(e->F, e->D, 1)),
+                         std::max(slice_bytes(e->D, e->F, 1), slice_bytes(e->V, e->D, 1)));
+  full = align_up(full, 128);
+  size_t wbuf;
+  int nbuf;
+  if (2 * full <= avail) {
+    wbuf = full;
+    nbuf = (int)std::min<size_t>(kMaxWBuf, avail / wbuf);
+  } else {
+    wbuf = (avail / 2) / 128 * 128;
+    nbuf = 2;
+  }
+  int rc = build_tiles(s, P, (int)wbuf, st);
+  if (rc != SOPRO_OK) return rc;
+  p.tiles = s->tiles;
+  p.n_tiles = s->n_tiles;
+  p.stage_tiles = s->stage_tiles;
+  p.nbuf = nbuf;
+  p.wbuf_bytes = (int)wbuf;
+  p.act_bytes = (int)act_bytes;
+  const size_t smem = act_bytes + (size_t)nbuf * wbuf + table_bytes;
+  // ---- stage program of one step
+  {
+    int n = 0;
+    for (int i = 0; i < e->n_layers; ++i) {
+      p.prog[n++] = {K_GLU, (unsigned char)i};
+      p.prog[n++] = {K_FFN1, (unsigned char)i};
+      p.prog[n++] = {K_FFN2, (unsigned char)i};
+      if (e->layer[i].has_attn) {
+        p.prog[n++] = {K_Q, (unsigned char)i};
+        p.prog[n++] = {K_ATT, (unsigned char)i};
+        p.prog[n++] = {K_O, (unsigned char)i};
+      }
+    }
+    p.prog[n++] = {K_HEAD, 0};
+    p.prog[n++] = {K_SAMPLE, 0};
+    p.n_stage = n;
+  }
+  const int grid = g * P;
+  if (Bt >= 8) return launch_ar_tu<WT, 8>(s, p, smem, grid, st);
+  if (Bt >= 4) return launch_ar_tu<WT, 4>(s, p, smem, grid, st);
+  if (Bt >= 2) return launch_ar_tu<WT, 2>(s, p, smem, grid, st);
+  return launch_ar_tu<WT, 1>(s, p, smem, grid, st);
 }
 
 extern "C" {

@@ -9,14 +9,20 @@
 //
 // Work decomposition: the grid is split into `g` TEAMS of `P`
 // CTAs (one CTA per SM, co-resident: cooperative launch).  A team owns a group
-// of <= 32 utterances.  Every stage of the step is a skinny GEMM
+// of <= 16 utterances.  Every stage of the step is a skinny GEMM
 // [utterances x K] . [K x N]; inside a team the N output features are
-// partitioned over the P CTAs, so each weight element is read from L2/HBM once
-// per team per step with coalesced 128-bit loads, and the [utterances x K]
-// activations are broadcast through L2.  Stages are separated by a team-scoped
-// barrier (one atomic counter per team, release/acquire at gpu scope).
-// All arithmetic is fp32 (FFMA2 packed pairs, warp-shuffle reductions); bf16
-// is a weight STORAGE format only.
+// partitioned over the P CTAs.  Each CTA's weight slice is streamed global ->
+// shared by 1-D TMA bulk copies into a ring of buffers, several stages ahead
+// of its use (the weights do not depend on other CTAs), so a stage never waits
+// on a weight load; the [utterances x K] activations are broadcast through L2.
+// Stages are separated by a team-scoped barrier (one counter per team,
+// release/acquire at gpu scope).  All arithmetic is fp32 (FFMA2 packed pairs,
+// warp-shuffle reductions); bf16 is a weight STORAGE format only.
+//
+// The step is written as a small INTERPRETER over a host-built stage program
+// with ONE shared GEMV body: the whole per-step instruction footprint must
+// stay near the SM's instruction cache (the first version, with one inlined
+// specialisation per stage, was 590 KB of SASS and instruction-fetch bound).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -28,9 +34,15 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxLayers = 16;
 constexpr int kMaxTopK = 64;
+constexpr int kCand = 128;  // candidate slots of the sampler's top-k
 constexpr int kMaxUttPerTeam = 32;
-constexpr int kSampNPT = 8;  // vocab entries per thread in the sampler: V <= 4096
-constexpr int kTimingSlots = 128;
+constexpr int kMaxVocab = 8 * kThreads;
+constexpr int kTimingSlots = 224;  // [0,160) stage stamps, [160,192) sampler phases, [192,224) attention phases
+constexpr int kMaxStages = 6 * kMaxLayers + 2;
+constexpr int kMaxTilesPerStep = 256;
+constexpr int kMaxWBuf = 8;
+
+enum StageKind { K_GLU = 0, K_FFN1 = 1, K_FFN2 = 2, K_Q = 3, K_O = 4, K_HEAD = 5, K_ATT = 6, K_SAMPLE = 7 };
 
 struct LayerDev {
   const float* norm_w;
@@ -48,10 +60,10 @@ struct LayerDev {
   const void* wo;
   float gate_tanh;
   int has_attn;
-  int attn_slot;      // index into the K/V cache
+  int attn_slot;       // index into the K/V cache
   int dil;
-  int ring_len;       // (k-1)*dil + 1
-  long long ring_off; // float offset of this layer's rings: [B][ring_len][D]
+  int ring_len;        // (k-1)*dil + 1 (receptive field of the layer; informational)
+  long long ring_off;  // float offset of this layer's conv state: [B][D][dil][KcP]
 };
 
 struct UttState {
@@ -68,9 +80,30 @@ struct SamplingDev {
   int top_k, anti_loop, loop_streak, min_gen, stop_on_first_eos;
 };
 
+// One weight tile of a CTA's slice: copied global -> shared by 1-D TMA bulk copies.
+// The host builds, per team rank, the list of tiles of ONE AR step in consumption order.
+struct TileDesc {
+  unsigned long long src0;  // global address of part 0 (rows [row0, row0+nrows) of the matrix)
+  unsigned long long src1;  // part 1: the GLU gate rows (row0 + D ...), else 0
+  unsigned long long src2;  // part 2: epilogue constants. GLU: rows of the packed [D][KcE] table
+                            // (dwconv taps, dwconv bias, GLU value bias, GLU gate bias); other stages:
+                            // the 16-byte aligned span of the bias vector covering the tile's rows
+  unsigned bytes0, bytes1, bytes2;  // multiples of 16
+  int off2;                 // float index of the tile's first row inside part 2
+  int row0;                 // first output feature of the tile
+  int nrows;
+  int pad;
+};
+
+struct StageOp {
+  unsigned char kind, layer;
+};
+
 struct ArParams {
-  int D, F, V, Vpad, H, Dh, Kc, n_layers, eos_id;
+  int D, F, V, Vpad, H, Dh, Kc, KcP, KcE, n_layers, eos_id;  // KcP = Kc rounded up to 4, KcE = Kc+3 rounded up to 4
   LayerDev layer[kMaxLayers];
+  StageOp prog[kMaxStages];
+  int n_stage;
   const float* final_norm_w;
   const void* head_w;
   const float* head_b;
@@ -98,7 +131,11 @@ struct ArParams {
   const SamplingDev* samp;
   float* trace_blocks;
   float* trace_logits;
-  unsigned* barrier;  // [g][32]
+  unsigned* barrier;      // [g][32]
+  const TileDesc* tiles;  // [P][kMaxTilesPerStep]
+  const int* n_tiles;     // [P] tiles per step of each rank
+  const unsigned char* stage_tiles;  // [P][kMaxStages] tiles of each stage
+  int nbuf, wbuf_bytes, act_bytes;
   long long* timing;  // debug: [grid][kTimingSlots] clock64 stamps of step `timing_step` (null = off)
   int timing_step;
   int g, P, Bt;
@@ -124,7 +161,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// weights: read-only path, 4 consecutive k per lane
+// weights straight from global (K/V builder): read-only path, 4 consecutive k per lane
 __device__ __forceinline__ float4 ldw4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float4 ldw4(const __nv_bfloat16* p) {
   uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
@@ -140,7 +177,6 @@ __device__ __forceinline__ float4 ldw4(const __nv_bfloat16* p) {
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float ldcg1(const float* p) { return __ldcg(p); }
 
-// team barrier: monotonically increasing arrival counter, host zeroes it before each launch
 struct Stamp {
   long long* buf;  // this CTA's slots, or null
   int n;
@@ -149,6 +185,7 @@ struct Stamp {
   }
 };
 
+// team barrier: monotonically increasing arrival counter, host zeroes it before each launch
 __device__ __forceinline__ void team_barrier(unsigned* counter, unsigned P, unsigned& epoch, Stamp& ts) {
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -167,114 +204,261 @@ __device__ __forceinline__ void team_barrier(unsigned* counter, unsigned P, unsi
 }
 
 // ---------------------------------------------------------------------------
-// warp GEMV tile: out[r][u] = sum_k W[row_r][k] * act[u][k]
-// lanes split K (4 consecutive k per lane per 128-k chunk), FFMA2 accumulation,
-// butterfly reduction: every lane ends with all TR*TU totals.
+// TMA 1-D bulk copy + mbarrier + cp.async helpers (sm_90+/sm_100a PTX)
 // ---------------------------------------------------------------------------
-template <int TR, int TU, typename WT>
-__device__ __forceinline__ void warp_rows(const WT* const (&wrow)[TR], const float* __restrict__ act, int lda,
-                                          int K, int lane, float (&out)[TR][TU]) {
-  float2 acc[TR][TU];
-#pragma unroll
-  for (int r = 0; r < TR; ++r)
-#pragma unroll
-    for (int u = 0; u < TU; ++u) acc[r][u] = make_float2(0.f, 0.f);
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(unsigned dst_smem, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned a = smem_u32(bar);
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ float lds32(unsigned a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float4 lds128(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+// 4 consecutive weights at shared address a (WT = float: 16 B, bf16: 8 B)
+template <typename WT>
+__device__ __forceinline__ float4 ldsw4(unsigned a);
+template <>
+__device__ __forceinline__ float4 ldsw4<float>(unsigned a) {
+  return lds128(a);
+}
+template <>
+__device__ __forceinline__ float4 ldsw4<__nv_bfloat16>(unsigned a) {
+  unsigned x, y;
+  asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
+  float4 r;
+  r.x = __uint_as_float(x << 16);
+  r.y = __uint_as_float(x & 0xffff0000u);
+  r.z = __uint_as_float(y << 16);
+  r.w = __uint_as_float(y & 0xffff0000u);
+  return r;
+}
 
-#pragma unroll 2
-  for (int k = lane * 4; k < K; k += 128) {
-    float4 w[TR];
+// The weight ring of a CTA: nbuf shared buffers filled by TMA in tile order.  Tile i lives in
+// buffer i % nbuf and completes phase (i / nbuf) of that buffer's mbarrier.  All indices are kept
+// as small wrapping counters: no integer division on the critical path.
+struct WeightRing {
+  unsigned long long* bars;  // [kMaxWBuf] "full" mbarriers
+  unsigned base;             // shared address of buffer 0
+  unsigned wbuf;             // bytes per buffer
+  int nbuf;
+  const TileDesc* table;     // this rank's tiles (shared-memory copy)
+  int n_tiles;               // per step
+  int tile;                  // table index of the next tile to consume
+  int buf;                   // its buffer
+  unsigned phase;            // bit b: parity to wait for on buffer b
+  int itile;                 // table index of the next tile to issue
+  int left;                  // tiles of this launch not yet issued
+  int inflight;              // issued, not yet consumed
+  __device__ __forceinline__ void issue_into(const TileDesc& td, int b) const {  // one thread
+    mbar_expect_tx(&bars[b], td.bytes0 + td.bytes1 + td.bytes2);
+    const unsigned dst = base + (unsigned)b * wbuf;
+    tma_load_1d(dst, reinterpret_cast<const void*>(td.src0), td.bytes0, &bars[b]);
+    if (td.bytes1) tma_load_1d(dst + td.bytes0, reinterpret_cast<const void*>(td.src1), td.bytes1, &bars[b]);
+    if (td.bytes2)
+      tma_load_1d(dst + td.bytes0 + td.bytes1, reinterpret_cast<const void*>(td.src2), td.bytes2, &bars[b]);
+  }
+  __device__ __forceinline__ void start(int total) {  // all threads (uniform bookkeeping)
+    tile = 0;
+    buf = 0;
+    phase = 0;
+    itile = 0;
+    left = total;
+    inflight = 0;
+    for (int b = 0; b < nbuf && left > 0; ++b) {
+      if (threadIdx.x == 0) issue_into(table[itile], b);
+      if (++itile == n_tiles) itile = 0;
+      --left;
+      ++inflight;
+    }
+  }
+  // all threads: wait for the next tile; returns its shared address
+  __device__ __forceinline__ unsigned acquire(const TileDesc*& td) const {
+    td = &table[tile];
+    mbar_wait(&bars[buf], (phase >> buf) & 1u);
+    return base + (unsigned)buf * wbuf;
+  }
+  // all threads, after the last read of the tile: recycle its buffer with the next tile to issue
+  __device__ __forceinline__ void release() {
+    __syncthreads();
+    --inflight;
+    if (left > 0) {
+      if (threadIdx.x == 0) issue_into(table[itile], buf);
+      if (++itile == n_tiles) itile = 0;
+      --left;
+      ++inflight;
+    }
+    phase ^= 1u << buf;
+    if (++buf == nbuf) buf = 0;
+    if (++tile == n_tiles) tile = 0;
+  }
+  // all threads: bulk copies still in flight must land before the CTA exits
+  __device__ __forceinline__ void drain() {
+    while (inflight > 0) {
+      mbar_wait(&bars[buf], (phase >> buf) & 1u);
+      phase ^= 1u << buf;
+      if (++buf == nbuf) buf = 0;
+      --inflight;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------
+// warp GEMV tile, 2 rows x TU utterances: out[r][u] = sum_k W[row_r][k] * act[u][k]
+// lanes split K (4 consecutive k per lane per 128-k chunk), FFMA2 accumulation, butterfly
+// reduction (every lane ends with all totals).  Weights AND activations in shared memory.
+// ---------------------------------------------------------------------------
+template <int TU, typename WT>
+__device__ __forceinline__ void warp_rows_s(unsigned w0, unsigned w1, unsigned act, int K, int lane,
+                                            float (&out)[2][TU]) {
+  float2 acc[2][TU];
 #pragma unroll
-    for (int r = 0; r < TR; ++r) w[r] = ldw4(wrow[r] + k);
+  for (int u = 0; u < TU; ++u) acc[0][u] = acc[1][u] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 wa = ldsw4<WT>(w0 + (unsigned)k * (unsigned)sizeof(WT));
+    const float4 wb = ldsw4<WT>(w1 + (unsigned)k * (unsigned)sizeof(WT));
 #pragma unroll
     for (int u = 0; u < TU; ++u) {
-      const float4 x = *reinterpret_cast<const float4*>(act + (size_t)u * lda + k);
-#pragma unroll
-      for (int r = 0; r < TR; ++r) {
-        acc[r][u] = __ffma2_rn(make_float2(w[r].x, w[r].y), make_float2(x.x, x.y), acc[r][u]);
-        acc[r][u] = __ffma2_rn(make_float2(w[r].z, w[r].w), make_float2(x.z, x.w), acc[r][u]);
-      }
+      const float4 x = lds128(act + ((unsigned)u * (unsigned)K + (unsigned)k) * 4u);
+      acc[0][u] = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(x.x, x.y), acc[0][u]);
+      acc[0][u] = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(x.z, x.w), acc[0][u]);
+      acc[1][u] = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(x.x, x.y), acc[1][u]);
+      acc[1][u] = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(x.z, x.w), acc[1][u]);
     }
   }
 #pragma unroll
-  for (int r = 0; r < TR; ++r)
+  for (int r = 0; r < 2; ++r)
 #pragma unroll
     for (int u = 0; u < TU; ++u) out[r][u] = warp_sum(acc[r][u].x + acc[r][u].y);
 }
 
-// pick element [i] of a register array with a runtime index without spilling
-template <int N>
-__device__ __forceinline__ float pick(const float (&a)[N], int i) {
-  float v = a[0];
+// same, weights from global memory (K/V builder only)
+template <int TU, typename WT>
+__device__ __forceinline__ void warp_rows_g(const WT* w0, const WT* w1, const float* __restrict__ act, int K, int lane,
+                                            float (&out)[2][TU]) {
+  float2 acc[2][TU];
 #pragma unroll
-  for (int j = 1; j < N; ++j) v = (i == j) ? a[j] : v;
-  return v;
+  for (int u = 0; u < TU; ++u) acc[0][u] = acc[1][u] = make_float2(0.f, 0.f);
+#pragma unroll 3
+  for (int k = lane * 4; k < K; k += 128) {
+    const float4 wa = ldw4(w0 + k);
+    const float4 wb = ldw4(w1 + k);
+#pragma unroll
+    for (int u = 0; u < TU; ++u) {
+      const float4 x = *reinterpret_cast<const float4*>(act + (size_t)u * K + k);
+      acc[0][u] = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(x.x, x.y), acc[0][u]);
+      acc[0][u] = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(x.z, x.w), acc[0][u]);
+      acc[1][u] = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(x.x, x.y), acc[1][u]);
+      acc[1][u] = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(x.z, x.w), acc[1][u]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int u = 0; u < TU; ++u) out[r][u] = warp_sum(acc[r][u].x + acc[r][u].y);
 }
-template <int TR, int TU>
-__device__ __forceinline__ float pick2(const float (&a)[TR][TU], int r, int u) {
+
+// pick element [r][u] of a register array with runtime indices without spilling
+template <int TU>
+__device__ __forceinline__ float pick2(const float (&a)[2][TU], int r, int u) {
   float v = a[0][0];
 #pragma unroll
-  for (int i = 0; i < TR; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < TU; ++j) v = (i == r && j == u) ? a[i][j] : v;
   return v;
 }
 
 // ---------------------------------------------------------------------------
-// activation staging: global [nb][K] -> smem, optionally RMS-normalised
-// (nn/blocks.py:32-37: y = (x * rsqrt(mean(x^2) + eps)) * w, two roundings)
-// one warp per utterance row
+// activation staging: [nb][K] rows -> smem, optionally RMS-normalised
+// (nn/blocks.py:32-37: y = (x * rsqrt(mean(x^2) + eps)) * w, two roundings).
+// The whole [nb][K] block is fetched by ALL threads with one wave of 16-byte cp.async (a single
+// L2 round trip, no registers); the norm weights are requested before the wait so both latencies
+// overlap.  src == nullptr: the rows are already in `dst` (layer 0), normalise in place.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int ld_src, int nb, int K,
-                                           float* __restrict__ dst, const float* __restrict__ norm_w,
-                                           float* __restrict__ raw_copy) {
+__device__ __forceinline__ void stage_rows(const float* __restrict__ src, int nb, int K, float* __restrict__ dst,
+                                           const float* __restrict__ norm_w, float* __restrict__ raw_copy) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (src) {
+    const unsigned dst_s = smem_u32(dst);
+    const int total = nb * K;
+    for (int e = threadIdx.x * 4; e < total; e += kThreads * 4) cp_async16(dst_s + (unsigned)e * 4u, src + e);
+  }
+  cp_async_commit();
+  float4 nw[4];  // this lane's norm weights when K <= 512 (else they are read in the loop)
+  const bool pre = norm_w != nullptr && K <= 512;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int k = lane * 4 + c * 128;
+    nw[c] = (pre && k < K) ? __ldg(reinterpret_cast<const float4*>(norm_w + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  cp_async_wait0();
+  __syncthreads();
+  if (!norm_w && !raw_copy) return;
   for (int u = warp; u < nb; u += kWarps) {
-    const float* s = src + (size_t)u * ld_src;
     float* d = dst + (size_t)u * K;
     float ss = 0.f;
     for (int k = lane * 4; k < K; k += 128) {
-      const float4 v = ldcg4(s + k);
-      *reinterpret_cast<float4*>(d + k) = v;
+      const float4 v = *reinterpret_cast<float4*>(d + k);
       if (raw_copy) *reinterpret_cast<float4*>(raw_copy + (size_t)u * K + k) = v;
       ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     if (norm_w) {
       ss = warp_sum(ss);
       const float inv = 1.0f / sqrtf(ss / (float)K + 1e-6f);
-      for (int k = lane * 4; k < K; k += 128) {
-        float4 v = *reinterpret_cast<float4*>(d + k);
-        const float4 w = __ldg(reinterpret_cast<const float4*>(norm_w + k));
-        v.x = (v.x * inv) * w.x;
-        v.y = (v.y * inv) * w.y;
-        v.z = (v.z * inv) * w.z;
-        v.w = (v.w * inv) * w.w;
-        *reinterpret_cast<float4*>(d + k) = v;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int k = lane * 4 + c * 128;
+        if (pre && k < K) {
+          float4 v = *reinterpret_cast<float4*>(d + k);
+          v.x = (v.x * inv) * nw[c].x;
+          v.y = (v.y * inv) * nw[c].y;
+          v.z = (v.z * inv) * nw[c].z;
+          v.w = (v.w * inv) * nw[c].w;
+          *reinterpret_cast<float4*>(d + k) = v;
+        }
       }
-    }
-  }
-}
-
-// in-place RMSNorm of smem rows that were produced locally (layer 0: x = cond + emb)
-__device__ __forceinline__ void norm_rows_inplace(float* __restrict__ buf, int nb, int K,
-                                                  const float* __restrict__ norm_w) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int u = warp; u < nb; u += kWarps) {
-    float* d = buf + (size_t)u * K;
-    float ss = 0.f;
-    for (int k = lane * 4; k < K; k += 128) {
-      const float4 v = *reinterpret_cast<float4*>(d + k);
-      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    }
-    ss = warp_sum(ss);
-    const float inv = 1.0f / sqrtf(ss / (float)K + 1e-6f);
-    for (int k = lane * 4; k < K; k += 128) {
-      float4 v = *reinterpret_cast<float4*>(d + k);
-      const float4 w = __ldg(reinterpret_cast<const float4*>(norm_w + k));
-      v.x = (v.x * inv) * w.x;
-      v.y = (v.y * inv) * w.y;
-      v.z = (v.z * inv) * w.z;
-      v.w = (v.w * inv) * w.w;
-      *reinterpret_cast<float4*>(d + k) = v;
+      if (!pre) {
+        for (int k = lane * 4; k < K; k += 128) {
+          float4 v = *reinterpret_cast<float4*>(d + k);
+          const float4 w = __ldg(reinterpret_cast<const float4*>(norm_w + k));
+          v.x = (v.x * inv) * w.x;
+          v.y = (v.y * inv) * w.y;
+          v.z = (v.z * inv) * w.z;
+          v.w = (v.w * inv) * w.w;
+          *reinterpret_cast<float4*>(d + k) = v;
+        }
+      }
     }
   }
 }
@@ -284,8 +468,8 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 
 // Row partition of N outputs over the team's P CTAs.
 __device__ __forceinline__ void slice(int N, int rank, int P, int& lo, int& hi) {
-  lo = (int)(((long long)N * rank) / P);
-  hi = (int)(((long long)N * (rank + 1)) / P);
+  lo = (int)(((unsigned)N * (unsigned)rank) / (unsigned)P);  // N * P < 2^32 (checked on the host)
+  hi = (int)(((unsigned)N * (unsigned)(rank + 1)) / (unsigned)P);
 }
 
 struct TeamCtx {
@@ -294,208 +478,167 @@ struct TeamCtx {
 };
 
 // ---------------------------------------------------------------------------
-// Stage 1 of a block: h = GLU(RMSNorm(x)); ring push; y = dwconv taps; x' = x + y
-// (nn/blocks.py:156-160, 92-106).  xraw/act: smem [nb][D].
+// Cached text cross-attention core (nn/text.py:101-128): softmax(q.K^T / sqrt(Dh)) . V in fp32
+// over the keys l < text_len.  One CTA per (utterance, head) item; the 16 warps split the keys,
+// lanes split the head dimension (float4 each), so every K/V row is one coalesced load and all
+// loads of an item are independent (one L2 round trip).
+// smem: sc[Lmax] scores, part[kWarps][Dh] per-warp partial outputs, [kWarps][2][4][Dh] K/V rows.
 // ---------------------------------------------------------------------------
-template <int TU, typename WT>
-__device__ __forceinline__ void stage_glu_conv(const ArParams& p, const LayerDev& L, const TeamCtx& tc, int t,
-                                               const float* __restrict__ act, const float* __restrict__ xraw,
-                                               float* __restrict__ xout) {
-  const int D = p.D, Kc = p.Kc;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int c0, c1;
-  slice(D, tc.rank, tc.P, c0, c1);
-  const int n_ut = (tc.nb + TU - 1) / TU;
-  const int n_task = (c1 - c0) * n_ut;
-  const WT* W = reinterpret_cast<const WT*>(L.glu_w);
-  float* ring = p.ring + L.ring_off;
-  const int RL = L.ring_len;
-  for (int task = warp; task < n_task; task += kWarps) {
-    const int c = c0 + task / n_ut;
-    const int u0 = (task % n_ut) * TU;
-    const WT* rows[2] = {W + (size_t)c * D, W + (size_t)(c + D) * D};
-    // clamp the utterance tile to valid smem rows (results of clamped rows are dropped)
-    const int ub = min(u0, max(tc.nb - TU, 0));
-    float out[2][TU];
-    warp_rows<2, TU, WT>(rows, act + (size_t)ub * D, D, D, lane, out);
-    const int u = ub + lane;  // lane < TU handles utterance u
-    if (lane < TU && u >= u0 && u < tc.nb) {
-      const float a = pick2<2, TU>(out, 0, lane) + __ldg(L.glu_b + c);
-      const float gt = pick2<2, TU>(out, 1, lane) + __ldg(L.glu_b + c + D);
-      const float h = a * sigmoid_ref(gt);
-      const int b = tc.b0 + u;
-      float* rb = ring + ((size_t)b * RL) * D + c;
-      // slot of frame tau is tau mod RL; frames before 0 are the zero-initialised ring
-      const int slot_now = t % RL;
-      rb[(size_t)slot_now * D] = h;
-      const float* wt = L.dw_w + (size_t)c * Kc;
-      float y = 0.f;
-      for (int j = 0; j < Kc - 1; ++j) {
-        const int tau = t - (Kc - 1 - j) * L.dil;
-        int sl = tau % RL;
-        if (sl < 0) sl += RL;
-        const float tap = rb[(size_t)sl * D];  // own writes only: plain load
-        y += tap * __ldg(wt + j);
-      }
-      y += h * __ldg(wt + Kc - 1);
-      y += __ldg(L.dw_b + c);
-      xout[(size_t)b * D + c] = xraw[(size_t)u * D + c] + y;
-    }
-  }
-}
-
-// generic epilogue kinds
-enum { EPI_FFN1 = 0, EPI_FFN2 = 1, EPI_Q = 2, EPI_O = 3, EPI_HEAD = 4 };
-
-// out-feature rows [n0,n1) of a [N][K] matrix times the staged activations.
-template <int EPI, int TU, typename WT>
-__device__ __forceinline__ void stage_rows_gemv(const ArParams& p, const TeamCtx& tc, const void* Wv, int N, int K,
-                                                const float* __restrict__ bias, const float* __restrict__ act,
-                                                float* __restrict__ dst, int ld_dst, float scale,
-                                                float* __restrict__ trace) {
-  constexpr int TR = 2;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int n0, n1;
-  slice(N, tc.rank, tc.P, n0, n1);
-  const int n_rt = (n1 - n0 + TR - 1) / TR;
-  const int n_ut = (tc.nb + TU - 1) / TU;
-  const WT* W = reinterpret_cast<const WT*>(Wv);
-  for (int task = warp; task < n_rt * n_ut; task += kWarps) {
-    const int r0 = n0 + (task / n_ut) * TR;
-    const int u0 = (task % n_ut) * TU;
-    const WT* rows[TR];
-#pragma unroll
-    for (int i = 0; i < TR; ++i) rows[i] = W + (size_t)min(r0 + i, n1 - 1) * K;
-    const int ub = min(u0, max(tc.nb - TU, 0));
-    float out[TR][TU];
-    warp_rows<TR, TU, WT>(rows, act + (size_t)ub * K, K, K, lane, out);
-    const int i = lane / TU, uu = lane % TU;
-    const int r = r0 + i, u = ub + uu;
-    if (lane < TR * TU && r < n1 && u >= u0 && u < tc.nb) {
-      float v = pick2<TR, TU>(out, i, uu);
-      const int b = tc.b0 + u;
-      float* d = dst + (size_t)b * ld_dst + r;
-      if (EPI == EPI_FFN1) {
-        *d = gelu_erf(v + __ldg(bias + r));
-      } else if (EPI == EPI_FFN2) {
-        const float nv = ldcg1(d) + (v + __ldg(bias + r));
-        *d = nv;
-        if (trace) trace[(size_t)b * ld_dst + r] = nv;
-      } else if (EPI == EPI_Q) {
-        *d = v;
-      } else if (EPI == EPI_O) {
-        const float nv = ldcg1(d) + scale * v;
-        *d = nv;
-        if (trace) trace[(size_t)b * ld_dst + r] = nv;
-      } else {  // EPI_HEAD
-        v += __ldg(bias + r);
-        *d = v;
-        if (trace) trace[(size_t)b * p.V + r] = v;
-      }
-    }
-  }
-}
-
-// dispatch on the utterance-tile width
-template <int EPI, typename WT>
-__device__ __forceinline__ void gemv_dispatch(const ArParams& p, const TeamCtx& tc, const void* W, int N, int K,
-                                              const float* bias, const float* act, float* dst, int ld_dst,
-                                              float scale, float* trace) {
-  if (tc.nb >= 8)
-    stage_rows_gemv<EPI, 8, WT>(p, tc, W, N, K, bias, act, dst, ld_dst, scale, trace);
-  else if (tc.nb >= 4)
-    stage_rows_gemv<EPI, 4, WT>(p, tc, W, N, K, bias, act, dst, ld_dst, scale, trace);
-  else if (tc.nb >= 2)
-    stage_rows_gemv<EPI, 2, WT>(p, tc, W, N, K, bias, act, dst, ld_dst, scale, trace);
-  else
-    stage_rows_gemv<EPI, 1, WT>(p, tc, W, N, K, bias, act, dst, ld_dst, scale, trace);
-}
-
-// ---------------------------------------------------------------------------
-// Cached text cross-attention core (nn/text.py:101-128): one warp per
-// (utterance, head).  scores in smem (per-warp slice of Lmax floats).
-// softmax(q.K^T / sqrt(Dh)) . V, fp32, keys l < text_len only.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void stage_attention(const ArParams& p, const LayerDev& L, const TeamCtx& tc,
-                                                float* __restrict__ smem_scores) {
+__device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank, int P, int b0, int nb,
+                                             float* __restrict__ smem) {
+  const LayerDev& L = p.layer[li];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, Dh = p.Dh, D = p.D, Lmax = p.Lmax;
-  float* sc = smem_scores + (size_t)warp * (Lmax + Dh);
-  float* qs = sc + Lmax;
+  float* sc = smem;
+  float* part = smem + Lmax;
+  const unsigned kv_s = smem_u32(part + (size_t)kWarps * Dh);
   const float scale = 1.0f / sqrtf((float)Dh);
-  const int n_items = tc.nb * H;
-  for (int item = tc.rank * kWarps + warp; item < n_items; item += tc.P * kWarps) {
+  const int n_items = nb * H;
+  const int d4 = lane * 4;
+  const bool act_lane = d4 < Dh;
+  constexpr int PF = 4;
+  for (int item = rank; item < n_items; item += P) {
     const int u = item / H, h = item % H;
-    const int b = tc.b0 + u;
+    const int b = b0 + u;
     const int len = p.text_len[b];
-    const float* q = p.qbuf + (size_t)b * D + (size_t)h * Dh;
     const size_t kv_off = ((((size_t)L.attn_slot * p.B + b) * H + h) * Lmax) * Dh;
     const float* Kp = p.kc + kv_off;
     const float* Vp = p.vc + kv_off;
-    for (int d = lane; d < Dh; d += 32) qs[d] = ldcg1(q + d);
-    __syncwarp();
-    // scores: lane handles keys lane, lane+32, ...
-    float mx = -INFINITY;
-    for (int l = lane; l < len; l += 32) {
-      const float* kr = Kp + (size_t)l * Dh;
-      float s = 0.f;
-      for (int d = 0; d < Dh; d += 4) {
-        const float4 kk = __ldg(reinterpret_cast<const float4*>(kr + d));
-        const float4 qq = *reinterpret_cast<const float4*>(qs + d);
-        s += kk.x * qq.x + kk.y * qq.y + kk.z * qq.z + kk.w * qq.w;
+    // q (registers) and the first PF K/V rows of this warp (cp.async -> shared, no registers held)
+    // are requested together
+    const unsigned kS = kv_s + (unsigned)warp * (unsigned)(2 * PF * Dh * 4);
+    const unsigned vS = kS + (unsigned)(PF * Dh * 4);
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act_lane) {
+#pragma unroll 1
+      for (int i = 0; i < PF; ++i) {
+        const int l = warp + i * kWarps;
+        if (l < len) {
+          cp_async16(kS + (unsigned)(i * Dh + d4) * 4u, Kp + (size_t)l * Dh + d4);
+          cp_async16(vS + (unsigned)(i * Dh + d4) * 4u, Vp + (size_t)l * Dh + d4);
+        }
       }
-      s *= scale;
-      sc[l] = s;
-      mx = fmaxf(mx, s);
+      q4 = ldcg4(p.qbuf + (size_t)b * D + (size_t)h * Dh + d4);
     }
+    cp_async_commit();
+    cp_async_wait0();
+    // phase 1: scores of this warp's keys
+    {
+      int i = 0;
+#pragma unroll 1
+      for (int l = warp; l < len; l += kWarps, ++i) {
+        float s = 0.f;
+        if (act_lane) {
+          const float4 kk = (i < PF) ? lds128(kS + (unsigned)(i * Dh + d4) * 4u)
+                                     : __ldg(reinterpret_cast<const float4*>(Kp + (size_t)l * Dh + d4));
+          s = kk.x * q4.x + kk.y * q4.y + kk.z * q4.z + kk.w * q4.w;
+        }
+        s = warp_sum(s);
+        if (lane == 0) sc[l] = s * scale;
+      }
+    }
+    __syncthreads();
+    // phase 2: max / sum over all keys (every warp, redundantly), weighted V rows of own keys
+    float mx = -INFINITY;
+    for (int l = lane; l < len; l += 32) mx = fmaxf(mx, sc[l]);
     mx = warp_max(mx);
     float sum = 0.f;
-    for (int l = lane; l < len; l += 32) {
-      const float e = expf(sc[l] - mx);
-      sc[l] = e;
-      sum += e;
-    }
+    for (int l = lane; l < len; l += 32) sum += expf(sc[l] - mx);
     sum = warp_sum(sum);
-    __syncwarp();
-    // out[d] = sum_l p_l V[l][d] / sum ; lane handles d = lane, lane+32, ...
-    for (int d = lane; d < Dh; d += 32) {
-      float o = 0.f;
-      for (int l = 0; l < len; ++l) o += sc[l] * __ldg(Vp + (size_t)l * Dh + d);
-      o = o / sum;
-      if (!isfinite(o)) o = 0.f;  // nan_to_num(nan=0, posinf=0, neginf=0), nn/text.py:128
-      p.abuf[(size_t)b * D + (size_t)h * Dh + d] = o;
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    {
+      int i = 0;
+#pragma unroll 1
+      for (int l = warp; l < len; l += kWarps, ++i) {
+        const float e = expf(sc[l] - mx);
+        if (act_lane) {
+          const float4 vv = (i < PF) ? lds128(vS + (unsigned)(i * Dh + d4) * 4u)
+                                     : __ldg(reinterpret_cast<const float4*>(Vp + (size_t)l * Dh + d4));
+          o.x += e * vv.x;
+          o.y += e * vv.y;
+          o.z += e * vv.z;
+          o.w += e * vv.w;
+        }
+      }
     }
-    __syncwarp();
+    if (act_lane) *reinterpret_cast<float4*>(part + (size_t)warp * Dh + d4) = o;
+    __syncthreads();
+    // phase 3: fixed-order sum of the warp partials, normalise, nan_to_num (nn/text.py:128)
+    for (int d = threadIdx.x; d < Dh; d += kThreads) {
+      float acc = 0.f;
+#pragma unroll 1
+      for (int w = 0; w < kWarps; ++w) acc += part[(size_t)w * Dh + d];
+      acc = acc / sum;
+      if (!isfinite(acc)) acc = 0.f;
+      p.abuf[(size_t)b * D + (size_t)h * Dh + d] = acc;
+    }
+    __syncthreads();
   }
 }
 
 // ---------------------------------------------------------------------------
 // Sampler (sampling.py:24-93) + bookkeeping (model.py:293-305), one CTA per utterance.
+// Probabilities live in shared memory; every loop over the vocabulary is a rolled loop
+// (v = tid, tid+512, ...) to keep the code small.
 // ---------------------------------------------------------------------------
 struct SamplerSmem {
   float red_v[kWarps];
   int red_i[kWarps];
-  float topv[kMaxTopK];
-  int topi[kMaxTopK];
+  float topv[kCand];  // unordered candidates; empty slots hold (-1, INT_MAX)
+  int topi[kCand];
+  float sortv[kMaxTopK];  // the best kMaxTopK of them, best first
+  int sorti[kMaxTopK];
   float bc_f;
   int bc_i;
   int fallback;
+  unsigned n_cand;
+  // radix select (cold path)
+  unsigned hist[2048];
+  unsigned wtot[kWarps];
+  unsigned sel_digit, sel_need;
+  unsigned n_gt, n_eq, n_eq2;
 };
 
-__device__ __forceinline__ void argmax_pair(float& v, int& i, float ov, int oi) {
-  // larger value wins; ties -> lower index (torch.argmax / topk / sort keep the first)
-  if (ov > v || (ov == v && oi < i)) {
-    v = ov;
-    i = oi;
-  }
+__device__ __forceinline__ bool cand_before(float av, int ai, float bv, int bi) {
+  // larger value first; ties -> lower index (torch.argmax / topk / sort keep the first)
+  return av > bv || (av == bv && ai < bi);
 }
 __device__ __forceinline__ void warp_argmax(float& v, int& i) {
-#pragma unroll
+#pragma unroll 1
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, v, o);
     const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-    argmax_pair(v, i, ov, oi);
+    if (cand_before(ov, oi, v, i)) {
+      v = ov;
+      i = oi;
+    }
   }
+}
+
+// All 512 threads order the kCand candidate slots by counting: rank(i) = #{j : slot j comes before
+// slot i} (value desc, index asc); 4 threads per slot, 32 comparisons each, then the best
+// kMaxTopK are scattered to sortv/sorti.  Empty slots (-1, INT_MAX) tie with each other and rank
+// after every real candidate.  ~60 instructions, no single-warp serial section.
+__device__ __forceinline__ void rank_order(SamplerSmem& sm) {
+  const int tid = threadIdx.x;
+  if (tid < kMaxTopK) {
+    sm.sortv[tid] = -1.f;
+    sm.sorti[tid] = 0x7fffffff;
+  }
+  __syncthreads();
+  const int i = tid >> 2, g = tid & 3;
+  const float vi = sm.topv[i];
+  const int ii = sm.topi[i];
+  int cnt = 0;
+#pragma unroll 4
+  for (int j = g * (kCand / 4); j < (g + 1) * (kCand / 4); ++j) cnt += cand_before(sm.topv[j], sm.topi[j], vi, ii) ? 1 : 0;
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
+  cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
+  if (g == 0 && cnt < kMaxTopK && ii != 0x7fffffff) {
+    sm.sortv[cnt] = vi;
+    sm.sorti[cnt] = ii;
+  }
+  __syncthreads();
 }
 
 // block-wide argmax; result valid in every thread
@@ -520,7 +663,6 @@ __device__ __forceinline__ void block_argmax(float& v, int& i, SamplerSmem& sm) 
   v = sm.bc_f;
   i = sm.bc_i;
 }
-
 __device__ __forceinline__ float block_max(float v, SamplerSmem& sm) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   v = warp_max(v);
@@ -542,96 +684,264 @@ __device__ __forceinline__ float block_sum(float v, SamplerSmem& sm) {
   return r;
 }
 
-// sx: smem [Vpad] floats, flags: smem [Vpad] bytes
-__device__ __forceinline__ void sample_utterance(const ArParams& p, int b, int t, float* __restrict__ sx,
-                                                 unsigned char* __restrict__ flags, SamplerSmem& sm) {
+// COLD: exact top-kk of the candidates {v : sp[v] >= t_lb} when they do not fit the 64 slots:
+// MSB-first radix select on the float bits (p >= 0, so uint order == float order), 11+11+9 bits.
+// Leaves the kk selected (value, index) pairs, unsorted, in sm.topv / sm.topi.
+__device__ __noinline__ void topk_radix_cold(const float* __restrict__ sp, int V, int kk, float t_lb, SamplerSmem& sm) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int V = p.V;
-  UttState st = p.st[b];
-  const SamplingDev sp = p.samp[b];
-  if (st.done) return;  // CTA-uniform
-  const float top_p = st.recovery ? sp.rec_top_p : sp.top_p;
-  const float temp = st.recovery ? sp.rec_temp : sp.temperature;
-  const float rep = sp.rep_pen;
-  const int* hist = p.tokens + (size_t)b * p.steps;
-  const int hlen = st.len;
-
-  // 1. logits -> nan_to_num -> /T ; repetition-penalty flags from set(hist[-50:])
-  for (int v = tid; v < p.Vpad; v += kThreads) flags[v] = 0;
-  __syncthreads();
-  if (rep != 1.0f && tid < 50 && tid < hlen) {
-    const int tok = hist[hlen - 1 - tid];
-    if (tok >= 0 && tok < V) flags[tok] = 1;
-  }
-  __syncthreads();
-  const float* lg = p.logits + (size_t)b * p.Vpad;
-  float xv[kSampNPT];
-  float mx = -INFINITY;
-#pragma unroll
-  for (int i = 0; i < kSampNPT; ++i) {
-    const int v = tid + i * kThreads;
-    float x = -INFINITY;
-    if (v < V) {
-      x = ldcg1(lg + v);
-      if (isnan(x)) x = -1e9f;
-      else if (isinf(x)) x = x > 0.f ? 1e9f : -1e9f;
-      if (temp != 0.0f && temp != 1.0f) x = x / temp;
-      if (flags[v]) x = (x < 0.f) ? x * rep : x / rep;
-      sx[v] = x;
-      mx = fmaxf(mx, x);
+  unsigned prefix = 0, pmask = 0, need = (unsigned)kk;
+  for (int pass = 0; pass < 3; ++pass) {
+    const int shift = pass == 0 ? 20 : (pass == 1 ? 9 : 0);
+    const int nbits = pass == 2 ? 9 : 11;
+    const int NB = 1 << nbits;
+    const int PER = NB / kThreads > 0 ? NB / kThreads : 1;
+    for (int i = tid; i < NB; i += kThreads) sm.hist[i] = 0;
+    __syncthreads();
+    for (int v = tid; v < V; v += kThreads) {
+      const float q = sp[v];
+      const unsigned key = __float_as_uint(q);
+      if (q >= t_lb && (key & pmask) == prefix) atomicAdd(&sm.hist[(key >> shift) & (NB - 1)], 1u);
     }
-    xv[i] = x;
-  }
-  // 2. softmax + nan_to_num
-  mx = block_max(mx, sm);
-  float pv[kSampNPT];
-  float se = 0.f;
-#pragma unroll
-  for (int i = 0; i < kSampNPT; ++i) {
-    const int v = tid + i * kThreads;
-    pv[i] = (v < V) ? expf(xv[i] - mx) : 0.f;
-    se += pv[i];
-  }
-  se = block_sum(se, sm);
-#pragma unroll
-  for (int i = 0; i < kSampNPT; ++i) {
-    const int v = tid + i * kThreads;
-    float q = pv[i] / se;
-    if (!isfinite(q)) q = 0.f;
-    pv[i] = (v < V) ? q : -1.f;  // -1 = not a candidate
-  }
-  // 3. top-k: kk passes of block argmax over the remaining candidates, value desc, index asc
-  const int kk = min(min(sp.top_k, V), kMaxTopK);
-  for (int j = 0; j < kk; ++j) {
-    float bv = -1.f;
-    int bi = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < kSampNPT; ++i) {
-      if (pv[i] > bv) {
-        bv = pv[i];
-        bi = tid + i * kThreads;
+    __syncthreads();
+    unsigned mine = 0;
+    if (tid * PER < NB)
+      for (int j = 0; j < PER; ++j) mine += sm.hist[tid * PER + j];
+    unsigned x = mine;  // inclusive suffix sum within the warp (bins above mine)
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_down_sync(0xffffffffu, x, o);
+      if (lane + o < 32) x += y;
+    }
+    if (lane == 0) sm.wtot[warp] = x;
+    __syncthreads();
+    unsigned higher = 0;
+    for (int w = warp + 1; w < kWarps; ++w) higher += sm.wtot[w];
+    const unsigned incl = x + higher, excl = incl - mine;
+    if (excl < need && need <= incl) {  // exactly one thread
+      unsigned run = excl;
+      for (int j = PER - 1; j >= 0; --j) {
+        const unsigned c = sm.hist[tid * PER + j];
+        if (run + c >= need) {
+          sm.sel_digit = (unsigned)(tid * PER + j);
+          sm.sel_need = need - run;
+          break;
+        }
+        run += c;
       }
     }
-    block_argmax(bv, bi, sm);
-    if (tid == 0) {
-      sm.topv[j] = bv;
-      sm.topi[j] = bi;
-    }
-    if ((bi % kThreads) == tid) {
-      const int slot = bi / kThreads;
-#pragma unroll
-      for (int i = 0; i < kSampNPT; ++i)
-        if (i == slot) pv[i] = -1.f;
+    __syncthreads();
+    prefix |= sm.sel_digit << shift;
+    pmask |= (unsigned)(NB - 1) << shift;
+    need = sm.sel_need;
+    __syncthreads();
+  }
+  const unsigned T = prefix;
+  const int n_gt_expect = kk - (int)need;
+  if (tid == 0) {
+    sm.n_gt = 0;
+    sm.n_eq = 0;
+    sm.n_eq2 = 0;
+  }
+  __syncthreads();
+  for (int v = tid; v < V; v += kThreads) {
+    const float q = sp[v];
+    const unsigned key = __float_as_uint(q);
+    if (q >= t_lb && key > T) {
+      const unsigned slot = atomicAdd(&sm.n_gt, 1u);
+      sm.topv[slot] = q;
+      sm.topi[slot] = v;
+    } else if (q >= t_lb && key == T) {
+      atomicAdd(&sm.n_eq, 1u);
     }
   }
   __syncthreads();
+  if (sm.n_eq == need) {  // no tie straddles the cut
+    for (int v = tid; v < V; v += kThreads) {
+      const float q = sp[v];
+      if (q >= t_lb && __float_as_uint(q) == T) {
+        const unsigned slot = n_gt_expect + atomicAdd(&sm.n_eq2, 1u);
+        sm.topv[slot] = q;
+        sm.topi[slot] = v;
+      }
+    }
+  } else {  // ties at the threshold: take the lowest indices, one block argmax per pick
+    int taken_below = -1;  // indices <= taken_below are already taken
+    for (unsigned j = 0; j < need; ++j) {
+      float bv = -1.f;
+      int bi = 0x7fffffff;
+      for (int v = tid; v < V; v += kThreads) {
+        if (v > taken_below && __float_as_uint(sp[v]) == T && sp[v] >= t_lb && bv < 0.f) {
+          bv = 1.f;
+          bi = v;
+        }
+      }
+      block_argmax(bv, bi, sm);
+      if (tid == 0) {
+        sm.topv[n_gt_expect + j] = __uint_as_float(T);
+        sm.topi[n_gt_expect + j] = bi;
+      }
+      taken_below = bi;
+    }
+  }
+  __syncthreads();
+}
+
+// COLD: argmax of the penalised, temperature-scaled logits (sampling.py:65,80,90)
+__device__ __noinline__ int argmax_logits_cold(const float* __restrict__ sx, int V, SamplerSmem& sm) {
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += kThreads)
+    if (cand_before(sx[v], v, bv, bi)) {
+      bv = sx[v];
+      bi = v;
+    }
+  __syncthreads();
+  block_argmax(bv, bi, sm);
+  return bi;
+}
+
+// sx, sp: smem [Vpad] floats; flags: smem [Vpad] bytes
+__device__ __noinline__ void sample_utterance(const ArParams& p, int b, int t, float* __restrict__ sx,
+                                              float* __restrict__ sp, unsigned char* __restrict__ flags,
+                                              SamplerSmem& sm) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int V = p.V;
+  long long* dbg = (p.timing && t == p.timing_step && tid == 0) ? p.timing + (size_t)blockIdx.x * kTimingSlots + 160 : nullptr;
+  int dn = 0;
+#define SMARK() do { if (dbg) dbg[dn++] = clock64(); } while (0)
+  SMARK();
+  const UttState st = p.st[b];
+  const SamplingDev spar = p.samp[b];
+  int* toks = p.tokens + (size_t)b * p.steps;
+  if (st.done) return;  // CTA-uniform
+  const float top_p = st.recovery ? spar.rec_top_p : spar.top_p;
+  const float temp = st.recovery ? spar.rec_temp : spar.temperature;
+  const float rep = spar.rep_pen;
+  const int hlen = st.len;
+
+  // 1. repetition-penalty flags from set(hist[-50:]); logits -> nan_to_num -> /T -> penalty.
+  //    The logits row is fetched with one wave of 16-byte cp.async (a single L2 round trip).
+  const float* lg = p.logits + (size_t)b * p.Vpad;
+  {
+    const unsigned sx_s = smem_u32(sx);
+    for (int v = tid * 4; v < p.Vpad; v += kThreads * 4) cp_async16(sx_s + (unsigned)v * 4u, lg + v);
+    cp_async_commit();
+  }
+  for (int v = tid; v < p.Vpad; v += kThreads) flags[v] = 0;
+  if (tid < kCand) {
+    sm.topv[tid] = -1.f;
+    sm.topi[tid] = 0x7fffffff;
+  }
+  if (tid == 0) sm.n_cand = 0;
+  __syncthreads();
+  if (rep != 1.0f && tid < 50 && tid < hlen) {
+    const int tok = toks[hlen - 1 - tid];
+    if (tok >= 0 && tok < V) flags[tok] = 1;
+  }
+  cp_async_wait0();
+  __syncthreads();
+  SMARK();  // 1: state + logits fetched
+  float mx = -INFINITY;
+#pragma unroll 1
+  for (int v = tid; v < V; v += kThreads) {
+    float x = sx[v];
+    if (isnan(x)) x = -1e9f;
+    else if (isinf(x)) x = x > 0.f ? 1e9f : -1e9f;
+    if (temp != 0.0f && temp != 1.0f) x = x / temp;
+    if (flags[v]) x = (x < 0.f) ? x * rep : x / rep;
+    sx[v] = x;
+    mx = fmaxf(mx, x);
+  }
+  // 2. softmax + nan_to_num; each thread remembers its largest probability
+  SMARK();  // 2: penalised logits
+  mx = block_max(mx, sm);
+  SMARK();  // 3: block max
+  float se = 0.f;
+#pragma unroll 1
+  for (int v = tid; v < V; v += kThreads) {
+    const float e = expf(sx[v] - mx);
+    sp[v] = e;
+    se += e;
+  }
+  se = block_sum(se, sm);
+  SMARK();  // 4: exp + block sum
+  float lmax = -1.f;
+  int limax = 0x7fffffff;
+#pragma unroll 1
+  for (int v = tid; v < V; v += kThreads) {
+    float q = sp[v] / se;
+    if (!isfinite(q)) q = 0.f;
+    sp[v] = q;
+    if (q > lmax) {
+      lmax = q;
+      limax = v;
+    }
+  }
+  // 3. top-k.  (a) a lower bound T_lb of the kk-th largest probability: every warp extracts the
+  //    r = ceil(kk/16) largest of its lanes' maxima; those 16*r <= 64 values are real elements, so the
+  //    kk-th largest of them is <= the true threshold.  (b) elements >= T_lb are the only candidates
+  //    (~1.5*kk of them on typical data): if they fit the 64 slots, one warp sort both selects and
+  //    orders them; otherwise the exact radix select (cold) runs.  Order everywhere: value desc,
+  //    index asc (topk/sort keep the first of a tie).
+  const int kk = min(min(spar.top_k, V), kMaxTopK);
+  SMARK();  // 5: probabilities
+  {
+    const int rr = (kk + kWarps - 1) / kWarps;  // <= 4
+    float cv = lmax;
+    int ci = limax;
+#pragma unroll 1
+    for (int r = 0; r < rr; ++r) {
+      float bv = cv;
+      int bi = ci;
+      warp_argmax(bv, bi);
+      if (lane == 0) {
+        sm.topv[warp * rr + r] = bv;
+        sm.topi[warp * rr + r] = bi;
+      }
+      if (ci == bi) cv = -1.f, ci = 0x7fffffff;  // the winner lane retires its maximum
+    }
+  }
+  __syncthreads();
+  rank_order(sm);
+  SMARK();  // 6: lower bound (lane maxima ranked)
+  const float t_lb = sm.sortv[kk - 1];
+  __syncthreads();  // topv is rewritten below
+  if (tid < kCand) {
+    sm.topv[tid] = -1.f;
+    sm.topi[tid] = 0x7fffffff;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int v = tid; v < V; v += kThreads) {
+    const float q = sp[v];
+    if (q >= t_lb) {
+      const unsigned slot = atomicAdd(&sm.n_cand, 1u);
+      if (slot < (unsigned)kCand) {
+        sm.topv[slot] = q;
+        sm.topi[slot] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (sm.n_cand > (unsigned)kCand) {
+    __syncthreads();
+    if (tid < kCand) {
+      sm.topv[tid] = -1.f;
+      sm.topi[tid] = 0x7fffffff;
+    }
+    __syncthreads();
+    topk_radix_cold(sp, V, kk, t_lb, sm);
+  }
+  rank_order(sm);
+  SMARK();  // 7: candidates compacted
   // 4. renormalise, top-p, draw: warp 0, two candidates per lane (j = lane, lane + 32)
   if (warp == 0) {
     const int j0 = lane, j1 = lane + 32;
-    float a0 = j0 < kk ? sm.topv[j0] : 0.f;
-    float a1 = j1 < kk ? sm.topv[j1] : 0.f;
-    const int i0 = j0 < kk ? sm.topi[j0] : 0x7fffffff;
-    const int i1 = j1 < kk ? sm.topi[j1] : 0x7fffffff;
+    const float sv0 = sm.sortv[j0], sv1 = sm.sortv[j1];
+    const int si0 = sm.sorti[j0], si1 = sm.sorti[j1];
+    float a0 = j0 < kk ? sv0 : 0.f;
+    float a1 = j1 < kk ? sv1 : 0.f;
+    const int i0 = j0 < kk ? si0 : 0x7fffffff;
+    const int i1 = j1 < kk ? si1 : 0x7fffffff;
     const float s1 = (float)warp_sum_d((double)a0 + (double)a1);
     int fallback = 0;
     int token = 0;
@@ -647,14 +957,14 @@ __device__ __forceinline__ void sample_utterance(const ArParams& p, int b, int t
         // cumsum in double, rounded to float at each position (ATen CPU cumsum accumulates in
         // acc_type<float> = double); inclusive scan over lanes, first the low 32, then the high 32
         double c0 = (double)a0;
-#pragma unroll
+#pragma unroll 1
         for (int o = 1; o < 32; o <<= 1) {
           const double n = __shfl_up_sync(0xffffffffu, c0, o);
           if (lane >= o) c0 += n;
         }
         const double tot0 = __shfl_sync(0xffffffffu, c0, 31);
         double c1 = (double)a1;
-#pragma unroll
+#pragma unroll 1
         for (int o = 1; o < 32; o <<= 1) {
           const double n = __shfl_up_sync(0xffffffffu, c1, o);
           if (lane >= o) c1 += n;
@@ -662,7 +972,7 @@ __device__ __forceinline__ void sample_utterance(const ArParams& p, int b, int t
         c1 += tot0;
         const float cf0 = (float)c0, cf1 = (float)c1;
         // remove[j] = cum[j-1] > top_p, remove[0] = False (sampling.py:72-74)
-        float prev0 = __shfl_up_sync(0xffffffffu, cf0, 1);
+        const float prev0 = __shfl_up_sync(0xffffffffu, cf0, 1);
         float prev1 = __shfl_up_sync(0xffffffffu, cf1, 1);
         const float last0 = __shfl_sync(0xffffffffu, cf0, 31);
         if (lane == 0) prev1 = last0;
@@ -697,18 +1007,14 @@ __device__ __forceinline__ void sample_utterance(const ArParams& p, int b, int t
         }
       }
       if (!fallback) {
-        float bv = r0;
-        int bk = t0, bt = i0;
+        float bv = j0 < kk ? r0 : -1.f;
+        int bk = j0 < kk ? t0 : 0x7fffffff, bt = i0;
         if (j1 < kk && (r1 > bv || (r1 == bv && t1 < bk))) {
           bv = r1;
           bk = t1;
           bt = i1;
         }
-        if (j0 >= kk) {
-          bv = -1.f;
-          bk = 0x7fffffff;
-        }
-#pragma unroll
+#pragma unroll 1
         for (int o = 16; o > 0; o >>= 1) {
           const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
           const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
@@ -728,23 +1034,11 @@ __device__ __forceinline__ void sample_utterance(const ArParams& p, int b, int t
     }
   }
   __syncthreads();
+  SMARK();  // 8: sorted, top-p, drawn
   int token = sm.bc_i;
-  if (sm.fallback) {
-    // argmax of the penalised, temperature-scaled logits (sampling.py:65,80,90)
-    float bv = -INFINITY;
-    int bi = 0x7fffffff;
-#pragma unroll
-    for (int i = 0; i < kSampNPT; ++i) {
-      const int v = tid + i * kThreads;
-      if (v < V) argmax_pair(bv, bi, xv[i], v);
-    }
-    __syncthreads();
-    block_argmax(bv, bi, sm);
-    token = bi;
-  }
+  if (sm.fallback) token = argmax_logits_cold(sx, V, sm);
   // 5. bookkeeping: one warp (repeated_tail needs lanes 3..16)
   if (warp == 0) {
-    int* toks = p.tokens + (size_t)b * p.steps;
     if (lane == 0) p.sampled[(size_t)b * p.steps + t] = token;
     if (p.forced) token = p.forced[(size_t)b * p.steps + t];
     if (lane == 0) toks[t] = token;
@@ -770,10 +1064,10 @@ __device__ __forceinline__ void sample_utterance(const ArParams& p, int b, int t
     if (lane == 0) {
       const int streak = (st.last >= 0 && token == st.last) ? st.streak + 1 : 0;
       int recovery = 0;
-      if (sp.anti_loop && (any_rep || streak >= sp.loop_streak)) recovery = 1;
+      if (spar.anti_loop && (any_rep || streak >= spar.loop_streak)) recovery = 1;
       const bool is_eos = token == p.eos_id;
       int done = 0;
-      if (is_eos && (sp.stop_on_first_eos || len >= sp.min_gen)) done = 1;
+      if (is_eos && (spar.stop_on_first_eos || len >= spar.min_gen)) done = 1;
       if (len >= p.steps) done = 1;
       UttState ns;
       ns.len = len;
@@ -787,22 +1081,19 @@ __device__ __forceinline__ void sample_utterance(const ArParams& p, int b, int t
       p.done[b] = done;
     }
   }
+  SMARK();  // 9: bookkeeping
+#undef SMARK
 }
 
 // ---------------------------------------------------------------------------
-// the persistent kernel
+// the persistent kernel: an interpreter over p.prog with one shared GEMV body
 // ---------------------------------------------------------------------------
-template <int TU, typename WT>
-__device__ __forceinline__ void glu_dispatch_one(const ArParams& p, const LayerDev& L, const TeamCtx& tc, int t,
-                                                 const float* act, const float* xraw, float* xout) {
-  stage_glu_conv<TU, WT>(p, L, tc, t, act, xraw, xout);
-}
-
-template <typename WT>
+template <typename WT, int TU>
 __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid_constant__ ArParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ SamplerSmem ssm;
-  float* act = reinterpret_cast<float*>(smem_raw);  // [nb][max(D,F)] (or 2 x [nb][D])
+  __shared__ __align__(8) unsigned long long wbars[kMaxWBuf];
+  float* act = reinterpret_cast<float*>(smem_raw);  // [nb][max(D,F)] (or 2 x [nb][D] + tap scratch)
   TeamCtx tc;
   tc.team = blockIdx.x / p.P;
   tc.rank = blockIdx.x % p.P;
@@ -811,11 +1102,42 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
   tc.b0 = tc.team * p.Bt;
   tc.nb = min(p.Bt, p.B - tc.b0);
   if (tc.nb <= 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned* bar = p.barrier + (size_t)tc.team * 32;
   unsigned epoch = 0;
   const int D = p.D, F = p.F;
-  float* xraw = act + (size_t)tc.nb * D;  // second [nb][D] buffer (stage 1 only)
+  float* xraw = act + (size_t)tc.nb * D;  // second [nb][D] buffer (GLU stage only)
+  const unsigned act_s = smem_u32(act);
+  const unsigned scratch_s = act_s + (unsigned)(2 * tc.nb * D) * 4u;  // GLU stage: per-warp dwconv tap rows
+  const int n_ut = (tc.nb + TU - 1) / TU;
+  // ---- weight ring: [act region][nbuf x wbuf][tile table]
+  WeightRing ring;
+  {
+    TileDesc* tab = reinterpret_cast<TileDesc*>(smem_raw + p.act_bytes + (size_t)p.nbuf * p.wbuf_bytes);
+    const int nt = p.n_tiles[tc.rank];
+    const TileDesc* gt = p.tiles + (size_t)tc.rank * kMaxTilesPerStep;
+    for (int i = threadIdx.x; i < nt; i += kThreads) tab[i] = gt[i];
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < p.nbuf; ++i) mbar_init(&wbars[i], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    ring.bars = wbars;
+    ring.base = smem_u32(smem_raw + p.act_bytes);
+    ring.wbuf = (unsigned)p.wbuf_bytes;
+    ring.nbuf = p.nbuf;
+    ring.table = tab;
+    ring.n_tiles = nt;
+    ring.start((p.t_end - p.t_begin) * nt);
+  }
+  // per-stage tile counts of this rank + per-layer conv phase bookkeeping (shared, refreshed every step)
+  __shared__ unsigned char stage_tiles[kMaxStages];
+  __shared__ int conv_phase[kMaxLayers], conv_slot[kMaxLayers];
+  for (int i = threadIdx.x; i < p.n_stage; i += kThreads)
+    stage_tiles[i] = p.stage_tiles[(size_t)tc.rank * kMaxStages + i];
+  __syncthreads();
 
+#pragma unroll 1
   for (int t = p.t_begin; t < p.t_end; ++t) {
     // team-uniform early exit: all utterances of the team finished
     {
@@ -823,106 +1145,199 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
       for (int u = 0; u < tc.nb; ++u) live |= (__ldcg(&p.st[tc.b0 + u].done) == 0);
       if (!live) break;
     }
+    if (threadIdx.x < p.n_layers) {  // the only integer divisions of the step: one thread per layer
+      const int dl = p.layer[threadIdx.x].dil;
+      conv_phase[threadIdx.x] = t % dl;
+      conv_slot[threadIdx.x] = (t / dl) % p.Kc;
+    }
+    __syncthreads();
     float* cur = p.xa;
     float* nxt = p.xb;
     Stamp ts;
     ts.buf = (p.timing && t == p.timing_step && threadIdx.x == 0) ? p.timing + (size_t)blockIdx.x * kTimingSlots : nullptr;
     ts.n = 0;
     ts.mark();
-    for (int li = 0; li < p.n_layers; ++li) {
-      const LayerDev& L = p.layer[li];
-      // ---- stage 1: x (or cond+emb) -> RMSNorm -> GLU -> ring/dwconv -> nxt
-      if (li == 0) {
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int u = warp; u < tc.nb; u += kWarps) {
-          const int b = tc.b0 + u;
-          const int row = (t == 0) ? p.V : __ldcg(&p.tokens[(size_t)b * p.steps + t - 1]);
-          const float* cr = p.cond + ((size_t)b * p.steps + t) * D;
-          const float* er = p.emb + (size_t)row * D;
-          for (int k = lane * 4; k < D; k += 128) {
-            const float4 c = __ldg(reinterpret_cast<const float4*>(cr + k));
-            const float4 e = __ldg(reinterpret_cast<const float4*>(er + k));
-            const float4 x = make_float4(c.x + e.x, c.y + e.y, c.z + e.z, c.w + e.w);
-            *reinterpret_cast<float4*>(act + (size_t)u * D + k) = x;
-            *reinterpret_cast<float4*>(xraw + (size_t)u * D + k) = x;
+#pragma unroll 1
+    for (int si = 0; si < p.n_stage; ++si) {
+      const int kind = p.prog[si].kind, li = p.prog[si].layer;
+      if (kind <= K_HEAD) {
+        const LayerDev& L = p.layer[li];
+        // ---- decode the stage: y[N] = W[N][K] . act, epilogue by kind
+        int N = D, K = D, ld_dst = D;
+        const float* src = cur;
+        const float* norm_w = nullptr;
+        float* dst = cur;
+        float* trace = nullptr;
+        float scale = 0.f;
+        if (kind == K_GLU) {          // x -> RMSNorm -> GLU -> dwconv -> + x  (nn/blocks.py:156-160)
+          norm_w = L.norm_w;
+          dst = nxt;
+          if (li == 0) src = nullptr;
+        } else if (kind == K_FFN1) {  // RMSNorm -> W1 + b1 -> GELU          (nn/blocks.py:129-131)
+          norm_w = L.ffn_norm_w;
+          N = F;
+          dst = p.hbuf;
+          ld_dst = F;
+        } else if (kind == K_FFN2) {  // W2 + b2 -> + x (in place, own slice) (nn/blocks.py:132,161)
+          src = p.hbuf;
+          K = F;
+          if (p.trace_blocks && !L.has_attn) trace = p.trace_blocks + (((size_t)t * p.n_layers + li) * p.B) * D;
+        } else if (kind == K_Q) {     // q = Wq . RMSNorm_q(x)                (nn/text.py:93-94)
+          norm_w = L.nq_w;
+          dst = p.qbuf;
+        } else if (kind == K_O) {     // x += tanh(gate) * Wo . a            (nn/text.py:129-131)
+          src = p.abuf;
+          scale = L.gate_tanh;
+          if (p.trace_blocks) trace = p.trace_blocks + (((size_t)t * p.n_layers + li) * p.B) * D;
+        } else {                      // logits = Wh . RMSNorm(x) + bh       (nn/generator.py:127-128)
+          norm_w = p.final_norm_w;
+          N = p.V;
+          dst = p.logits;
+          ld_dst = p.Vpad;
+          if (p.trace_logits) trace = p.trace_logits + ((size_t)t * p.B) * p.V;
+        }
+        // ---- stage the activations
+        if (src == nullptr) {  // layer 0: x = cond_ar[:, t] + emb(prev token | BOS)  (model.py:266-272)
+          // cond row -> act, embedding row -> xraw (cp.async, all loads in flight together), then add
+          for (int u = warp; u < tc.nb; u += kWarps) {
+            const int b = tc.b0 + u;
+            const float* cr = p.cond + ((size_t)b * p.steps + t) * D;
+            for (int k = lane * 4; k < D; k += 128) cp_async16(act_s + (unsigned)(u * D + k) * 4u, cr + k);
+            const int row = (t == 0) ? p.V : __ldcg(&p.tokens[(size_t)b * p.steps + t - 1]);
+            const float* er = p.emb + (size_t)row * D;
+            for (int k = lane * 4; k < D; k += 128) cp_async16(act_s + (unsigned)((tc.nb + u) * D + k) * 4u, er + k);
           }
+          cp_async_commit();
+          cp_async_wait0();
+          __syncwarp();
+          for (int u = warp; u < tc.nb; u += kWarps) {
+            for (int k = lane * 4; k < D; k += 128) {
+              const float4 c = *reinterpret_cast<float4*>(act + (size_t)u * D + k);
+              const float4 e = *reinterpret_cast<float4*>(xraw + (size_t)u * D + k);
+              const float4 x = make_float4(c.x + e.x, c.y + e.y, c.z + e.z, c.w + e.w);
+              *reinterpret_cast<float4*>(act + (size_t)u * D + k) = x;
+              *reinterpret_cast<float4*>(xraw + (size_t)u * D + k) = x;
+            }
+          }
+          __syncwarp();
         }
+        stage_rows(src ? src + (size_t)tc.b0 * K : nullptr, tc.nb, K, act, norm_w, (kind == K_GLU && src) ? xraw : nullptr);
         __syncthreads();
-        norm_rows_inplace(act, tc.nb, D, L.norm_w);
-      } else {
-        stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, L.norm_w, xraw);
-      }
-      __syncthreads();
-      if (tc.nb >= 8)
-        stage_glu_conv<8, WT>(p, L, tc, t, act, xraw, nxt);
-      else if (tc.nb >= 4)
-        stage_glu_conv<4, WT>(p, L, tc, t, act, xraw, nxt);
-      else if (tc.nb >= 2)
-        stage_glu_conv<2, WT>(p, L, tc, t, act, xraw, nxt);
-      else
-        stage_glu_conv<1, WT>(p, L, tc, t, act, xraw, nxt);
-      {
-        float* tmp = cur;
-        cur = nxt;
-        nxt = tmp;
-      }
-      team_barrier(bar, tc.P, epoch, ts);
-      // ---- stage 2: FFN up + GELU
-      stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, L.ffn_norm_w, nullptr);
-      __syncthreads();
-      gemv_dispatch<EPI_FFN1, WT>(p, tc, L.w1, F, D, L.b1, act, p.hbuf, F, 0.f, nullptr);
-      team_barrier(bar, tc.P, epoch, ts);
-      // ---- stage 3: FFN down + residual (in place on this CTA's slice of cur)
-      stage_rows(p.hbuf + (size_t)tc.b0 * F, F, tc.nb, F, act, nullptr, nullptr);
-      __syncthreads();
-      {
-        float* tr = (p.trace_blocks && !L.has_attn)
-                        ? p.trace_blocks + (((size_t)t * p.n_layers + li) * p.B) * D
-                        : nullptr;
-        gemv_dispatch<EPI_FFN2, WT>(p, tc, L.w2, D, F, L.b2, act, cur, D, 0.f, tr);
-      }
-      team_barrier(bar, tc.P, epoch, ts);
-      if (L.has_attn) {
-        // ---- q projection
-        stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, L.nq_w, nullptr);
-        __syncthreads();
-        gemv_dispatch<EPI_Q, WT>(p, tc, L.wq, D, D, nullptr, act, p.qbuf, D, 0.f, nullptr);
-        team_barrier(bar, tc.P, epoch, ts);
-        // ---- attention core
-        stage_attention(p, L, tc, act);
-        team_barrier(bar, tc.P, epoch, ts);
-        // ---- out projection + gated residual
-        stage_rows(p.abuf + (size_t)tc.b0 * D, D, tc.nb, D, act, nullptr, nullptr);
-        __syncthreads();
-        {
-          float* tr = p.trace_blocks ? p.trace_blocks + (((size_t)t * p.n_layers + li) * p.B) * D : nullptr;
-          gemv_dispatch<EPI_O, WT>(p, tc, L.wo, D, D, nullptr, act, cur, D, L.gate_tanh, tr);
+        ts.mark();  // activations staged
+        // ---- this CTA's rows, tile by tile from the weight ring
+        const bool glu = kind == K_GLU;
+        const unsigned row_bytes = (unsigned)K * (unsigned)sizeof(WT);
+        float* state = p.ring + L.ring_off;
+        const int dil = L.dil;
+        const int phase = conv_phase[li], slot_now = conv_slot[li];
+        const unsigned tap_s = scratch_s + (unsigned)warp * (unsigned)(8 * p.KcP * 4) + (unsigned)(lane % TU) * (unsigned)(p.KcP * 4);
+#pragma unroll 1
+        for (int ti = stage_tiles[si]; ti > 0; --ti) {
+          const TileDesc* td;
+          const unsigned wb = ring.acquire(td);
+          const int nr = td->nrows;
+          const int n_rt = glu ? nr : (nr + 1) / 2;
+          const unsigned epi_s = wb + td->bytes0 + td->bytes1;
+#pragma unroll 1
+          for (int task = warp; task < n_rt * n_ut; task += kWarps) {
+            const int rt = n_ut == 1 ? task : (int)((unsigned)task / (unsigned)n_ut);
+            const int u0 = (task - rt * n_ut) * TU;
+            const unsigned w0 = wb + (unsigned)(glu ? rt : min(2 * rt, nr - 1)) * row_bytes;
+            const unsigned w1 = glu ? wb + td->bytes0 + (unsigned)rt * row_bytes
+                                    : wb + (unsigned)min(2 * rt + 1, nr - 1) * row_bytes;
+            const int ub = min(u0, max(tc.nb - TU, 0));
+            const int i = lane / TU, uu = lane % TU;
+            const int ri = glu ? rt : 2 * rt + i;
+            const int u = ub + uu;
+            const bool mine = lane < (glu ? TU : 2 * TU) && ri < nr && u >= u0 && u < tc.nb;
+            const int r = td->row0 + ri;  // output feature (GLU: channel)
+            const int b = tc.b0 + (mine ? u : 0);
+            float* d = dst + (size_t)b * ld_dst + (mine ? r : td->row0);
+            // operands of the epilogue are requested before the K loop: their latency hides under it
+            float res_v = 0.f;
+            float* rb = nullptr;
+            if (glu) {
+              // conv state row of (utterance, channel, phase): [KcP] floats, see DESIGN.md §2
+              rb = state + (((size_t)b * D + (mine ? r : td->row0)) * dil + phase) * p.KcP;
+              if (mine)
+                for (int q = 0; q < p.KcP; q += 4) cp_async16(tap_s + (unsigned)q * 4u, rb + q);
+            } else if (mine && (kind == K_FFN2 || kind == K_O)) {
+              res_v = ldcg1(d);
+            }
+            cp_async_commit();
+            float out[2][TU];
+            warp_rows_s<TU, WT>(w0, w1, act_s + (unsigned)ub * (unsigned)K * 4u, K, lane, out);
+            cp_async_wait0();
+            if (mine) {
+              if (glu) {
+                const int Kc = p.Kc;
+                const unsigned er = epi_s + (unsigned)(ri * p.KcE) * 4u;  // [w0..w(Kc-1), dw_b, b_value, b_gate]
+                const float a = pick2<TU>(out, 0, uu) + lds32(er + (unsigned)(Kc + 1) * 4u);
+                const float gt = pick2<TU>(out, 1, uu) + lds32(er + (unsigned)(Kc + 2) * 4u);
+                const float h = a * sigmoid_ref(gt);
+                rb[slot_now] = h;  // slot (t / dil) mod Kc of frame t inside its phase
+                float y = 0.f;
+                int pos = slot_now + 1;  // oldest tap: frame t - (Kc-1)*dil
+#pragma unroll 1
+                for (int j = 0; j < Kc - 1; ++j) {
+                  if (pos == Kc) pos = 0;
+                  y += lds32(tap_s + (unsigned)pos * 4u) * lds32(er + (unsigned)j * 4u);
+                  ++pos;
+                }
+                y += h * lds32(er + (unsigned)(Kc - 1) * 4u);
+                y += lds32(er + (unsigned)Kc * 4u);
+                *d = xraw[(size_t)u * D + r] + y;
+              } else {
+                float v = pick2<TU>(out, i, uu);
+                const float bias_v = (kind == K_Q || kind == K_O) ? 0.f : lds32(epi_s + (unsigned)(td->off2 + ri) * 4u);
+                if (kind == K_FFN1) {
+                  *d = gelu_erf(v + bias_v);
+                } else if (kind == K_FFN2) {
+                  v = res_v + (v + bias_v);
+                  *d = v;
+                  if (trace) trace[(size_t)b * D + r] = v;
+                } else if (kind == K_Q) {
+                  *d = v;
+                } else if (kind == K_O) {
+                  v = res_v + scale * v;
+                  *d = v;
+                  if (trace) trace[(size_t)b * D + r] = v;
+                } else {
+                  v += bias_v;
+                  *d = v;
+                  if (trace) trace[(size_t)b * p.V + r] = v;
+                }
+              }
+            }
+            __syncwarp();  // the tap scratch is reused by the next task of this warp
+          }
+          ring.release();
         }
-        team_barrier(bar, tc.P, epoch, ts);
+        ts.mark();  // tiles done
+        if (glu) {
+          float* tmp = cur;
+          cur = nxt;
+          nxt = tmp;
+        }
+      } else if (kind == K_ATT) {
+        ts.mark();
+        ts.mark();
+        stage_attention(p, li, tc.rank, tc.P, tc.b0, tc.nb, act);
+      } else {  // K_SAMPLE: utterances round-robin over the team's CTAs
+        ts.mark();
+        ts.mark();
+        float* sx = act;
+        float* sp = act + p.Vpad;
+        unsigned char* flags = reinterpret_cast<unsigned char*>(act + 2 * p.Vpad);
+        for (int u = tc.rank; u < tc.nb; u += tc.P) {
+          sample_utterance(p, tc.b0 + u, t, sx, sp, flags, ssm);
+          __syncthreads();
+        }
       }
+      team_barrier(bar, tc.P, epoch, ts);
     }
-    // ---- head
-    stage_rows(cur + (size_t)tc.b0 * D, D, tc.nb, D, act, p.final_norm_w, nullptr);
-    __syncthreads();
-    {
-      float* tr = p.trace_logits ? p.trace_logits + ((size_t)t * p.B) * p.V : nullptr;
-      gemv_dispatch<EPI_HEAD, WT>(p, tc, p.head_w, p.V, D, p.head_b, act, p.logits, p.Vpad, 0.f, tr);
-    }
-    team_barrier(bar, tc.P, epoch, ts);
-    // ---- sampler: utterances round-robin over the team's CTAs
-    {
-      float* sx = act;
-      unsigned char* flags = reinterpret_cast<unsigned char*>(act + p.Vpad);
-      for (int u = tc.rank; u < tc.nb; u += tc.P) {
-        sample_utterance(p, tc.b0 + u, t, sx, flags, ssm);
-        __syncthreads();
-      }
-    }
-    team_barrier(bar, tc.P, epoch, ts);
-    // x ping-pong parity: after an even number of swaps per step cur == xa again only if
-    // n_layers is even; keep it simple and copy nothing: the next step's layer 0 reads
-    // cond/emb, never cur.
   }
+  ring.drain();  // early team exit: prefetched tiles must land before the CTA exits
 }
 
 // ---------------------------------------------------------------------------
@@ -931,7 +1346,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
 // ---------------------------------------------------------------------------
 struct KvParams {
   int D, H, Dh, B, Lmax, text_stride, n_attn;
-  const float* txt;      // [B][text_stride][D]
+  const float* txt;  // [B][text_stride][D]
   const int* text_len;
   const float* nkv_w[kMaxLayers];
   const void* wk[kMaxLayers];
@@ -942,38 +1357,34 @@ struct KvParams {
 
 template <typename WT>
 __global__ void __launch_bounds__(kThreads, 1) kv_build_kernel(const __grid_constant__ KvParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   float* act = reinterpret_cast<float*>(smem_raw);  // [16][D]
-  constexpr int TL = 16, TU = 8, TR = 2;
+  constexpr int TL = 16, TU = 8;
   const int l0 = blockIdx.x * TL, b = blockIdx.y, slot = blockIdx.z;
   const int len = p.text_len[b];
   if (l0 >= len) return;
   const int nl = min(TL, len - l0);
   const int D = p.D;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // positions beyond nl: fill with zeros so the tiles stay in-bounds
+  // positions beyond nl: zeros, so the tiles stay in-bounds
   for (int i = threadIdx.x; i < TL * D; i += kThreads) act[i] = 0.f;
   __syncthreads();
-  stage_rows(p.txt + ((size_t)b * p.text_stride + l0) * D, D, nl, D, act, p.nkv_w[slot], nullptr);
+  stage_rows(p.txt + ((size_t)b * p.text_stride + l0) * D, nl, D, act, p.nkv_w[slot], nullptr);
   __syncthreads();
   const WT* Wk = reinterpret_cast<const WT*>(p.wk[slot]);
   const WT* Wv = reinterpret_cast<const WT*>(p.wv[slot]);
-  const int n_rt = (2 * D) / TR, n_ut = TL / TU;
+  const int n_rt = (2 * D) / 2, n_ut = TL / TU;
   for (int task = warp; task < n_rt * n_ut; task += kWarps) {
-    const int r0 = (task / n_ut) * TR, u0 = (task % n_ut) * TU;
+    const int r0 = (task / n_ut) * 2, u0 = (task % n_ut) * TU;
     if (u0 >= nl) continue;
-    const WT* rows[TR];
-#pragma unroll
-    for (int i = 0; i < TR; ++i) {
-      const int r = r0 + i;
-      rows[i] = (r < D) ? Wk + (size_t)r * D : Wv + (size_t)(r - D) * D;
-    }
-    float out[TR][TU];
-    warp_rows<TR, TU, WT>(rows, act + (size_t)u0 * D, D, D, lane, out);
+    const WT* w0 = (r0 < D) ? Wk + (size_t)r0 * D : Wv + (size_t)(r0 - D) * D;
+    const WT* w1 = (r0 + 1 < D) ? Wk + (size_t)(r0 + 1) * D : Wv + (size_t)(r0 + 1 - D) * D;
+    float out[2][TU];
+    warp_rows_g<TU, WT>(w0, w1, act + (size_t)u0 * D, D, lane, out);
     const int i = lane / TU, uu = lane % TU;
     const int r = r0 + i, l = u0 + uu;
-    if (lane < TR * TU && l < nl) {
-      const float v = pick2<TR, TU>(out, i, uu);
+    if (lane < 2 * TU && l < nl) {
+      const float v = pick2<TU>(out, i, uu);
       const int rr = r < D ? r : r - D;
       const int h = rr / p.Dh, dh = rr % p.Dh;
       float* dst = (r < D ? p.kc : p.vc) + ((((size_t)slot * p.B + b) * p.H + h) * p.Lmax + (l0 + l)) * p.Dh + dh;

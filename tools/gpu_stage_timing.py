@@ -29,7 +29,7 @@ def run(B, wdtype, team=0, steps=64, L=52, step=40):
     noise = torch.empty(B, steps, 50).exponential_(1.0, generator=torch.Generator().manual_seed(0))
     ses = eng.session(B, steps, L)
     if team: ses.set_team(team)
-    buf = torch.zeros(eng.num_sms, 128, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(eng.num_sms, 224, dtype=torch.int64, device="cuda")
     ses.set_timing(buf, step)
     ses.begin(cond, txt, [L] * B, noise, Sampling(min_gen_frames=2**31 - 1))
     ses.run(); torch.cuda.synchronize()
@@ -37,19 +37,22 @@ def run(B, wdtype, team=0, steps=64, L=52, step=40):
     names = stage_names(cfg)
     ns = len(names)
     clk = 1.0  # cycles
-    print(f"== B={B} {wdtype} team={team}: per-stage cycles (median / max over CTAs): work = start->stage done, "
-          f"post = done->arrival posted, wait = arrival->released")
-    tot = np.zeros(3)
+    print(f"== B={B} {wdtype} team={team}: per-stage cycles (median / max over CTAs)")
+    tot = np.zeros(5)
     for s_i, nm in enumerate(names):
-        t0 = t[:, 0] if s_i == 0 else t[:, 3 * s_i]      # previous release (or step start)
-        done, arr, rel = t[:, 1 + 3 * s_i], t[:, 2 + 3 * s_i], t[:, 3 + 3 * s_i]
+        base = 1 + 5 * s_i
+        t0 = t[:, base - 1]                      # previous release (or step start)
+        staged, tiles, done, arr, rel = (t[:, base + k] for k in range(5))
         ok = rel > 0
-        w, p_, q = (done - t0)[ok], (arr - done)[ok], (rel - arr)[ok]
-        tot += [np.median(w), np.median(p_), np.median(q)]
-        print(f"  {nm:9s} work {np.median(w):7.0f}/{w.max():7.0f}  post {np.median(p_):6.0f}/{p_.max():6.0f}  "
-              f"wait {np.median(q):7.0f}/{q.max():7.0f}  (min wait {q.min():6.0f})")
-    span = (t[:, 3 * ns] - t[:, 0])
-    print(f"  step span cycles median {np.median(span[span>0]):.0f}; sums of medians work {tot[0]:.0f} post {tot[1]:.0f} wait {tot[2]:.0f}")
+        parts = [(staged - t0)[ok], (tiles - staged)[ok], (done - tiles)[ok], (arr - done)[ok], (rel - arr)[ok]]
+        tot += [np.median(x) for x in parts]
+        print(f"  {nm:9s} stage-in {np.median(parts[0]):6.0f}/{parts[0].max():6.0f}  tiles {np.median(parts[1]):6.0f}/{parts[1].max():6.0f}  "
+              f"tail {np.median(parts[2]):6.0f}/{parts[2].max():6.0f}  post {np.median(parts[3]):5.0f}  wait {np.median(parts[4]):6.0f}/{parts[4].max():6.0f} (min {parts[4].min():5.0f})")
+    sm = t[0, 160:170]
+    print("  sampler phases (CTA 0):", [int(b - a) for a, b in zip(sm[:-1], sm[1:])],
+          "= fetch, penalise, max, exp+sum, probs, lower bound, compaction, sort/top-p/draw, bookkeeping")
+    span = (t[:, 5 * ns] - t[:, 0])
+    print(f"  step span cycles median {np.median(span[span>0]):.0f}; sums of medians stage-in {tot[0]:.0f} tiles {tot[1]:.0f} tail {tot[2]:.0f} post {tot[3]:.0f} wait {tot[4]:.0f}")
 
 
 if __name__ == "__main__":
