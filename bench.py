@@ -335,9 +335,9 @@ def main():
     }
     if not args.no_cpu_baseline:
         threads, avail = pick_threads(cfg, sd)
-        v, dt = cpu_reference_sample(cfg, sd, 3, threads)
+        v, dt = cpu_reference_sample(cfg, sd, 16, threads)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "cores_available": avail, "kind": "port",
-                                "sample": f"3 utterances x 401 AR frames of the same workload, sequential, {dt:.1f} s "
+                                "sample": f"16 utterances x 401 AR frames of the same workload, sequential, {dt:.1f} s "
                                           "(oracle/ar_oracle.py, torch CPU eager; the reference has no batch path)"}
     print(json.dumps(line))
     if world > 1:

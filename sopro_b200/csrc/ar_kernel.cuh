@@ -337,13 +337,45 @@ struct WeightRing {
 // lanes split K (4 consecutive k per lane per 128-k chunk), FFMA2 accumulation, butterfly
 // reduction (every lane ends with all totals).  Weights AND activations in shared memory.
 // ---------------------------------------------------------------------------
+// After the K loop the 2*TU partial sums of every lane are combined with a TRANSPOSED reduction:
+// log2(2*TU) halving exchanges (each lane keeps half of the outputs and hands the other half to its
+// partner) followed by plain butterflies: 2*TU - 1 + (5 - log2(2*TU)) shuffles instead of 5 * 2*TU.
+// On return every lane holds the total of output o = (lane >> (5 - log2(2*TU))) & (2*TU - 1),
+// with o = r * TU + u.
+template <int N>
+__device__ __forceinline__ float reduce_transposed(float (&v)[N], int lane) {
+  int n = N;
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    if (n > 1) {
+      const int half = n >> 1;
+      const bool up = (lane & s) != 0;
+#pragma unroll
+      for (int i = 0; i < N / 2; ++i) {
+        if (i < half) {
+          const float keep = up ? v[i + half] : v[i];
+          const float send = up ? v[i] : v[i + half];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+        }
+      }
+      n = half;
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], s);
+    }
+  }
+  return v[0];
+}
+template <>
+__device__ __forceinline__ float reduce_transposed<1>(float (&v)[1], int lane) {
+  return warp_sum(v[0]);
+}
+
 template <int TU, typename WT>
-__device__ __forceinline__ void warp_rows_s(unsigned w0, unsigned w1, unsigned act, int K, int lane,
-                                            float (&out)[2][TU]) {
+__device__ __forceinline__ float warp_rows_s(unsigned w0, unsigned w1, unsigned act, int K, int lane) {
   float2 acc[2][TU];
 #pragma unroll
   for (int u = 0; u < TU; ++u) acc[0][u] = acc[1][u] = make_float2(0.f, 0.f);
-#pragma unroll 1
+#pragma unroll 3
   for (int k = lane * 4; k < K; k += 128) {
     const float4 wa = ldsw4<WT>(w0 + (unsigned)k * (unsigned)sizeof(WT));
     const float4 wb = ldsw4<WT>(w1 + (unsigned)k * (unsigned)sizeof(WT));
@@ -356,10 +388,12 @@ __device__ __forceinline__ void warp_rows_s(unsigned w0, unsigned w1, unsigned a
       acc[1][u] = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(x.z, x.w), acc[1][u]);
     }
   }
+  float v[2 * TU];
 #pragma unroll
   for (int r = 0; r < 2; ++r)
 #pragma unroll
-    for (int u = 0; u < TU; ++u) out[r][u] = warp_sum(acc[r][u].x + acc[r][u].y);
+    for (int u = 0; u < TU; ++u) v[r * TU + u] = acc[r][u].x + acc[r][u].y;
+  return reduce_transposed<2 * TU>(v, lane);
 }
 
 // same, weights from global memory (K/V builder only)
@@ -1230,7 +1264,6 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
         float* state = p.ring + L.ring_off;
         const int dil = L.dil;
         const int phase = conv_phase[li], slot_now = conv_slot[li];
-        const unsigned tap_s = scratch_s + (unsigned)warp * (unsigned)(8 * p.KcP * 4) + (unsigned)(lane % TU) * (unsigned)(p.KcP * 4);
 #pragma unroll 1
         for (int ti = stage_tiles[si]; ti > 0; --ti) {
           const TileDesc* td;
@@ -1246,34 +1279,41 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
             const unsigned w1 = glu ? wb + td->bytes0 + (unsigned)rt * row_bytes
                                     : wb + (unsigned)min(2 * rt + 1, nr - 1) * row_bytes;
             const int ub = min(u0, max(tc.nb - TU, 0));
-            const int i = lane / TU, uu = lane % TU;
+            // after the transposed reduction lane L owns output o = (L >> SH) & (2*TU-1) = i*TU + uu
+            constexpr int LOG2N = (TU == 1 ? 1 : TU == 2 ? 2 : TU == 4 ? 3 : 4);
+            constexpr int SH = 5 - LOG2N;
+            const int o = (lane >> SH) & (2 * TU - 1);
+            const int i = o / TU, uu = o % TU;
+            const bool writer = (lane & ((1 << SH) - 1)) == 0;
             const int ri = glu ? rt : 2 * rt + i;
             const int u = ub + uu;
-            const bool mine = lane < (glu ? TU : 2 * TU) && ri < nr && u >= u0 && u < tc.nb;
+            const bool mine = writer && (glu ? i == 0 : true) && ri < nr && u >= u0 && u < tc.nb;
             const int r = td->row0 + ri;  // output feature (GLU: channel)
             const int b = tc.b0 + (mine ? u : 0);
             float* d = dst + (size_t)b * ld_dst + (mine ? r : td->row0);
             // operands of the epilogue are requested before the K loop: their latency hides under it
             float res_v = 0.f;
             float* rb = nullptr;
+            const unsigned tap_w = scratch_s + (unsigned)warp * (unsigned)(8 * p.KcP * 4) + (unsigned)uu * (unsigned)(p.KcP * 4);
             if (glu) {
               // conv state row of (utterance, channel, phase): [KcP] floats, see DESIGN.md §2
               rb = state + (((size_t)b * D + (mine ? r : td->row0)) * dil + phase) * p.KcP;
               if (mine)
-                for (int q = 0; q < p.KcP; q += 4) cp_async16(tap_s + (unsigned)q * 4u, rb + q);
+                for (int q = 0; q < p.KcP; q += 4) cp_async16(tap_w + (unsigned)q * 4u, rb + q);
             } else if (mine && (kind == K_FFN2 || kind == K_O)) {
               res_v = ldcg1(d);
             }
             cp_async_commit();
-            float out[2][TU];
-            warp_rows_s<TU, WT>(w0, w1, act_s + (unsigned)ub * (unsigned)K * 4u, K, lane, out);
+            float v = warp_rows_s<TU, WT>(w0, w1, act_s + (unsigned)ub * (unsigned)K * 4u, K, lane);
+            // GLU: the gate total of utterance uu lives in the lanes of output TU + uu
+            const float gate_v = __shfl_sync(0xffffffffu, v, ((TU + uu) << SH) & 31);
             cp_async_wait0();
             if (mine) {
               if (glu) {
                 const int Kc = p.Kc;
                 const unsigned er = epi_s + (unsigned)(ri * p.KcE) * 4u;  // [w0..w(Kc-1), dw_b, b_value, b_gate]
-                const float a = pick2<TU>(out, 0, uu) + lds32(er + (unsigned)(Kc + 1) * 4u);
-                const float gt = pick2<TU>(out, 1, uu) + lds32(er + (unsigned)(Kc + 2) * 4u);
+                const float a = v + lds32(er + (unsigned)(Kc + 1) * 4u);
+                const float gt = gate_v + lds32(er + (unsigned)(Kc + 2) * 4u);
                 const float h = a * sigmoid_ref(gt);
                 rb[slot_now] = h;  // slot (t / dil) mod Kc of frame t inside its phase
                 float y = 0.f;
@@ -1281,14 +1321,13 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
 #pragma unroll 1
                 for (int j = 0; j < Kc - 1; ++j) {
                   if (pos == Kc) pos = 0;
-                  y += lds32(tap_s + (unsigned)pos * 4u) * lds32(er + (unsigned)j * 4u);
+                  y += lds32(tap_w + (unsigned)pos * 4u) * lds32(er + (unsigned)j * 4u);
                   ++pos;
                 }
                 y += h * lds32(er + (unsigned)(Kc - 1) * 4u);
                 y += lds32(er + (unsigned)Kc * 4u);
                 *d = xraw[(size_t)u * D + r] + y;
               } else {
-                float v = pick2<TU>(out, i, uu);
                 const float bias_v = (kind == K_Q || kind == K_O) ? 0.f : lds32(epi_s + (unsigned)(td->off2 + ri) * 4u);
                 if (kind == K_FFN1) {
                   *d = gelu_erf(v + bias_v);
