@@ -177,6 +177,74 @@ int sopro_ar_debug_sampled(sopro_ar_session_t* s, int32_t* dst, void* stream);
  * [n_attn_layers, batch, H, Lpad, Dh] f32 (device), Lpad = max_text_len rounded up to 4 */
 int sopro_ar_debug_kv(sopro_ar_session_t* s, float* k_dst, float* v_dst, void* stream);
 
+
+/* ======================= Mimi codec decode (codes -> waveform) =======================
+ * Replaces transformers.MimiModel.decode as the reference calls it: MimiCodec.decode_full
+ * (codec/mimi.py:65-72) and, through it, MimiStreamDecoder.decode_step (codec/mimi.py:115-181).
+ * Citations below are transformers/models/mimi/modeling_mimi.py (5.5.0). */
+#define SOPRO_MIMI_MAX_LAYERS 16
+#define SOPRO_MIMI_MAX_RATIOS 8
+
+typedef struct sopro_mimi_config {
+  int32_t hidden;        /* 512  MimiConfig.hidden_size */
+  int32_t codebook_dim;  /* 256  (hidden == 2*codebook_dim: the two 1x1 output projections are fused) */
+  int32_t n_q;           /* 32   num_quantizers */
+  int32_t n_sem;         /* 1    num_semantic_quantizers */
+  int32_t vocab;         /* 2048 codebook_size */
+  int32_t n_layers;      /* 8 */
+  int32_t n_heads;       /* 8 */
+  int32_t ffn;           /* 2048 intermediate_size */
+  int32_t window;        /* 250  sliding_window */
+  int32_t num_filters;   /* 64 */
+  int32_t kernel;        /* 7 */
+  int32_t last_kernel;   /* 3 */
+  int32_t res_kernel;    /* 3 */
+  int32_t compress;      /* 2 */
+  int32_t n_ratios;      /* 4 */
+  int32_t ratios[SOPRO_MIMI_MAX_RATIOS]; /* 8,6,5,4 */
+  float norm_eps;        /* 1e-5 */
+  float rope_theta;      /* 10000 */
+} sopro_mimi_config_t;
+
+/* HOST fp32 pointers, state_dict layouts. */
+typedef struct sopro_mimi_layer_weights {
+  const float *ln1_w, *ln1_b;            /* input_layernorm                 :933 */
+  const float *q_w, *k_w, *v_w, *o_w;    /* self_attn.*_proj.weight [C,C]    :676-679 */
+  const float* ls1;                      /* self_attn_layer_scale.scale     :935 */
+  const float *ln2_w, *ln2_b;            /* post_attention_layernorm        :934 */
+  const float *fc1_w, *fc2_w;            /* mlp.fc1 [F,C], mlp.fc2 [C,F] */
+  const float* ls2;                      /* mlp_layer_scale.scale */
+} sopro_mimi_layer_weights_t;
+
+typedef struct sopro_mimi_stage_weights {
+  const float *convt_w, *convt_b;        /* decoder.layers.{i}.conv: ConvTranspose1d [Cin, Cout, 2r], [Cout] */
+  const float *res1_w, *res1_b;          /* ...block.1.conv [Cout/2, Cout, 3] */
+  const float *res2_w, *res2_b;          /* ...block.3.conv [Cout, Cout/2, 1] */
+} sopro_mimi_stage_weights_t;
+
+typedef struct sopro_mimi_weights {
+  const float* embed;         /* [n_q, vocab, codebook_dim]: embed_sum / clamp(cluster_usage, 1e-5)  (:1192-1196),
+                                 semantic codebooks first, then acoustic */
+  const float* sem_out_proj;  /* quantizer.semantic_residual_vector_quantizer.output_proj.weight [C, Dc] */
+  const float* ac_out_proj;   /* quantizer.acoustic_...output_proj.weight [C, Dc] */
+  const float* upsample_w;    /* upsample.conv.weight [C, 1, 4] */
+  sopro_mimi_layer_weights_t layer[SOPRO_MIMI_MAX_LAYERS];
+  const float *conv0_w, *conv0_b; /* decoder.layers.0.conv [16F, C, 7] */
+  sopro_mimi_stage_weights_t stage[SOPRO_MIMI_MAX_RATIOS];
+  const float *last_w, *last_b;   /* decoder.layers.14.conv [1, F, 3] */
+} sopro_mimi_weights_t;
+
+typedef struct sopro_mimi sopro_mimi_t;
+
+int sopro_mimi_create(const sopro_mimi_config_t* cfg, const sopro_mimi_weights_t* host_weights, int device,
+                      sopro_mimi_t** out);
+int sopro_mimi_destroy(sopro_mimi_t* m);
+int64_t sopro_mimi_samples_per_frame(const sopro_mimi_t* m); /* 1920 */
+/* codes [B, n_q, T] i32 (device) -> wav [B, T*1920] f32 (device).  MimiModel.decode (:1633-1680). */
+int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float* wav, void* stream);
+/* same with HOST buffers; synchronises the stream */
+int sopro_mimi_decode_host(sopro_mimi_t* m, const int32_t* codes_host, int B, int T, float* wav_host, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

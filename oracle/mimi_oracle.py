@@ -1,0 +1,178 @@
+"""CPU oracle for the Mimi codec DECODE path.  TEST INFRASTRUCTURE ONLY (see oracle/ar_oracle.py).
+
+The arithmetic of this path does not live in /root/reference: the reference calls
+``transformers.MimiModel.decode`` (reference codec/mimi.py:65-72, 152-156; dependency
+``transformers>=4.46``, uv.lock pins 4.57.6 / 5.0.0; installed here: 5.5.0).  This file restates
+that published algorithm functionally over the model's state_dict, citing
+``transformers/models/mimi/modeling_mimi.py`` (5.5.0) line numbers, and is pinned by
+tests/test_mimi_oracle.py against the installed ``MimiModel`` itself on seeded random weights
+(no checkpoint exists offline: "parity unpinned by the reference").
+
+Layout note: everything here is channel-last [B, T, C] (the CUDA engine's layout); the HF modules
+are channel-first, the restatement transposes nothing numerically relevant.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+SD = Dict[str, Tensor]
+
+UPSAMPLING_RATIOS = (8, 6, 5, 4)  # MimiConfig.upsampling_ratios
+
+
+def codebook(sd: SD, p: str) -> Tensor:
+    """MimiEuclideanCodebook.embed (:1192-1196): embed_sum / clamp(cluster_usage, eps)."""
+    return sd[p + "embed_sum"] / sd[p + "cluster_usage"].clamp(min=1e-5)[:, None]
+
+
+def rvq_decode(sd: SD, codes_bqt: Tensor, n_sem: int = 1) -> Tensor:
+    """MimiSplitResidualVectorQuantizer.decode (:1340-1350) + MimiResidualVectorQuantizer.decode
+    (:1282-1293): sum of per-codebook embeddings, then a bias-free 1x1 conv 256->512, separately for
+    the semantic (first) and acoustic (other) groups.  Returns [B, T, 512]."""
+    out = 0.0
+    for grp, lo, hi in (("semantic", 0, n_sem), ("acoustic", n_sem, codes_bqt.size(1))):
+        if hi <= lo:
+            continue
+        pre = f"quantizer.{grp}_residual_vector_quantizer."
+        q = 0.0
+        for i in range(hi - lo):
+            q = q + F.embedding(codes_bqt[:, lo + i], codebook(sd, pre + f"layers.{i}.codebook."))  # [B,T,256]
+        out = out + F.linear(q, sd[pre + "output_proj.weight"].squeeze(-1))
+    return out
+
+
+def upsample(sd: SD, x_btc: Tensor) -> Tensor:
+    """MimiConvTranspose1d (:354-409) with groups=C, kernel 4, stride 2, no bias, causal trim of
+    kernel-stride samples on the right (:388-392, :405-408)."""
+    y = F.conv_transpose1d(x_btc.transpose(1, 2), sd["upsample.conv.weight"], None, stride=2, groups=x_btc.size(-1))
+    return y[..., : y.size(-1) - 2].transpose(1, 2)
+
+
+def rope(q: Tensor, k: Tensor, theta: float = 10000.0):
+    """MimiRotaryEmbedding.forward (:565-577) + apply_rotary_pos_emb (:589-612); q,k [B,H,T,Dh]."""
+    Dh, T = q.size(-1), q.size(-2)
+    inv = 1.0 / (theta ** (torch.arange(0, Dh, 2, dtype=torch.int64).float() / Dh))
+    freqs = torch.arange(T).float()[:, None] * inv[None, :]
+    emb = torch.cat((freqs, freqs), dim=-1)
+    cos, sin = emb.cos()[None, None], emb.sin()[None, None]
+    rot = lambda x: torch.cat((-x[..., Dh // 2:], x[..., : Dh // 2]), dim=-1)  # noqa: E731
+    return q * cos + rot(q) * sin, k * cos + rot(k) * sin
+
+
+def transformer(sd: SD, x: Tensor, n_layers: int = 8, n_heads: int = 8, window: int = 250, eps: float = 1e-5) -> Tensor:
+    """MimiTransformerModel (:1001-1140) / MimiTransformerLayer.forward (:966-993) /
+    MimiAttention.forward (:681-738): pre-LayerNorm, RoPE, causal sliding-window softmax in fp32,
+    LayerScale on both residual branches, GELU(erf) MLP."""
+    B, T, C = x.shape
+    Dh = C // n_heads
+    i = torch.arange(T)
+    allowed = (i[None, :] <= i[:, None]) & (i[:, None] - i[None, :] < window)
+    bias = torch.zeros(T, T).masked_fill(~allowed, float("-inf"))
+    for l in range(n_layers):
+        p = f"decoder_transformer.layers.{l}."
+        h = F.layer_norm(x, (C,), sd[p + "input_layernorm.weight"], sd[p + "input_layernorm.bias"], eps)
+        sp = lambda t: t.view(B, T, n_heads, Dh).transpose(1, 2)  # noqa: E731
+        q, k, v = (sp(F.linear(h, sd[p + f"self_attn.{n}_proj.weight"])) for n in ("q", "k", "v"))
+        q, k = rope(q, k)
+        w = torch.matmul(q, k.transpose(2, 3)) * (1.0 / math.sqrt(Dh)) + bias
+        w = F.softmax(w, dim=-1, dtype=torch.float32)
+        a = torch.matmul(w, v).transpose(1, 2).contiguous().view(B, T, C)
+        x = x + sd[p + "self_attn_layer_scale.scale"] * F.linear(a, sd[p + "self_attn.o_proj.weight"])
+        h = F.layer_norm(x, (C,), sd[p + "post_attention_layernorm.weight"], sd[p + "post_attention_layernorm.bias"], eps)
+        h = F.linear(F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"])), sd[p + "mlp.fc2.weight"])
+        x = x + sd[p + "mlp_layer_scale.scale"] * h
+    return x
+
+
+def conv1d_causal(x_btc: Tensor, w: Tensor, b: Tensor, dilation: int = 1) -> Tensor:
+    """MimiConv1d.forward (:331-351), stride 1, causal: left zero-pad (k-1)*dilation (:337-339)."""
+    k = w.size(-1)
+    xt = F.pad(x_btc.transpose(1, 2), ((k - 1) * dilation, 0))
+    return F.conv1d(xt, w, b, dilation=dilation).transpose(1, 2)
+
+
+def conv_transpose_causal(x_btc: Tensor, w: Tensor, b: Tensor, stride: int) -> Tensor:
+    """MimiConvTranspose1d.forward (:402-409): full transposed conv, drop kernel-stride samples on the right."""
+    y = F.conv_transpose1d(x_btc.transpose(1, 2), w, b, stride=stride)
+    return y[..., : y.size(-1) - (w.size(-1) - stride)].transpose(1, 2)
+
+
+def seanet_decoder(sd: SD, x: Tensor) -> Tensor:
+    """MimiDecoder (:1143-1173): conv k7 -> 4 x [ELU, ConvT(stride r, kernel 2r), ResnetBlock] -> ELU -> conv k3.
+    ResnetBlock (:412-451): x + conv1(ELU(conv3(ELU(x)))), true skip."""
+    x = conv1d_causal(x, sd["decoder.layers.0.conv.weight"], sd["decoder.layers.0.conv.bias"])
+    li = 1
+    for r in UPSAMPLING_RATIOS:
+        x = conv_transpose_causal(F.elu(x), sd[f"decoder.layers.{li + 1}.conv.weight"], sd[f"decoder.layers.{li + 1}.conv.bias"], r)
+        p = f"decoder.layers.{li + 2}.block."
+        h = conv1d_causal(F.elu(x), sd[p + "1.conv.weight"], sd[p + "1.conv.bias"])
+        h = conv1d_causal(F.elu(h), sd[p + "3.conv.weight"], sd[p + "3.conv.bias"])
+        x = x + h
+        li += 3
+    return conv1d_causal(F.elu(x), sd[f"decoder.layers.{li + 1}.conv.weight"], sd[f"decoder.layers.{li + 1}.conv.bias"])
+
+
+def mimi_decode(sd: SD, codes_bqt: Tensor) -> Tensor:
+    """MimiModel._decode_frame (:1613-1631) + decode (:1633-1680): codes [B,Q,T] int64 -> wav [B,1,T*1920]."""
+    x = rvq_decode(sd, codes_bqt)
+    x = upsample(sd, x)
+    x = transformer(sd, x)
+    return seanet_decoder(sd, x).transpose(1, 2)
+
+
+def synth_mimi_state_dict(seed: int = 5, layer_scale: float = 0.3) -> SD:
+    """Seeded random weights for the decode path of ``MimiModel(MimiConfig(num_quantizers=32))``, platform
+    independent (integer hashing, like sopro_b200.weights).  LayerScale is raised from its 0.01 init so the
+    attention / MLP branches are visible in the output."""
+    import numpy as np
+
+    from sopro_b200.weights import hash_uniform
+
+    def U(name, shape, bound):
+        import zlib
+        n = int(np.prod(shape))
+        return torch.from_numpy(hash_uniform(n, (zlib.crc32(name.encode()) << 20) ^ seed) * np.float32(bound)).view(shape)
+
+    sd: SD = {}
+    for grp, n in (("semantic", 1), ("acoustic", 31)):
+        pre = f"quantizer.{grp}_residual_vector_quantizer."
+        for i in range(n):
+            sd[pre + f"layers.{i}.codebook.embed_sum"] = U(pre + f"{i}.e", (2048, 256), 1.0)
+            sd[pre + f"layers.{i}.codebook.cluster_usage"] = U(pre + f"{i}.u", (2048,), 0.4) + 1.0
+            sd[pre + f"layers.{i}.codebook.initialized"] = torch.ones(1)
+        sd[pre + "output_proj.weight"] = U(pre + "o", (512, 256, 1), 1 / 16.0)
+        sd[pre + "input_proj.weight"] = U(pre + "i", (256, 512, 1), 1 / 22.6)
+    sd["upsample.conv.weight"] = U("up", (512, 1, 4), 0.7)
+    for l in range(8):
+        p = f"decoder_transformer.layers.{l}."
+        for n in ("q", "k", "v", "o"):
+            sd[p + f"self_attn.{n}_proj.weight"] = U(p + n, (512, 512), 1 / 22.6)
+        sd[p + "mlp.fc1.weight"] = U(p + "f1", (2048, 512), 1 / 22.6)
+        sd[p + "mlp.fc2.weight"] = U(p + "f2", (512, 2048), 1 / 45.0)
+        for n in ("input_layernorm", "post_attention_layernorm"):
+            sd[p + n + ".weight"] = 1.0 + U(p + n + "w", (512,), 0.2)
+            sd[p + n + ".bias"] = U(p + n + "b", (512,), 0.1)
+        sd[p + "self_attn_layer_scale.scale"] = layer_scale + U(p + "ls1", (512,), 0.1)
+        sd[p + "mlp_layer_scale.scale"] = layer_scale + U(p + "ls2", (512,), 0.1)
+    chans = [(512, 1024, 7)]
+    sd["decoder.layers.0.conv.weight"] = U("d0w", (1024, 512, 7), 1 / math.sqrt(512 * 7))
+    sd["decoder.layers.0.conv.bias"] = U("d0b", (1024,), 0.02)
+    li, c = 1, 1024
+    for r in UPSAMPLING_RATIOS:
+        sd[f"decoder.layers.{li + 1}.conv.weight"] = U(f"t{li}w", (c, c // 2, 2 * r), 1 / math.sqrt(c * 2))
+        sd[f"decoder.layers.{li + 1}.conv.bias"] = U(f"t{li}b", (c // 2,), 0.02)
+        p = f"decoder.layers.{li + 2}.block."
+        sd[p + "1.conv.weight"] = U(p + "1w", (c // 4, c // 2, 3), 1 / math.sqrt(c // 2 * 3))
+        sd[p + "1.conv.bias"] = U(p + "1b", (c // 4,), 0.02)
+        sd[p + "3.conv.weight"] = U(p + "3w", (c // 2, c // 4, 1), 1 / math.sqrt(c // 4))
+        sd[p + "3.conv.bias"] = U(p + "3b", (c // 2,), 0.02)
+        li += 3
+        c //= 2
+    sd[f"decoder.layers.{li + 1}.conv.weight"] = U("lw", (1, 64, 3), 1 / math.sqrt(64 * 3))
+    sd[f"decoder.layers.{li + 1}.conv.bias"] = U("lb", (1,), 0.02)
+    return sd

@@ -51,6 +51,30 @@ class ArSampling(C.Structure):
     ]
 
 
+MIMI_MAX_LAYERS, MIMI_MAX_RATIOS = 16, 8
+
+
+class MimiConfigC(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "hidden", "codebook_dim", "n_q", "n_sem", "vocab", "n_layers", "n_heads", "ffn", "window", "num_filters",
+        "kernel", "last_kernel", "res_kernel", "compress", "n_ratios")] + [
+        ("ratios", C.c_int32 * MIMI_MAX_RATIOS), ("norm_eps", C.c_float), ("rope_theta", C.c_float)]
+
+
+class MimiLayerWeights(C.Structure):
+    _fields_ = [(n, _FP) for n in ("ln1_w", "ln1_b", "q_w", "k_w", "v_w", "o_w", "ls1", "ln2_w", "ln2_b", "fc1_w", "fc2_w", "ls2")]
+
+
+class MimiStageWeights(C.Structure):
+    _fields_ = [(n, _FP) for n in ("convt_w", "convt_b", "res1_w", "res1_b", "res2_w", "res2_b")]
+
+
+class MimiWeights(C.Structure):
+    _fields_ = [("embed", _FP), ("sem_out_proj", _FP), ("ac_out_proj", _FP), ("upsample_w", _FP),
+                ("layer", MimiLayerWeights * MIMI_MAX_LAYERS), ("conv0_w", _FP), ("conv0_b", _FP),
+                ("stage", MimiStageWeights * MIMI_MAX_RATIOS), ("last_w", _FP), ("last_b", _FP)]
+
+
 # every symbol include/sopro_b200.h declares: name -> (restype, argtypes)
 _VP, _I, _I32P = C.c_void_p, C.c_int, C.POINTER(C.c_int32)
 SYMBOLS = {
@@ -74,6 +98,11 @@ SYMBOLS = {
     "sopro_ar_set_timing": (_I, [_VP, _VP, _I]),
     "sopro_ar_debug_sampled": (_I, [_VP, _VP, _VP]),
     "sopro_ar_debug_kv": (_I, [_VP, _VP, _VP, _VP]),
+    "sopro_mimi_create": (_I, [C.POINTER(MimiConfigC), C.POINTER(MimiWeights), _I, C.POINTER(_VP)]),
+    "sopro_mimi_destroy": (_I, [_VP]),
+    "sopro_mimi_samples_per_frame": (C.c_int64, [_VP]),
+    "sopro_mimi_decode": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
+    "sopro_mimi_decode_host": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
 }
 
 _lib = None

@@ -69,6 +69,10 @@ struct Arena {
 
 }  // namespace
 
+namespace mimi {
+void set_error(const char* msg) { g_err = msg; }
+}  // namespace mimi
+
 struct sopro_engine {
   int device = 0;
   int n_sms = 0;

@@ -1,0 +1,615 @@
+// Mimi codec DECODE path on sm_100a: codes [B, Q, T] -> wav [B, T*1920].
+//
+// Replaces transformers.MimiModel.decode as called by the reference (codec/mimi.py:65-72):
+// RVQ lookup-sum + 1x1 projections, depthwise 2x ConvTranspose upsample, 8-layer causal
+// sliding-window transformer, SEANet decoder (modeling_mimi.py 5.5.0: _decode_frame :1613-1631,
+// MimiSplitResidualVectorQuantizer.decode :1340-1350, MimiTransformerLayer :966-993,
+// MimiAttention :681-738, MimiDecoder :1143-1173, MimiConvTranspose1d :402-409, MimiConv1d :331-351,
+// MimiResnetBlock :437-451).
+//
+// Round-1 design: every dense block is an implicit GEMM over channel-last
+// activations [T, C]: Linear, causal Conv1d (K = taps x Cin gathered from shifted rows) and causal
+// ConvTranspose1d (stride s, kernel 2s == a 2-tap conv producing s*Cout columns, which IS the
+// channel-last upsampled tensor), with ELU fused on the operand load and bias / GELU / LayerScale
+// residual fused in the epilogue.  This first version runs the contractions in fp32 on the FFMA2
+// pipe (parity 1e-4 against the fp32 oracle); the tcgen05/TMEM bf16 path is the next step.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sopro_b200.h"
+
+namespace mimi {
+
+// shared with ar_engine.cu through sopro_last_error()
+void set_error(const char* msg);
+
+enum { EPI_NONE = 0, EPI_GELU = 1, EPI_RES_SCALE = 2, EPI_RES = 3 };
+
+struct GemmOp {
+  const float* A;   // channel-last input [B][Min][Cin]
+  const float* W;   // [N][K], K = taps*Cin ordered (tap, ci)
+  const float* bias;  // [bias_mod] or null
+  const float* R;     // residual [B][M][N] or null
+  const float* scale; // [N] LayerScale or null
+  float* C;           // [B][M][ldc]
+  long long a_bs, c_bs, r_bs;  // batch strides (floats)
+  int M, N, K, Min, Cin, taps, dil, pad, ldc, bias_mod, epi, a_elu;
+};
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// C[m][n] = epi( sum_k A'[m][k] * W[n][k] + bias ),  A'[m][(j,ci)] = act(X[m + j*dil - pad][ci]) (0 outside)
+template <int BN>
+__global__ void __launch_bounds__(256) igemm_kernel(const GemmOp op) {
+  constexpr int BM = 64, BK = 16, TM = 4, TN = BN / 16;
+  __shared__ float As[2][BK][BM + 4];
+  __shared__ float Bs[2][BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, b = blockIdx.z;
+  const float* X = op.A + (size_t)b * op.a_bs;
+  const int lrow = tid >> 2, lk = (tid & 3) * 4;  // loader mapping: 64 rows x 4 float4 along k
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  auto load_a = [&](int k0) -> float4 {
+    const int kk = k0 + lk;
+    const int j = kk / op.Cin, ci = kk - j * op.Cin;
+    const int m = m0 + lrow;
+    const int rin = m + j * op.dil - op.pad;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (m < op.M && rin >= 0 && rin < op.Min) {
+      v = *reinterpret_cast<const float4*>(X + (size_t)rin * op.Cin + ci);
+      if (op.a_elu) {
+        v.x = elu1(v.x);
+        v.y = elu1(v.y);
+        v.z = elu1(v.z);
+        v.w = elu1(v.w);
+      }
+    }
+    return v;
+  };
+  auto load_b = [&](int k0) -> float4 {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lrow < BN && n0 + lrow < op.N) v = __ldg(reinterpret_cast<const float4*>(op.W + (size_t)(n0 + lrow) * op.K + k0 + lk));
+    return v;
+  };
+  auto store_tiles = [&](int buf, const float4& a, const float4& bq) {
+    As[buf][lk + 0][lrow] = a.x;
+    As[buf][lk + 1][lrow] = a.y;
+    As[buf][lk + 2][lrow] = a.z;
+    As[buf][lk + 3][lrow] = a.w;
+    if (lrow < BN) {
+      Bs[buf][lk + 0][lrow] = bq.x;
+      Bs[buf][lk + 1][lrow] = bq.y;
+      Bs[buf][lk + 2][lrow] = bq.z;
+      Bs[buf][lk + 3][lrow] = bq.w;
+    }
+  };
+  float4 ra = load_a(0), rb = load_b(0);
+  store_tiles(0, ra, rb);
+  __syncthreads();
+  const int nk = op.K / BK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) {
+      ra = load_a((kt + 1) * BK);
+      rb = load_b((kt + 1) * BK);
+    }
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][k][ty * TM]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      float bv[TN];
+      if (TN == 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * TN]);
+        bv[0] = b4.x;
+        bv[1] = b4.y;
+        bv[TN - 2] = b4.z;
+        bv[TN - 1] = b4.w;
+      } else {
+        const float2 b2 = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * TN]);
+        bv[0] = b2.x;
+        bv[TN - 1] = b2.y;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) store_tiles(buf ^ 1, ra, rb);
+    __syncthreads();
+  }
+  float* Cb = op.C + (size_t)b * op.c_bs;
+  const float* Rb = op.R ? op.R + (size_t)b * op.r_bs : nullptr;
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + ty * TM + i;
+    if (m >= op.M) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int n = n0 + tx * TN + j;
+      if (n >= op.N) continue;
+      float v = acc[i][j];
+      if (op.bias) v += __ldg(op.bias + (n % op.bias_mod));
+      if (op.epi == EPI_GELU) v = gelu_erf(v);
+      else if (op.epi == EPI_RES_SCALE) v = Rb[(size_t)m * op.N + n] + __ldg(op.scale + n) * v;
+      else if (op.epi == EPI_RES) v = Rb[(size_t)m * op.N + n] + v;
+      Cb[(size_t)m * op.ldc + n] = v;
+    }
+  }
+}
+
+// RVQ lookup-sum: codes [B][Q][T] -> S [B][T][2*Dc] = [semantic sum | acoustic sum]
+__global__ void rvq_gather_kernel(const int* __restrict__ codes, const float* __restrict__ embed, float* __restrict__ S,
+                                  int Q, int T, int Dc, int vocab, int n_sem) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  for (int c = threadIdx.x; c < Dc; c += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int q = 0; q < Q; ++q) {
+      const int code = codes[((size_t)b * Q + q) * T + t];
+      const float e = __ldg(embed + ((size_t)q * vocab + code) * Dc + c);
+      if (q < n_sem) s0 += e;
+      else s1 += e;
+    }
+    float* o = S + ((size_t)b * T + t) * (2 * Dc);
+    o[c] = s0;
+    o[Dc + c] = s1;
+  }
+}
+
+// depthwise ConvTranspose k=4 s=2, causal: y[2t+r][c] = x[t][c]*w[c][r] + x[t-1][c]*w[c][r+2]
+__global__ void upsample_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int T,
+                                int C) {
+  const int to = blockIdx.x, b = blockIdx.y;  // output row 0..2T-1
+  const int t = to >> 1, r = to & 1;
+  const float* xb = x + (size_t)b * T * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float v = xb[(size_t)t * C + c] * __ldg(w + c * 4 + r);
+    if (t > 0) v += xb[(size_t)(t - 1) * C + c] * __ldg(w + c * 4 + r + 2);
+    y[((size_t)b * 2 * T + to) * C + c] = v;
+  }
+}
+
+// LayerNorm over C (one warp per row)
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bb,
+                                 float* __restrict__ y, long long rows, int C, float eps) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] - mean;
+    v += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float inv = 1.0f / sqrtf(v / (float)C + eps);
+  for (int c = lane; c < C; c += 32) y[row * C + c] = (xr[c] - mean) * inv * __ldg(w + c) + __ldg(bb + c);
+}
+
+// RoPE in place on the q and k thirds of QKV [rows][3C]; rope table [T2][Dh/2] cos, then sin
+__global__ void rope_kernel(float* __restrict__ qkv, const float* __restrict__ cs, int T2, int tab_T2, int C, int H) {
+  const int t = blockIdx.x, b = blockIdx.y;
+  const int Dh = C / H, half = Dh / 2;
+  float* row = qkv + ((size_t)b * T2 + t) * 3 * C;
+  const float* cosr = cs + (size_t)t * half;
+  const float* sinr = cs + (size_t)(tab_T2 + t) * half;  // table: [cos rows 0..tab_T2) | sin rows 0..tab_T2)]
+  for (int i = threadIdx.x; i < 2 * H * half; i += blockDim.x) {
+    const int which = i / (H * half);  // 0 = q, 1 = k
+    const int rem = i - which * H * half;
+    const int h = rem / half, d = rem - h * half;
+    float* p = row + which * C + h * Dh;
+    const float x1 = p[d], x2 = p[d + half];
+    const float c = cosr[d], s = sinr[d];
+    p[d] = x1 * c - x2 * s;          // q*cos + rotate_half(q)*sin, first half: -x2
+    p[d + half] = x2 * c + x1 * s;   // second half: +x1
+  }
+}
+
+// causal sliding-window attention, one warp per (b, h, query); QKV rotated; out [B][T2][C]
+__global__ void __launch_bounds__(256) attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T2, int C,
+                                                   int H, int window) {
+  extern __shared__ float sm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Dh = C / H;
+  const int i = blockIdx.x * 8 + warp, h = blockIdx.y, b = blockIdx.z;
+  float* qs = sm + warp * (Dh + window);
+  float* sc = qs + Dh;
+  if (i >= T2) return;
+  const float* base = qkv + (size_t)b * T2 * 3 * C;
+  const float* q = base + (size_t)i * 3 * C + h * Dh;
+  for (int d = lane; d < Dh; d += 32) qs[d] = q[d];
+  __syncwarp();
+  const int j0 = max(0, i - window + 1);
+  const int nk = i - j0 + 1;
+  const float scale = 1.0f / sqrtf((float)Dh);
+  float mx = -INFINITY;
+  for (int jj = lane; jj < nk; jj += 32) {
+    const float* kr = base + (size_t)(j0 + jj) * 3 * C + C + h * Dh;
+    float s = 0.f;
+    for (int d = 0; d < Dh; d += 4) {
+      const float4 kk = *reinterpret_cast<const float4*>(kr + d);
+      s += kk.x * qs[d] + kk.y * qs[d + 1] + kk.z * qs[d + 2] + kk.w * qs[d + 3];
+    }
+    s *= scale;
+    sc[jj] = s;
+    mx = fmaxf(mx, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int jj = lane; jj < nk; jj += 32) {
+    const float e = expf(sc[jj] - mx);
+    sc[jj] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  __syncwarp();
+  const float inv = 1.0f / sum;
+  for (int d = lane; d < Dh; d += 32) {
+    float o = 0.f;
+    for (int jj = 0; jj < nk; ++jj) o += (sc[jj] * inv) * base[(size_t)(j0 + jj) * 3 * C + 2 * C + h * Dh + d];
+    out[((size_t)b * T2 + i) * C + h * Dh + d] = o;
+  }
+}
+
+// final conv: ELU -> causal conv k taps, Cin -> 1
+__global__ void final_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                  float* __restrict__ y, long long Tn, int Cin, int taps) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (t >= Tn) return;
+  const float* xb = x + (size_t)b * Tn * Cin;
+  float acc = __ldg(bias);
+  for (int j = 0; j < taps; ++j) {
+    const long long r = t + j - (taps - 1);
+    if (r < 0) continue;
+    const float* xr = xb + r * Cin;
+    for (int c = 0; c < Cin; c += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + c);
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w + j * Cin + c));
+      acc += elu1(v.x) * ww.x + elu1(v.y) * ww.y + elu1(v.z) * ww.z + elu1(v.w) * ww.w;
+    }
+  }
+  y[(size_t)b * Tn + t] = acc;
+}
+
+}  // namespace mimi
+
+using namespace mimi;
+
+namespace {
+int mfail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  mimi::set_error(buf);
+  return code;
+}
+#define MCK(call)                                                                                      \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess)                                                                            \
+      return mfail(SOPRO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DevArena {
+  std::vector<float> host;
+  size_t add(const float* p, size_t n) {
+    const size_t off = (host.size() + 63) / 64 * 64;
+    host.resize(off + n);
+    if (p) memcpy(host.data() + off, p, n * 4);
+    return off;
+  }
+};
+}  // namespace
+
+struct sopro_mimi {
+  int device = 0;
+  sopro_mimi_config_t cfg{};
+  float* dev = nullptr;
+  size_t n_floats = 0;
+  // offsets (floats) into dev
+  size_t embed = 0, rvq_w = 0, up_w = 0;
+  struct Layer {
+    size_t ln1w, ln1b, qkv, wo, ls1, ln2w, ln2b, fc1, fc2, ls2;
+  };
+  std::vector<Layer> layers;
+  size_t c0w = 0, c0b = 0;
+  struct Stage {
+    size_t tw, tb, r1w, r1b, r2w, r2b;
+    int ratio, cin, cout;
+  };
+  std::vector<Stage> stages;
+  size_t lw = 0, lb = 0;
+  // rope table + workspace
+  float* rope = nullptr;
+  int rope_T2 = 0;
+  float* ws = nullptr;
+  size_t ws_floats = 0;
+  int* codes_dev = nullptr;
+  size_t codes_cap = 0;
+};
+
+extern "C" {
+
+int sopro_mimi_create(const sopro_mimi_config_t* cfg, const sopro_mimi_weights_t* w, int device, sopro_mimi_t** out) {
+  if (!cfg || !w || !out) return mfail(SOPRO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) return mfail(SOPRO_ERR_UNSUPPORTED, "no CUDA device; the Mimi decoder has no CPU fallback");
+  if (device < 0 || device >= ndev) return mfail(SOPRO_ERR_INVALID, "device %d out of range", device);
+  cudaDeviceProp prop;
+  MCK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return mfail(SOPRO_ERR_UNSUPPORTED, "device is sm_%d%d; this build targets sm_100a only", prop.major, prop.minor);
+  const int C = cfg->hidden, Dc = cfg->codebook_dim, Q = cfg->n_q, V = cfg->vocab, NL = cfg->n_layers, FF = cfg->ffn;
+  if (C % 64 || Dc % 4 || C != 2 * Dc || NL < 1 || cfg->n_ratios < 1 || cfg->n_ratios > 8 || cfg->n_heads < 1 || C % cfg->n_heads ||
+      (C / cfg->n_heads) % 4 || FF % 16)
+    return mfail(SOPRO_ERR_INVALID, "unsupported Mimi geometry (hidden=%d codebook_dim=%d)", C, Dc);
+  MCK(cudaSetDevice(device));
+  sopro_mimi* m = new sopro_mimi();
+  m->device = device;
+  m->cfg = *cfg;
+  DevArena A;
+  m->embed = A.add(w->embed, (size_t)Q * V * Dc);
+  {  // [C][2*Dc] = [W_sem | W_ac]
+    std::vector<float> cat((size_t)C * 2 * Dc);
+    for (int n = 0; n < C; ++n)
+      for (int k = 0; k < Dc; ++k) {
+        cat[(size_t)n * 2 * Dc + k] = w->sem_out_proj[(size_t)n * Dc + k];
+        cat[(size_t)n * 2 * Dc + Dc + k] = w->ac_out_proj[(size_t)n * Dc + k];
+      }
+    m->rvq_w = A.add(cat.data(), cat.size());
+  }
+  m->up_w = A.add(w->upsample_w, (size_t)C * 4);
+  for (int l = 0; l < NL; ++l) {
+    const sopro_mimi_layer_weights_t& L = w->layer[l];
+    sopro_mimi::Layer d;
+    d.ln1w = A.add(L.ln1_w, C);
+    d.ln1b = A.add(L.ln1_b, C);
+    std::vector<float> qkv((size_t)3 * C * C);
+    memcpy(qkv.data(), L.q_w, (size_t)C * C * 4);
+    memcpy(qkv.data() + (size_t)C * C, L.k_w, (size_t)C * C * 4);
+    memcpy(qkv.data() + (size_t)2 * C * C, L.v_w, (size_t)C * C * 4);
+    d.qkv = A.add(qkv.data(), qkv.size());
+    d.wo = A.add(L.o_w, (size_t)C * C);
+    d.ls1 = A.add(L.ls1, C);
+    d.ln2w = A.add(L.ln2_w, C);
+    d.ln2b = A.add(L.ln2_b, C);
+    d.fc1 = A.add(L.fc1_w, (size_t)FF * C);
+    d.fc2 = A.add(L.fc2_w, (size_t)C * FF);
+    d.ls2 = A.add(L.ls2, C);
+    m->layers.push_back(d);
+  }
+  // conv weights [Cout][Cin][k] -> [Cout][(tap, ci)]
+  auto repack_conv = [&](const float* src, int cout, int cin, int k) {
+    std::vector<float> r((size_t)cout * k * cin);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int j = 0; j < k; ++j) r[((size_t)co * k + j) * cin + ci] = src[((size_t)co * cin + ci) * k + j];
+    return A.add(r.data(), r.size());
+  };
+  int ch = cfg->num_filters << cfg->n_ratios;  // 1024
+  m->c0w = repack_conv(w->conv0_w, ch, C, cfg->kernel);
+  m->c0b = A.add(w->conv0_b, ch);
+  for (int s = 0; s < cfg->n_ratios; ++s) {
+    const sopro_mimi_stage_weights_t& S = w->stage[s];
+    sopro_mimi::Stage d;
+    const int r = cfg->ratios[s], cin = ch, cout = ch / 2;
+    d.ratio = r;
+    d.cin = cin;
+    d.cout = cout;
+    // ConvTranspose weight [Cin][Cout][2r] -> [(phase, co)][(tap, ci)]: tap 0 <-> x[t-1] <-> w[.., phase + r], tap 1 <-> x[t] <-> w[.., phase]
+    std::vector<float> tw((size_t)r * cout * 2 * cin);
+    for (int ph = 0; ph < r; ++ph)
+      for (int co = 0; co < cout; ++co)
+        for (int ci = 0; ci < cin; ++ci) {
+          const size_t n = (size_t)ph * cout + co;
+          tw[(n * 2 + 0) * cin + ci] = S.convt_w[((size_t)ci * cout + co) * 2 * r + ph + r];
+          tw[(n * 2 + 1) * cin + ci] = S.convt_w[((size_t)ci * cout + co) * 2 * r + ph];
+        }
+    d.tw = A.add(tw.data(), tw.size());
+    d.tb = A.add(S.convt_b, cout);
+    d.r1w = repack_conv(S.res1_w, cout / cfg->compress, cout, cfg->res_kernel);
+    d.r1b = A.add(S.res1_b, cout / cfg->compress);
+    d.r2w = repack_conv(S.res2_w, cout, cout / cfg->compress, 1);
+    d.r2b = A.add(S.res2_b, cout);
+    m->stages.push_back(d);
+    ch = cout;
+  }
+  m->lw = repack_conv(w->last_w, 1, ch, cfg->last_kernel);
+  m->lb = A.add(w->last_b, 1);
+  m->n_floats = A.host.size();
+  cudaError_t err = cudaMalloc(&m->dev, m->n_floats * 4);
+  if (err == cudaSuccess) err = cudaMemcpy(m->dev, A.host.data(), m->n_floats * 4, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    if (m->dev) cudaFree(m->dev);
+    delete m;
+    return mfail(SOPRO_ERR_CUDA, "Mimi weight upload failed: %s", cudaGetErrorString(err));
+  }
+  *out = m;
+  return SOPRO_OK;
+}
+
+int sopro_mimi_destroy(sopro_mimi_t* m) {
+  if (!m) return SOPRO_OK;
+  cudaSetDevice(m->device);
+  cudaFree(m->dev);
+  cudaFree(m->rope);
+  cudaFree(m->ws);
+  cudaFree(m->codes_dev);
+  delete m;
+  return SOPRO_OK;
+}
+
+int64_t sopro_mimi_samples_per_frame(const sopro_mimi_t* m) {
+  if (!m) return 0;
+  int64_t s = 2;
+  for (int i = 0; i < m->cfg.n_ratios; ++i) s *= m->cfg.ratios[i];
+  return s;
+}
+
+static int launch_gemm(const GemmOp& op, int B, cudaStream_t st) {
+  if (op.K % 16 || op.Cin % 4) return mfail(SOPRO_ERR_INVALID, "igemm: K=%d Cin=%d not aligned", op.K, op.Cin);
+  if (op.N % 64 == 0 || op.N > 32) {
+    dim3 grid((op.M + 63) / 64, (op.N + 63) / 64, B);
+    igemm_kernel<64><<<grid, 256, 0, st>>>(op);
+  } else {
+    dim3 grid((op.M + 63) / 64, (op.N + 31) / 32, B);
+    igemm_kernel<32><<<grid, 256, 0, st>>>(op);
+  }
+  MCK(cudaGetLastError());
+  return SOPRO_OK;
+}
+
+int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float* wav, void* stream) {
+  if (!m || !codes || !wav) return mfail(SOPRO_ERR_INVALID, "null argument");
+  if (B < 1 || T < 1) return mfail(SOPRO_ERR_INVALID, "B and T must be >= 1");
+  MCK(cudaSetDevice(m->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const sopro_mimi_config_t& c = m->cfg;
+  const int C = c.hidden, T2 = 2 * T, H = c.n_heads, Dh = C / H, FF = c.ffn;
+  const float* Wd = m->dev;
+  // ---- rope table
+  if (m->rope_T2 < T2) {
+    cudaFree(m->rope);
+    m->rope = nullptr;
+    std::vector<float> tab((size_t)2 * T2 * (Dh / 2));
+    for (int t = 0; t < T2; ++t)
+      for (int d = 0; d < Dh / 2; ++d) {
+        const float inv = 1.0f / powf(c.rope_theta, (float)(2 * d) / (float)Dh);
+        const float f = (float)t * inv;
+        tab[(size_t)t * (Dh / 2) + d] = cosf(f);
+        tab[(size_t)(T2 + t) * (Dh / 2) + d] = sinf(f);
+      }
+    MCK(cudaMalloc(&m->rope, tab.size() * 4));
+    MCK(cudaMemcpyAsync(m->rope, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaStreamSynchronize(st));
+    m->rope_T2 = T2;
+  }
+  // ---- workspace: three ping-pong buffers sized for the widest SEANet activation + transformer scratch
+  long long up = 2;
+  for (int i = 0; i < c.n_ratios; ++i) up *= c.ratios[i];
+  const size_t big = (size_t)B * T * up * c.num_filters;                     // [T*1920][64]
+  const size_t tr = (size_t)B * T2 * (size_t)std::max(3 * C, FF);            // QKV / MLP hidden
+  const size_t bufsz = std::max(std::max(big, tr), (size_t)B * T2 * (c.num_filters << c.n_ratios));
+  const size_t need = 3 * bufsz + (size_t)B * T2 * C * 2;
+  if (m->ws_floats < need) {
+    cudaFree(m->ws);
+    m->ws = nullptr;
+    m->ws_floats = 0;
+    cudaError_t e = cudaMalloc(&m->ws, need * 4);
+    if (e != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "Mimi workspace %zu MB: %s", need * 4 >> 20, cudaGetErrorString(e));
+    m->ws_floats = need;
+  }
+  float* b0 = m->ws;
+  float* b1 = b0 + bufsz;
+  float* b2 = b1 + bufsz;
+  float* x = b2 + bufsz;               // residual stream [B][T2][C]
+  float* ln = x + (size_t)B * T2 * C;  // normalised copy
+  // ---- RVQ + projection + upsample
+  rvq_gather_kernel<<<dim3(T, B), 256, 0, st>>>(codes, Wd + m->embed, b0, c.n_q, T, c.codebook_dim, c.vocab, c.n_sem);
+  MCK(cudaGetLastError());
+  GemmOp g{};
+  auto lin = [&](const float* A, int M, int K, const float* W, int N, float* Cc, int epi, const float* R, const float* scale) {
+    g = GemmOp{};
+    g.A = A; g.W = W; g.C = Cc; g.R = R; g.scale = scale; g.bias = nullptr;
+    g.M = M; g.N = N; g.K = K; g.Min = M; g.Cin = K; g.taps = 1; g.dil = 1; g.pad = 0; g.ldc = N; g.bias_mod = N; g.epi = epi;
+    g.a_bs = (long long)M * K; g.c_bs = (long long)M * N; g.r_bs = (long long)M * N;
+    return launch_gemm(g, B, st);
+  };
+  int rc;
+  if ((rc = lin(b0, T, C, Wd + m->rvq_w, C, b1, EPI_NONE, nullptr, nullptr))) return rc;
+  upsample_kernel<<<dim3(T2, B), 256, 0, st>>>(b1, Wd + m->up_w, x, T, C);
+  MCK(cudaGetLastError());
+  // ---- transformer
+  const long long rows = (long long)B * T2;
+  for (const sopro_mimi::Layer& L : m->layers) {
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, Wd + L.ln1w, Wd + L.ln1b, ln, rows, C, c.norm_eps);
+    if ((rc = lin(ln, T2, C, Wd + L.qkv, 3 * C, b0, EPI_NONE, nullptr, nullptr))) return rc;
+    rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H);
+    const size_t asm_bytes = (size_t)8 * (Dh + c.window) * 4;
+    attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, b1, T2, C, H, c.window);
+    MCK(cudaGetLastError());
+    if ((rc = lin(b1, T2, C, Wd + L.wo, C, x, EPI_RES_SCALE, x, Wd + L.ls1))) return rc;
+    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, Wd + L.ln2w, Wd + L.ln2b, ln, rows, C, c.norm_eps);
+    if ((rc = lin(ln, T2, C, Wd + L.fc1, FF, b0, EPI_GELU, nullptr, nullptr))) return rc;
+    if ((rc = lin(b0, T2, FF, Wd + L.fc2, C, x, EPI_RES_SCALE, x, Wd + L.ls2))) return rc;
+  }
+  // ---- SEANet decoder
+  auto conv = [&](const float* A, long long Tin, int cin, int taps, int pad, const float* W, const float* bias, int N, int bias_mod,
+                  float* Cc, int elu, int epi, const float* R) {
+    g = GemmOp{};
+    g.A = A; g.W = W; g.C = Cc; g.R = R; g.bias = bias; g.scale = nullptr;
+    g.M = (int)Tin; g.N = N; g.K = taps * cin; g.Min = (int)Tin; g.Cin = cin; g.taps = taps; g.dil = 1; g.pad = pad; g.ldc = N;
+    g.bias_mod = bias_mod; g.epi = epi; g.a_elu = elu;
+    g.a_bs = Tin * cin; g.c_bs = Tin * N; g.r_bs = Tin * N;
+    return launch_gemm(g, B, st);
+  };
+  long long Tn = T2;
+  int ch = c.num_filters << c.n_ratios;
+  if ((rc = conv(x, Tn, C, c.kernel, c.kernel - 1, Wd + m->c0w, Wd + m->c0b, ch, ch, b0, 0, EPI_NONE, nullptr))) return rc;
+  float* cur = b0;
+  float* o1 = b1;
+  float* o2 = b2;
+  for (const sopro_mimi::Stage& S : m->stages) {
+    if (Tn * S.ratio > 0x7fffffffLL) return mfail(SOPRO_ERR_INVALID, "sequence too long for one launch");
+    // ELU -> ConvTranspose(stride r, kernel 2r) as a 2-tap implicit GEMM with r*Cout columns
+    if ((rc = conv(cur, Tn, S.cin, 2, 1, Wd + S.tw, Wd + S.tb, S.ratio * S.cout, S.cout, o1, 1, EPI_NONE, nullptr))) return rc;
+    Tn *= S.ratio;
+    // ResnetBlock: o1 + conv1(ELU(conv3(ELU(o1))))
+    const int hid = S.cout / c.compress;
+    if ((rc = conv(o1, Tn, S.cout, c.res_kernel, c.res_kernel - 1, Wd + S.r1w, Wd + S.r1b, hid, hid, o2, 1, EPI_NONE, nullptr))) return rc;
+    if ((rc = conv(o2, Tn, hid, 1, 0, Wd + S.r2w, Wd + S.r2b, S.cout, S.cout, cur, 1, EPI_RES, o1))) return rc;
+    ch = S.cout;
+  }
+  final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
+  MCK(cudaGetLastError());
+  return SOPRO_OK;
+}
+
+int sopro_mimi_decode_host(sopro_mimi_t* m, const int32_t* codes_host, int B, int T, float* wav_host, void* stream) {
+  if (!m || !codes_host || !wav_host) return mfail(SOPRO_ERR_INVALID, "null argument");
+  MCK(cudaSetDevice(m->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t nc = (size_t)B * m->cfg.n_q * T;
+  const size_t nw = (size_t)B * T * sopro_mimi_samples_per_frame(m);
+  if (m->codes_cap < nc * 4 + nw * 4) {
+    cudaFree(m->codes_dev);
+    m->codes_dev = nullptr;
+    m->codes_cap = 0;
+    MCK(cudaMalloc(&m->codes_dev, nc * 4 + nw * 4));
+    m->codes_cap = nc * 4 + nw * 4;
+  }
+  float* wav_dev = reinterpret_cast<float*>(m->codes_dev + nc);
+  MCK(cudaMemcpyAsync(m->codes_dev, codes_host, nc * 4, cudaMemcpyHostToDevice, st));
+  int rc = sopro_mimi_decode(m, m->codes_dev, B, T, wav_dev, stream);
+  if (rc) return rc;
+  MCK(cudaMemcpyAsync(wav_host, wav_dev, nw * 4, cudaMemcpyDeviceToHost, st));
+  MCK(cudaStreamSynchronize(st));
+  return SOPRO_OK;
+}
+
+}  // extern "C"

@@ -134,3 +134,26 @@ def sampler_case_inputs(spec: dict):
     kw = dict(top_p=spec.get("top_p", 0.9), top_k=spec.get("top_k", 50),
               temperature=spec.get("temperature", 1.05), repetition_penalty=spec.get("repetition_penalty", 1.1))
     return logits, hist, kw, int(spec["seed"])
+
+
+# ---------------------------------------------------------------------------
+# whole-model case (prefill + AR + NAR): full synthetic checkpoint, small text vocabulary
+# ---------------------------------------------------------------------------
+E2E_CASE = dict(text_vocab=1000, L=52, ref_frames=38, max_frames=400, nar_T=50, style_strength=1.0, key=77)
+_E2E_CACHE = {}
+
+
+def e2e_inputs():
+    if "v" not in _E2E_CACHE:
+        cfg = SoproTTSConfig()
+        sd = synth_state_dict(cfg, text_vocab=E2E_CASE["text_vocab"], seed=0)
+        k = E2E_CASE["key"] * 1000
+        def ints(n, key, hi):
+            u = hash_uniform(n, key) * 0.5 + 0.5
+            return torch.from_numpy(np.minimum((u * hi).astype(np.int64), hi - 1))
+        text_ids = ints(E2E_CASE["L"], k + 1, E2E_CASE["text_vocab"])
+        ref_tokens = ints(E2E_CASE["ref_frames"] * 32, k + 2, 2048).view(E2E_CASE["ref_frames"], 32)
+        rvq1 = ints(E2E_CASE["nar_T"], k + 3, 2048)
+        _E2E_CACHE["v"] = (cfg, sd, dict(text_ids=text_ids, ref_tokens_tq=ref_tokens, rvq1=rvq1, max_frames=E2E_CASE["max_frames"],
+                                         nar_T=E2E_CASE["nar_T"], style_strength=E2E_CASE["style_strength"]))
+    return _E2E_CACHE["v"]
