@@ -1,0 +1,310 @@
+"""Public API: ``SoproTTS`` with the reference's signatures (reference model.py:404-583) over the B200 engine.
+
+``SoproTTS.model`` is a ``SoproModel``: it stands where the reference's ``SoproTTSModel`` stands
+(model.py:53-401) and keeps its method names, but ``ar_stream`` drives the persistent CUDA kernel and the
+codec decodes with the CUDA Mimi engine.  Prefill and the NAR refiner are torch ops on the same device
+(sopro_b200/prefill.py).  There is no CPU path: constructing the model without a CUDA device raises.
+
+Randomness: like the reference, sampling consumes the GLOBAL torch CPU generator (the reference has no seed
+argument; its CLI calls torch.manual_seed, cli.py:72-75), one [V]-sized Exp(1) draw per generated frame, so
+``torch.manual_seed(s); tts.synthesize(...)`` reproduces the reference's token ids.  Every generating method
+additionally accepts ``seed=`` / ``generator=`` (an extension) to leave the global generator untouched.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Iterator, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import prefill as P
+from .codec import MimiCodec
+from .config import TARGET_SR, SoproTTSConfig
+from .engine import ArEngine, ArSession, Sampling
+from .prefill import PreparedReference
+from .weights import load_safetensors, read_safetensors_cfg
+
+
+def center_crop_tokens(ref_tq: torch.Tensor, win_frames: int) -> torch.Tensor:
+    """reference sampling.py:8-13"""
+    T = int(ref_tq.size(0))
+    if T <= win_frames:
+        return ref_tq
+    s = (T - win_frames) // 2
+    return ref_tq[s: s + win_frames]
+
+
+class _Noise:
+    """The Exp(1) draws `steps` successive torch.multinomial calls would consume (see sopro_b200/sampling.py),
+    with the bookkeeping needed to leave the generator exactly where the reference would leave it."""
+
+    def __init__(self, steps: int, vocab: int, seed: Optional[int], generator: Optional[torch.Generator]):
+        self.vocab = vocab
+        self.private = seed is not None
+        self.gen = torch.Generator().manual_seed(int(seed)) if seed is not None else (generator or torch.default_generator)
+        self.state = self.gen.get_state()
+        self.tape = torch.empty(int(steps), int(vocab)).exponential_(1.0, generator=self.gen)
+
+    def settle(self, steps_used: int) -> None:
+        """Rewind to the state after exactly `steps_used` draws (the reference stops drawing when it stops stepping)."""
+        if self.private:
+            return
+        self.gen.set_state(self.state)
+        if steps_used > 0:
+            torch.empty(int(steps_used), int(self.vocab)).exponential_(1.0, generator=self.gen)
+
+
+class SoproModel:
+    def __init__(self, cfg: SoproTTSConfig, state_dict: Dict[str, torch.Tensor], device, weight_dtype: str = "fp32"):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("sopro_b200 runs on CUDA devices only (sm_100a); there is no CPU fallback")
+        self.cfg = cfg
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.eos_id = int(cfg.codebook_size)
+        self.weight_dtype = weight_dtype
+        self.engine = ArEngine(cfg, state_dict, self.device, weight_dtype)
+        # prefill / NAR weights live on the device as fp32 torch tensors
+        skip = ("ar.blocks.", "ar.head.", "ar.norm.")
+        self.sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()
+                   if not k.startswith(skip) and v.is_floating_point()}
+        self.text_pos = P.sinusoid_table(int(cfg.max_text_len) + 8, int(cfg.d_model), self.device)
+        self.frame_pos = P.sinusoid_table(int(cfg.pos_emb_max) + 8, int(cfg.d_model), self.device)
+        self._sessions: Dict[Tuple[int, int, int], ArSession] = {}
+
+    # ---- geometry helpers (reference model.py:119-131)
+    def rf_ar(self) -> int:
+        return self.cfg.rf_ar()
+
+    def rf_nar(self) -> int:
+        return self.cfg.rf_nar()
+
+    def eval(self):
+        return self
+
+    def _session(self, batch: int, steps: int, text_len: int) -> ArSession:
+        key = (int(batch), int(steps), (int(text_len) + 63) // 64 * 64)
+        if key not in self._sessions:
+            if len(self._sessions) >= 8:
+                self._sessions.pop(next(iter(self._sessions))).close()
+            self._sessions[key] = self.engine.session(*key)
+        return self._sessions[key]
+
+    # ---- prefill (torch)
+    @torch.no_grad()
+    def prepare_reference(self, ref_tokens_tq: torch.Tensor, *, device=None) -> PreparedReference:
+        return P.prepare_reference(self.sd, self.cfg, ref_tokens_tq, self.device)
+
+    @torch.no_grad()
+    def prepare_conditioning(self, text_ids_1d: torch.Tensor, ref: PreparedReference, *, max_frames: int, device=None,
+                             style_strength: float = 1.2) -> Dict[str, torch.Tensor]:
+        return P.prepare_conditioning(self.sd, self.cfg, text_ids_1d, ref, max_frames=max_frames, device=self.device,
+                                      style_strength=style_strength, text_pos=self.text_pos, frame_pos=self.frame_pos)
+
+    @torch.no_grad()
+    def nar_refine(self, cond_seq: torch.Tensor, rvq1_1xT: torch.Tensor) -> torch.Tensor:
+        return P.nar_refine(self.sd, self.cfg, cond_seq, rvq1_1xT)
+
+    # ---- the hot path
+    def _sampling(self, top_p, temperature, anti_loop, loop_streak, recovery_top_p, recovery_temp, min_gen_frames,
+                  stop_on_first_eos) -> Sampling:
+        mg = int(min_gen_frames if min_gen_frames is not None else self.cfg.min_gen_frames)
+        return Sampling(top_p=float(top_p), temperature=float(temperature), recovery_top_p=float(recovery_top_p),
+                        recovery_temp=float(recovery_temp), repetition_penalty=1.1, top_k=50, anti_loop=bool(anti_loop),
+                        loop_streak=int(loop_streak), min_gen_frames=min(mg, 2 ** 31 - 1), stop_on_first_eos=stop_on_first_eos)
+
+    @torch.no_grad()
+    def ar_stream(self, prep: Dict[str, torch.Tensor], *, max_frames: int, top_p: float = 0.9, temperature: float = 1.05,
+                  anti_loop: bool = True, loop_streak: int = 8, recovery_top_p: float = 0.85, recovery_temp: float = 1.2,
+                  min_gen_frames: Optional[int] = None, launch_frames: int = 0, seed: Optional[int] = None,
+                  generator: Optional[torch.Generator] = None) -> Iterator[Tuple[int, int, bool]]:
+        """Yields (t, token, is_eos) like the reference generator (model.py:218-305).  The persistent kernel runs
+        `launch_frames` frames per launch (0 = the whole utterance in one launch); a consumer that stops iterating
+        early simply abandons the frames computed ahead, and the RNG is settled to the frames actually consumed."""
+        cond, txt = prep["cond_ar"], prep["txt_seq"]
+        steps = int(max_frames) + 1
+        if cond.size(1) < steps:
+            raise ValueError(f"cond_ar has {cond.size(1)} rows, need max_frames+1 = {steps}")
+        L = int(txt.size(1))
+        noise = _Noise(steps, self.cfg.ar_vocab(), seed, generator)
+        ses = self._session(1, steps, L)
+        samp = self._sampling(top_p, temperature, anti_loop, loop_streak, recovery_top_p, recovery_temp, min_gen_frames, False)
+        ses.begin(cond[:, :steps], txt, [L], noise.tape[:, : samp.top_k].contiguous().unsqueeze(0), samp)
+        per = steps if launch_frames <= 0 else int(launch_frames)
+        t = 0
+        used = 0
+        try:
+            while t < steps:
+                ses.run(per)
+                toks, n, done = ses.read()
+                upto = int(n[0])
+                while t < upto:
+                    tok = int(toks[0, t])
+                    used = t + 1
+                    yield t, tok, tok == self.eos_id
+                    t += 1
+                if done[0] or upto < min(steps, ses.position):
+                    break
+        finally:
+            noise.settle(used)
+
+    @torch.no_grad()
+    def ar_generate_batch(self, preps: Sequence[Dict[str, torch.Tensor]], *, max_frames: int, top_p: float = 0.9,
+                          temperature: float = 1.05, anti_loop: bool = True, min_gen_frames: Optional[int] = None,
+                          seeds: Optional[Sequence[int]] = None, stop_on_first_eos: bool = True) -> List[List[int]]:
+        """NEW capability (the reference is batch-1): B independent utterances in ONE persistent launch.  Utterance i
+        equals the reference run alone with seed seeds[i].  Without seeds the global generator is
+        consumed utterance after utterance, full length each."""
+        B, steps = len(preps), int(max_frames) + 1
+        D, V = int(self.cfg.d_model), self.cfg.ar_vocab()
+        lens = [int(p["txt_seq"].size(1)) for p in preps]
+        Ls = max(lens)
+        cond = torch.stack([p["cond_ar"][0, :steps] for p in preps])
+        txt = torch.zeros(B, Ls, D, device=self.device)
+        for i, p in enumerate(preps):
+            txt[i, : lens[i]] = p["txt_seq"][0]
+        tapes = [_Noise(steps, V, None if seeds is None else int(seeds[i]), None).tape[:, :50] for i in range(B)]
+        ses = self._session(B, steps, Ls)
+        samp = self._sampling(top_p, temperature, anti_loop, 8, 0.85, 1.2, min_gen_frames, stop_on_first_eos)
+        ses.begin(cond, txt, lens, torch.stack(tapes).contiguous(), samp)
+        ses.run()
+        toks, n, _ = ses.read()
+        return [toks[i, : n[i]].tolist() for i in range(B)]
+
+    @torch.no_grad()
+    def generate_tokens(self, text_ids_1d: torch.Tensor, ref: PreparedReference, *, max_frames: int, device=None,
+                        top_p: float = 0.9, temperature: float = 1.05, anti_loop: bool = True, style_strength: float = 1.2,
+                        min_gen_frames: Optional[int] = None, seed: Optional[int] = None,
+                        generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """reference model.py:349-401: prefill, AR until the first EOS, cut there, NAR refine -> [T, Q] int64."""
+        prep = self.prepare_conditioning(text_ids_1d, ref, max_frames=max_frames, style_strength=style_strength)
+        hist: List[int] = []
+        for _t, tok, is_eos in self.ar_stream(prep, max_frames=max_frames, top_p=top_p, temperature=temperature,
+                                              anti_loop=anti_loop, min_gen_frames=min_gen_frames, seed=seed, generator=generator):
+            hist.append(tok)
+            if is_eos:
+                break
+        T = hist.index(self.eos_id) if self.eos_id in hist else len(hist)
+        if T <= 0:
+            return torch.zeros((0, int(self.cfg.num_codebooks)), dtype=torch.long, device=self.device)
+        rvq1 = torch.tensor(hist[:T], device=self.device, dtype=torch.long).unsqueeze(0)
+        return self.nar_refine(prep["cond_ar"][:, :T, :], rvq1).squeeze(0)
+
+
+class SoproTTS:
+    def __init__(self, model: SoproModel, cfg: SoproTTSConfig, tokenizer, codec: MimiCodec, device: str):
+        self.model = model
+        self.cfg = cfg
+        self.tokenizer = tokenizer
+        self.codec = codec
+        self.device = torch.device(device)
+
+    # ---- construction
+    @classmethod
+    def from_pretrained(cls, repo_id: str, *, revision: Optional[str] = None, cache_dir: Optional[str] = None,
+                        token: Optional[str] = None, device: Optional[str] = None, weight_dtype: str = "fp32") -> "SoproTTS":
+        """reference model.py:419-451: HF snapshot -> cfg from the safetensors header -> tokenizer -> weights -> Mimi."""
+        from huggingface_hub import snapshot_download
+
+        from .tokenizer import TextTokenizer
+
+        device = device or "cuda"
+        local_dir = repo_id if os.path.isdir(repo_id) else snapshot_download(repo_id=repo_id, revision=revision,
+                                                                             cache_dir=cache_dir, token=token)
+        model_path = os.path.join(local_dir, "model.safetensors")
+        if not os.path.exists(model_path):
+            raise FileNotFoundError(f"Expected {model_path} in repo snapshot.")
+        cfg = read_safetensors_cfg(model_path)
+        tokenizer = TextTokenizer(model_name=local_dir)
+        model = SoproModel(cfg, load_safetensors(model_path), device, weight_dtype)
+        codec = MimiCodec(num_quantizers=cfg.num_codebooks, device=device)
+        return cls(model=model, cfg=cfg, tokenizer=tokenizer, codec=codec, device=device)
+
+    @classmethod
+    def from_state_dict(cls, cfg: SoproTTSConfig, state_dict: Dict[str, torch.Tensor], tokenizer,
+                        mimi_state_dict: Dict[str, torch.Tensor], *, device: str = "cuda", weight_dtype: str = "fp32",
+                        mimi_hf_model=None) -> "SoproTTS":
+        """Offline constructor (synthetic or locally stored checkpoints): no hub access."""
+        model = SoproModel(cfg, state_dict, device, weight_dtype)
+        codec = MimiCodec(int(cfg.num_codebooks), device=device, state_dict=mimi_state_dict, hf_model=mimi_hf_model)
+        return cls(model=model, cfg=cfg, tokenizer=tokenizer, codec=codec, device=device)
+
+    # ---- reference plumbing (model.py:453-529)
+    def encode_text(self, text: str) -> torch.Tensor:
+        return torch.tensor(self.tokenizer.encode(text), dtype=torch.long, device=self.device)
+
+    def encode_reference(self, *, ref_audio_path: Optional[str] = None, ref_tokens_tq: Optional[torch.Tensor] = None,
+                         ref_seconds: Optional[float] = None) -> torch.Tensor:
+        if ref_tokens_tq is None and ref_audio_path is None:
+            raise RuntimeError("SoproTTS requires a reference. Provide ref_audio_path=... or ref_tokens_tq=...")
+        if ref_tokens_tq is not None and ref_audio_path is not None:
+            raise RuntimeError("Provide only one of ref_audio_path or ref_tokens_tq (not both).")
+        if ref_seconds is None:
+            ref_seconds = 12.0
+        if ref_tokens_tq is not None:
+            ref = ref_tokens_tq.to(self.device).long()
+            if ref_seconds and ref_seconds > 0:
+                ref = center_crop_tokens(ref, max(1, int(round(ref_seconds * float(self.cfg.mimi_fps)))))
+            return ref
+        crop = ref_seconds if ref_seconds is not None and ref_seconds > 0 else None
+        return self.codec.encode_file(ref_audio_path, crop_seconds=crop).to(self.device).long()
+
+    @torch.inference_mode()
+    def encode_speaker(self, **kw) -> torch.Tensor:
+        ref = self.encode_reference(**kw).unsqueeze(0)
+        lengths = torch.tensor([int(ref.size(1))], device=self.device, dtype=torch.long)
+        return P.token2sv(self.model.sd, self.cfg, ref, lengths).squeeze(0).detach()
+
+    @torch.inference_mode()
+    def prepare_reference(self, *, ref_audio_path: Optional[str] = None, ref_tokens_tq: Optional[torch.Tensor] = None,
+                          ref_seconds: Optional[float] = None) -> PreparedReference:
+        tokens_tq = self.encode_reference(ref_audio_path=ref_audio_path, ref_tokens_tq=ref_tokens_tq, ref_seconds=ref_seconds)
+        return self.model.prepare_reference(tokens_tq, device=self.device)
+
+    # ---- synthesis (model.py:531-580)
+    @torch.inference_mode()
+    def synthesize(self, text: str, *, ref: Optional[PreparedReference] = None, ref_audio_path: Optional[str] = None,
+                   ref_tokens_tq: Optional[torch.Tensor] = None, max_frames: int = 400, top_p: float = 0.9,
+                   temperature: float = 1.05, anti_loop: bool = True, style_strength: Optional[float] = None,
+                   ref_seconds: Optional[float] = None, min_gen_frames: Optional[int] = None, seed: Optional[int] = None,
+                   generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        text_ids = self.encode_text(text)
+        if ref is None:
+            ref = self.prepare_reference(ref_audio_path=ref_audio_path, ref_tokens_tq=ref_tokens_tq, ref_seconds=ref_seconds)
+        tokens_tq = self.model.generate_tokens(
+            text_ids, ref=ref, max_frames=max_frames, top_p=top_p, temperature=temperature, anti_loop=anti_loop,
+            style_strength=float(style_strength if style_strength is not None else self.cfg.style_strength),
+            min_gen_frames=min_gen_frames, seed=seed, generator=generator)
+        return self.codec.decode_full(tokens_tq)
+
+    @torch.inference_mode()
+    def synthesize_batch(self, texts: Sequence[str], *, ref: PreparedReference, max_frames: int = 400, top_p: float = 0.9,
+                         temperature: float = 1.05, anti_loop: bool = True, style_strength: Optional[float] = None,
+                         min_gen_frames: Optional[int] = None, seeds: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
+        """NEW: B texts with one shared prepared reference -> B waveforms [1, 1, N_i]; the AR tokens of all
+        utterances come from one persistent kernel launch."""
+        st = float(style_strength if style_strength is not None else self.cfg.style_strength)
+        preps = [self.model.prepare_conditioning(self.encode_text(t), ref, max_frames=max_frames, style_strength=st) for t in texts]
+        hists = self.model.ar_generate_batch(preps, max_frames=max_frames, top_p=top_p, temperature=temperature,
+                                             anti_loop=anti_loop, min_gen_frames=min_gen_frames, seeds=seeds)
+        out = []
+        eos = self.model.eos_id
+        for prep, h in zip(preps, hists):
+            T = h.index(eos) if eos in h else len(h)
+            if T <= 0:
+                out.append(torch.zeros(1, 1, 0, device=self.device))
+                continue
+            rvq1 = torch.tensor(h[:T], device=self.device, dtype=torch.long).unsqueeze(0)
+            out.append(self.codec.decode_full(self.model.nar_refine(prep["cond_ar"][:, :T], rvq1).squeeze(0)))
+        return out
+
+    def stream(self, text: str, **kwargs) -> Iterator[torch.Tensor]:
+        from .streaming import stream as _stream
+
+        return _stream(self, text, **kwargs)
+
+    def save_wav(self, path: str, wav_1xT: torch.Tensor) -> None:
+        from .audio import save_audio
+
+        save_audio(path, wav_1xT, sr=TARGET_SR)

@@ -1,0 +1,120 @@
+"""GPU: the public API end to end (prefill -> persistent AR kernel -> NAR -> CUDA Mimi) against the oracles."""
+import io
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ar_oracle as O
+from oracle import mimi_oracle as M
+from tests.cases import e2e_inputs
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+_TTS = {}
+
+
+def _tts():
+    if "t" not in _TTS:
+        from sopro_b200 import SoproTTS
+        from sopro_b200.tokenizer import IdsTokenizer
+
+        cfg, sd, inp = e2e_inputs()
+        _TTS["mimi_sd"] = M.synth_mimi_state_dict()
+        _TTS["t"] = SoproTTS.from_state_dict(cfg, sd, IdsTokenizer(1000), _TTS["mimi_sd"], device="cuda:0")
+    return _TTS["t"], _TTS["mimi_sd"]
+
+
+TEXT = " ".join(str(7 * i + 3) for i in range(20))
+
+
+def test_synthesize_matches_oracle_pipeline():
+    tts, mimi_sd = _tts()
+    cfg, sd, inp = e2e_inputs()
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    F = 40
+    # --- product
+    wav = tts.synthesize(TEXT, ref=ref, max_frames=F, seed=11, min_gen_frames=10 ** 9)
+    assert wav.shape == (1, 1, (F + 1) * 1920) and wav.dtype == torch.float32 and wav.device.type == "cuda"
+    # --- oracle, fed the device-computed conditioning (cond_ar / txt_seq are the kernel's INPUTS)
+    prep = tts.model.prepare_conditioning(tts.encode_text(TEXT), ref, max_frames=F, style_strength=cfg.style_strength)
+    tape = O.noise_tape(11, F + 1, cfg.ar_vocab())
+    want = O.ar_generate(sd, cfg, prep["cond_ar"].cpu(), prep["txt_seq"].cpu(), torch.ones(1, prep["txt_seq"].size(1), dtype=torch.bool),
+                         max_frames=F, sampling=O.ArSampling(min_gen_frames=10 ** 9), noise_tv=tape)
+    toks = tts.model.generate_tokens(tts.encode_text(TEXT), ref, max_frames=F, style_strength=cfg.style_strength, seed=11,
+                                     min_gen_frames=10 ** 9)
+    assert toks.shape == (F + 1, 32)
+    assert toks[:, 0].tolist() == want  # AR ids bit-identical
+    # NAR: argmax of torch ops on GPU vs CPU may flip on exact near-ties only
+    from sopro_b200 import prefill as P
+
+    nar_cpu = P.nar_refine({k: v.cpu() for k, v in tts.model.sd.items()}, cfg, prep["cond_ar"][:, : F + 1].cpu(),
+                           torch.tensor(want).unsqueeze(0))[0]
+    assert float((nar_cpu == toks.cpu()).float().mean()) >= 0.995
+    # Mimi: decode the product's own tokens with the oracle
+    ref_wav = M.mimi_decode(mimi_sd, toks.cpu().permute(1, 0).unsqueeze(0))
+    err = float((wav.cpu() - ref_wav).abs().max())
+    assert err <= 2e-4 * max(1.0, float(ref_wav.abs().max())), err
+
+
+def test_global_rng_is_consumed_like_the_reference():
+    """No seed kwarg: the global CPU generator is used, and left where `n` multinomial calls would leave it."""
+    tts, _ = _tts()
+    cfg, sd, inp = e2e_inputs()
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    ids = tts.encode_text(TEXT)
+    torch.manual_seed(5)
+    a = tts.model.generate_tokens(ids, ref, max_frames=24, style_strength=1.0, min_gen_frames=10 ** 9)
+    after = torch.get_rng_state()
+    torch.manual_seed(5)
+    b = tts.model.generate_tokens(ids, ref, max_frames=24, style_strength=1.0, min_gen_frames=10 ** 9)
+    assert torch.equal(a, b)
+    torch.manual_seed(5)
+    torch.empty(a.size(0), cfg.ar_vocab()).exponential_(1.0)
+    assert torch.equal(torch.get_rng_state(), after)
+    c = tts.model.generate_tokens(ids, ref, max_frames=24, style_strength=1.0, min_gen_frames=10 ** 9, seed=5)
+    assert torch.equal(a, c)
+
+
+def test_stream_chunks():
+    tts, _ = _tts()
+    cfg, sd, inp = e2e_inputs()
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    chunks = list(tts.stream(TEXT, ref=ref, max_frames=20, seed=3, min_gen_frames=10 ** 9))
+    # the stream ends at the first EOS whatever min_gen_frames says (reference streaming.py:114-115)
+    prep = tts.model.prepare_conditioning(tts.encode_text(TEXT), ref, max_frames=20, style_strength=cfg.style_strength)
+    toks = [tok for _t, tok, _e in tts.model.ar_stream(prep, max_frames=20, seed=3, min_gen_frames=10 ** 9)]
+    n = toks.index(2048) if 2048 in toks else len(toks)
+    want = [6] * (n // 6) + ([n % 6] if n % 6 else [])
+    assert [c.shape for c in chunks] == [(1, k * 1920) for k in want]
+    assert all(torch.isfinite(c).all() for c in chunks)
+    again = list(tts.stream(TEXT, ref=ref, max_frames=20, seed=3, min_gen_frames=10 ** 9))
+    assert all(torch.equal(a, b) for a, b in zip(chunks, again))
+
+
+def test_batch_synthesis_equals_single():
+    tts, _ = _tts()
+    cfg, sd, inp = e2e_inputs()
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    texts = [TEXT, " ".join(str(i) for i in range(3, 40, 3)), "5 9"]
+    wavs = tts.synthesize_batch(texts, ref=ref, max_frames=16, seeds=[1, 2, 3], min_gen_frames=10 ** 9)
+    for t, s, w in zip(texts, [1, 2, 3], wavs):
+        single = tts.synthesize(t, ref=ref, max_frames=16, seed=s, min_gen_frames=10 ** 9)
+        assert torch.equal(single, w)
+
+
+def test_prepared_reference_roundtrips_through_torch_save():
+    tts, _ = _tts()
+    cfg, sd, inp = e2e_inputs()
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    assert ref.ref_tokens_btq.shape == (1, 38, 32) and ref.sv_ref.shape == (1, 192) and ref.ref_seq.shape == (1, 38, 384)
+    assert len(ref.ref_kv_caches) == 3 and ref.ref_kv_caches[0]["k"].shape == (1, 2, 38, 192)
+    buf = io.BytesIO()
+    torch.save(ref, buf)
+    buf.seek(0)
+    back = torch.load(buf, weights_only=False)
+    assert torch.equal(back.ref_seq, ref.ref_seq)
+    with pytest.raises(RuntimeError):
+        tts.prepare_reference()
+    with pytest.raises(RuntimeError):
+        tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"], ref_audio_path="x.wav")

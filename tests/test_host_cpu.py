@@ -1,0 +1,122 @@
+"""CPU: host logic that needs no GPU - prefill/NAR against the reference fixtures, the API surface, the C-ABI
+library's exported symbols, the synthetic checkpoint generator, audio I/O."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import E2E_CASE, e2e_inputs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+torch.set_grad_enabled(False)
+
+
+def test_prefill_and_nar_match_reference_fixtures():
+    from sopro_b200 import prefill as P
+
+    cfg, sd, inp = e2e_inputs()
+    g = np.load(os.path.join(GOLD, "e2e_prefill.npz"))
+    dev = torch.device("cpu")
+    pr = P.prepare_reference(sd, cfg, inp["ref_tokens_tq"], dev)
+    tpos = P.sinusoid_table(int(cfg.max_text_len) + 8, int(cfg.d_model), dev)
+    fpos = P.sinusoid_table(int(cfg.pos_emb_max) + 8, int(cfg.d_model), dev)
+    prep = P.prepare_conditioning(sd, cfg, inp["text_ids"], pr, max_frames=inp["max_frames"], device=dev,
+                                  style_strength=inp["style_strength"], text_pos=tpos, frame_pos=fpos)
+    tol = dict(rtol=0, atol=2e-5)
+    np.testing.assert_allclose(pr.sv_ref.numpy(), g["sv_ref"], **tol)
+    np.testing.assert_allclose(pr.ref_seq[0, :4].numpy(), g["ref_seq_rows"], **tol)
+    np.testing.assert_allclose(pr.ref_kv_caches[2]["k"][0, :, :2].numpy(), g["k2_rows"], **tol)
+    np.testing.assert_allclose(prep["txt_seq"][0, :4].numpy(), g["txt_seq_rows"], **tol)
+    np.testing.assert_allclose(prep["txt_pool"].numpy(), g["txt_pool"], **tol)
+    np.testing.assert_allclose(prep["cond_ar"][0, g["cond_rows_idx"].tolist()].numpy(), g["cond_rows"], **tol)
+    assert abs(float(prep["cond_ar"].abs().mean()) - float(g["cond_absmean"])) < 1e-5
+    nar = P.nar_refine(sd, cfg, prep["cond_ar"][:, : inp["nar_T"]], inp["rvq1"].unsqueeze(0))[0]
+    assert float((nar.numpy() == g["nar_tokens"].astype(np.int64)).mean()) >= 0.999
+    assert nar[:, 0].tolist() == inp["rvq1"].tolist()
+
+
+def test_api_surface_mirrors_the_reference():
+    """Signatures of SURVEY.md §8b (reference model.py:419-428, 516-523, 531-546, 577-580; streaming.py:134-143)."""
+    from sopro_b200 import SoproTTS
+    from sopro_b200.streaming import SoproTTSStreamer, stream
+
+    def params(f):
+        return list(inspect.signature(f).parameters)
+
+    assert params(SoproTTS.__init__) == ["self", "model", "cfg", "tokenizer", "codec", "device"]
+    assert params(SoproTTS.from_pretrained)[:5] == ["repo_id", "revision", "cache_dir", "token", "device"]
+    assert params(SoproTTS.prepare_reference) == ["self", "ref_audio_path", "ref_tokens_tq", "ref_seconds"]
+    ref_syn = ["self", "text", "ref", "ref_audio_path", "ref_tokens_tq", "max_frames", "top_p", "temperature", "anti_loop",
+               "style_strength", "ref_seconds", "min_gen_frames"]
+    assert params(SoproTTS.synthesize)[: len(ref_syn)] == ref_syn
+    d = inspect.signature(SoproTTS.synthesize).parameters
+    assert (d["max_frames"].default, d["top_p"].default, d["temperature"].default, d["anti_loop"].default) == (400, 0.9, 1.05, True)
+    assert inspect.signature(stream).parameters["chunk_frames"].default == 6
+    for name in ("encode_text", "encode_reference", "encode_speaker", "save_wav", "stream"):
+        assert callable(getattr(SoproTTS, name))
+    assert "nar_context_frames" in params(SoproTTSStreamer.stream)
+
+
+def test_shared_library_exports_every_declared_symbol():
+    from sopro_b200 import _lib
+
+    hdr = open(os.path.join(ROOT, "include", "sopro_b200.h")).read()
+    declared = set(re.findall(r"\b(sopro_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"sopro_status"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().sopro_version().startswith(b"sopro_b200")
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("needs a GPU-less host")
+    from sopro_b200 import _lib
+    from sopro_b200.config import SoproTTSConfig
+    from sopro_b200.engine import ArEngine
+    from sopro_b200.model import SoproModel
+
+    with pytest.raises(RuntimeError):
+        SoproModel(SoproTTSConfig(), {}, "cpu")
+    from tests.cases import AR_CASES, ar_case_inputs
+
+    cfg, sd, _ = ar_case_inputs(AR_CASES["small_fp32"])
+    with pytest.raises(_lib.SoproError):
+        ArEngine(cfg, sd, 0)  # no device: the C-ABI refuses, nothing silently runs on the host
+
+
+def test_synthetic_checkpoint_is_deterministic_and_complete():
+    from sopro_b200.config import SoproTTSConfig
+    from sopro_b200.weights import ar_step_param_names, hash_uniform, param_specs, synth_state_dict
+
+    u = hash_uniform(5, 42)
+    np.testing.assert_array_equal(u, hash_uniform(5, 42))
+    assert u.dtype == np.float32 and np.all(np.abs(u) <= 1)
+    cfg = SoproTTSConfig()
+    specs = param_specs(cfg, 128257)
+    assert sum(int(np.prod(s)) if s else 1 for s, _, _ in specs.values()) == 132260272  # + 32 for the ref_cb_weights buffer
+    sd = synth_state_dict(cfg, 64, 0, only_prefix=("ar.",))
+    n_step = sum(sd[k].numel() for k in ar_step_param_names(cfg))
+    assert n_step == 10575492  # SURVEY.md §8d W_step
+
+
+def test_wav_roundtrip(tmp_path):
+    from sopro_b200.audio import load_audio_file, save_audio, trim_silence_energy
+
+    sr = 24000
+    t = torch.arange(sr) / sr
+    wav = torch.cat([torch.zeros(sr // 2), 0.5 * torch.sin(2 * np.pi * 440 * t), torch.zeros(sr // 2)])
+    p = str(tmp_path / "a.wav")
+    save_audio(p, wav.view(1, 1, -1), sr)
+    back, sr2 = load_audio_file(p)
+    assert sr2 == sr and back.shape == (1, wav.numel())
+    assert float((back[0] - wav).abs().max()) < 1e-3
+    trimmed = trim_silence_energy(back, sr)
+    assert sr * 0.9 < trimmed.shape[-1] < wav.numel()
