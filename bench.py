@@ -157,6 +157,82 @@ def cpu_reference_sample(cfg, sd, n_utts, threads, seed_base=1234):
     return frames / dt, dt
 
 
+def extras(cfg, dev):
+    """Side measurements of the other BASELINE.json configs on one GPU (not the headline `value`):
+    batch-1 AR rate (fp32, configs[1]), stream() time-to-first-audio p50 (configs[1]), end-to-end RTF of
+    synthesize() at batch 1 and synthesize_batch() at batch 64 (configs[1]/[2]), Mimi decode of 10k frames (configs[4])."""
+    from sopro_b200 import SoproTTS
+    from sopro_b200.engine import ArEngine, Sampling
+    from sopro_b200.tokenizer import IdsTokenizer
+    from sopro_b200.weights import synth_mimi_state_dict, synth_state_dict
+
+    out = {}
+    sd_full = synth_state_dict(cfg, 1000, 0)
+    tts = SoproTTS.from_state_dict(cfg, sd_full, IdsTokenizer(1000), synth_mimi_state_dict(), device=str(dev))
+    ref_tokens = torch.randint(0, 2048, (38, 32), generator=torch.Generator().manual_seed(7))
+    ref = tts.prepare_reference(ref_tokens_tq=ref_tokens)
+    text = " ".join(str(17 * i + 5) for i in range(50))  # 50 ids + BOS/EOS = 52
+
+    def timed(fn, n, warm=2):
+        ts = []
+        for i in range(n + warm):
+            torch.cuda.synchronize(dev)
+            t0 = time.perf_counter()
+            r = fn()
+            torch.cuda.synchronize(dev)
+            if i >= warm:
+                ts.append(time.perf_counter() - t0)
+        return float(np.median(ts)), r
+
+    # batch-1 AR rate, fp32 weights, device resident
+    eng = tts.model.engine
+    cond, txt, noise = _inputs(cfg, 0, 1, STEPS_AR, TEXT_LEN)
+    cond, txt, noise = cond.to(dev), txt.to(dev), noise.to(dev)
+    ses = eng.session(1, STEPS_AR, TEXT_LEN)
+    sp = Sampling(min_gen_frames=2 ** 31 - 1)
+
+    def ar1():
+        ses.begin(cond, txt, [TEXT_LEN], noise, sp)
+        ses.run()
+
+    t, _ = timed(ar1, 5)
+    out["batch1_ar_frames_per_sec_fp32"] = STEPS_AR / t
+    out["batch1_us_per_ar_step_fp32"] = t / STEPS_AR * 1e6
+    # TTFA p50: stream() with a prepared reference, default chunk_frames=6 (reference streaming.py:141)
+    def first_chunk():
+        it = tts.stream(text, ref=ref, max_frames=FRAMES, seed=1, min_gen_frames=10 ** 9)
+        c = next(it)
+        it.close()
+        return c
+
+    ts = []
+    for i in range(22):
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        c = first_chunk()
+        torch.cuda.synchronize(dev)
+        if i >= 2:
+            ts.append(time.perf_counter() - t0)
+    out["ttfa_ms_p50"] = float(np.median(ts)) * 1e3
+    out["ttfa_first_chunk_samples"] = int(c.numel())
+    # RTF: whole synthesize() (tokenize + prefill + AR + NAR + Mimi) / audio seconds
+    t, wav = timed(lambda: tts.synthesize(text, ref=ref, max_frames=FRAMES, seed=1, min_gen_frames=10 ** 9), 3, warm=1)
+    out["rtf_batch1"] = t / (wav.shape[-1] / 24000.0)
+    out["synthesize_batch1_ms"] = t * 1e3
+    texts = [" ".join(str(17 * i + 5 + j) for i in range(50)) for j in range(64)]
+    t, wavs = timed(lambda: tts.synthesize_batch(texts, ref=ref, max_frames=FRAMES, seeds=list(range(64)), min_gen_frames=10 ** 9), 1, warm=1)
+    out["rtf_batch64"] = t / sum(w.shape[-1] / 24000.0 for w in wavs)
+    out["synthesize_batch64_ms"] = t * 1e3
+    # Mimi standalone: 25 x 400 = 10k frames
+    codes = torch.randint(0, 2048, (25, 32, 400), generator=torch.Generator().manual_seed(5)).to(dev)
+    t, _ = timed(lambda: tts.codec.engine.decode(codes), 3, warm=1)
+    out["mimi_frames_per_sec"] = 10000 / t
+    out["mimi_ms_per_10k_frames"] = t * 1e3
+    out["mimi_alg_gb_per_s"] = 10000 * 7936 / t / 1e9
+    out["mimi_tflops_fp32"] = 10000 * 431.2e6 / t / 1e12
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +241,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="utterances per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip batch-1 / TTFA / RTF / Mimi side measurements")
     args = ap.parse_args()
     torch.set_grad_enabled(False)
 
@@ -219,26 +296,15 @@ def main():
     from sopro_b200.engine import ArEngine, Sampling
 
     # weights: built on rank 0, broadcast once over NCCL/NVLink (the only collective of the path)
-    names_shapes = None
+    sd = None
     if rank == 0:
         sd = round_through_bf16(synth_state_dict(cfg, 64, 0, only_prefix=("ar.", "cb_embed.")), ("ar.", "cb_embed."))
     if world > 1:
+        from sopro_b200.dp import broadcast_state_dict
         from sopro_b200.weights import param_specs
 
         specs = [(k, v[0]) for k, v in param_specs(cfg, 64).items() if k.startswith(("ar.", "cb_embed."))]
-        total = sum(int(np.prod(s)) if len(s) else 1 for _, s in specs)
-        flat = torch.empty(total, dtype=torch.float32, device=dev)
-        if rank == 0:
-            flat.copy_(torch.cat([sd[k].reshape(-1) for k, _ in specs]))
-        dist.broadcast(flat, src=0)
-        if rank != 0:
-            sd, off = {}, 0
-            host = flat.cpu()
-            for k, s in specs:
-                n = int(np.prod(s)) if len(s) else 1
-                sd[k] = host[off:off + n].view(s).clone()
-                off += n
-        del flat
+        sd = broadcast_state_dict(sd, specs, src=0, device=dev)
     eng = ArEngine(cfg, sd, dev, "bf16")
     B = args.batch
     cond_h, txt_h, noise_h = _inputs(cfg, rank, B, STEPS_AR, TEXT_LEN)
@@ -333,6 +399,11 @@ def main():
         "clocks": clocks.summary(),
         "extra": {"us_per_ar_step": t_kernel_ms / STEPS_AR * 1e3, "frames_per_pass_per_gpu": frames_per_pass},
     }
+    if world == 1 and not args.no_extras:
+        try:
+            line["extra"].update(extras(cfg, dev))
+        except Exception as ex:  # the headline number must survive a failure in the side measurements
+            line["extra"]["extras_error"] = repr(ex)
     if not args.no_cpu_baseline:
         threads, avail = pick_threads(cfg, sd)
         v, dt = cpu_reference_sample(cfg, sd, 16, threads)

@@ -125,54 +125,4 @@ def mimi_decode(sd: SD, codes_bqt: Tensor) -> Tensor:
     return seanet_decoder(sd, x).transpose(1, 2)
 
 
-def synth_mimi_state_dict(seed: int = 5, layer_scale: float = 0.3) -> SD:
-    """Seeded random weights for the decode path of ``MimiModel(MimiConfig(num_quantizers=32))``, platform
-    independent (integer hashing, like sopro_b200.weights).  LayerScale is raised from its 0.01 init so the
-    attention / MLP branches are visible in the output."""
-    import numpy as np
-
-    from sopro_b200.weights import hash_uniform
-
-    def U(name, shape, bound):
-        import zlib
-        n = int(np.prod(shape))
-        return torch.from_numpy(hash_uniform(n, (zlib.crc32(name.encode()) << 20) ^ seed) * np.float32(bound)).view(shape)
-
-    sd: SD = {}
-    for grp, n in (("semantic", 1), ("acoustic", 31)):
-        pre = f"quantizer.{grp}_residual_vector_quantizer."
-        for i in range(n):
-            sd[pre + f"layers.{i}.codebook.embed_sum"] = U(pre + f"{i}.e", (2048, 256), 1.0)
-            sd[pre + f"layers.{i}.codebook.cluster_usage"] = U(pre + f"{i}.u", (2048,), 0.4) + 1.0
-            sd[pre + f"layers.{i}.codebook.initialized"] = torch.ones(1)
-        sd[pre + "output_proj.weight"] = U(pre + "o", (512, 256, 1), 1 / 16.0)
-        sd[pre + "input_proj.weight"] = U(pre + "i", (256, 512, 1), 1 / 22.6)
-    sd["upsample.conv.weight"] = U("up", (512, 1, 4), 0.7)
-    for l in range(8):
-        p = f"decoder_transformer.layers.{l}."
-        for n in ("q", "k", "v", "o"):
-            sd[p + f"self_attn.{n}_proj.weight"] = U(p + n, (512, 512), 1 / 22.6)
-        sd[p + "mlp.fc1.weight"] = U(p + "f1", (2048, 512), 1 / 22.6)
-        sd[p + "mlp.fc2.weight"] = U(p + "f2", (512, 2048), 1 / 45.0)
-        for n in ("input_layernorm", "post_attention_layernorm"):
-            sd[p + n + ".weight"] = 1.0 + U(p + n + "w", (512,), 0.2)
-            sd[p + n + ".bias"] = U(p + n + "b", (512,), 0.1)
-        sd[p + "self_attn_layer_scale.scale"] = layer_scale + U(p + "ls1", (512,), 0.1)
-        sd[p + "mlp_layer_scale.scale"] = layer_scale + U(p + "ls2", (512,), 0.1)
-    chans = [(512, 1024, 7)]
-    sd["decoder.layers.0.conv.weight"] = U("d0w", (1024, 512, 7), 1 / math.sqrt(512 * 7))
-    sd["decoder.layers.0.conv.bias"] = U("d0b", (1024,), 0.02)
-    li, c = 1, 1024
-    for r in UPSAMPLING_RATIOS:
-        sd[f"decoder.layers.{li + 1}.conv.weight"] = U(f"t{li}w", (c, c // 2, 2 * r), 1 / math.sqrt(c * 2))
-        sd[f"decoder.layers.{li + 1}.conv.bias"] = U(f"t{li}b", (c // 2,), 0.02)
-        p = f"decoder.layers.{li + 2}.block."
-        sd[p + "1.conv.weight"] = U(p + "1w", (c // 4, c // 2, 3), 1 / math.sqrt(c // 2 * 3))
-        sd[p + "1.conv.bias"] = U(p + "1b", (c // 4,), 0.02)
-        sd[p + "3.conv.weight"] = U(p + "3w", (c // 2, c // 4, 1), 1 / math.sqrt(c // 4))
-        sd[p + "3.conv.bias"] = U(p + "3b", (c // 2,), 0.02)
-        li += 3
-        c //= 2
-    sd[f"decoder.layers.{li + 1}.conv.weight"] = U("lw", (1, 64, 3), 1 / math.sqrt(64 * 3))
-    sd[f"decoder.layers.{li + 1}.conv.bias"] = U("lb", (1,), 0.02)
-    return sd
+from sopro_b200.weights import synth_mimi_state_dict  # noqa: E402,F401  (seeded random decode-path weights)
