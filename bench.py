@@ -244,6 +244,14 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip batch-1 / TTFA / RTF / Mimi side measurements")
     args = ap.parse_args()
     torch.set_grad_enabled(False)
+    # Libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout.
+    # Everything else goes to stderr, the JSON is written to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,7 +289,7 @@ def main():
                                            "(torch CPU eager restatement of the reference, bit-equal to it); the reference has no "
                                            "batch path, so batch-64 throughput on CPU is this rate"},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     # ------------------------------------------------------------------ B200 arm
@@ -410,7 +418,7 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "cores_available": avail, "kind": "port",
                                 "sample": f"16 utterances x 401 AR frames of the same workload, sequential, {dt:.1f} s "
                                           "(oracle/ar_oracle.py, torch CPU eager; the reference has no batch path)"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

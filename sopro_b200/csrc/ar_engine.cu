@@ -105,6 +105,8 @@ struct sopro_ar_session {
   UttState* st = nullptr;
   SamplingDev* samp = nullptr;
   unsigned* barrier = nullptr;
+  unsigned* tok_ll = nullptr;
+  unsigned seq_base = 0;
   TileDesc* tiles = nullptr;  // [n_sms][kMaxTilesPerStep]
   int* n_tiles = nullptr;     // [n_sms]
   unsigned char* stage_tiles = nullptr;  // [n_sms][kMaxStages]
@@ -328,6 +330,7 @@ static void session_free(sopro_ar_session* s) {
   cudaFree(s->st);
   cudaFree(s->samp);
   cudaFree(s->barrier);
+  cudaFree(s->tok_ll);
   cudaFree(s->tiles);
   cudaFree(s->n_tiles);
   cudaFree(s->stage_tiles);
@@ -358,12 +361,14 @@ int sopro_ar_session_create(sopro_engine_t* e, int max_batch, int max_steps, int
     if (err == cudaSuccess) err = cudaMalloc(p, std::max<size_t>(bytes, 256));
   };
   A((void**)&s->ring, (size_t)e->ring_floats_per_utt * B * 4);
-  A((void**)&s->xa, B * D * 4);
-  A((void**)&s->xb, B * D * 4);
-  A((void**)&s->hbuf, B * F * 4);
-  A((void**)&s->qbuf, B * D * 4);
-  A((void**)&s->abuf, B * D * 4);
-  A((void**)&s->logits, B * e->Vpad * 4);
+  // exchange buffers are sized for the LL layout (value + flag per element)
+  A((void**)&s->xa, B * D * 8);
+  A((void**)&s->xb, B * D * 8);
+  A((void**)&s->hbuf, B * F * 8);
+  A((void**)&s->qbuf, B * D * 8);
+  A((void**)&s->abuf, B * D * 8);
+  A((void**)&s->logits, B * e->Vpad * 8);
+  A((void**)&s->tok_ll, B * 8);
   A((void**)&s->kc, kv * 4);
   A((void**)&s->vc, kv * 4);
   A((void**)&s->tokens, B * max_steps * 4);
@@ -488,6 +493,17 @@ int sopro_ar_begin(sopro_ar_session_t* s, int batch, int steps, const float* con
   CK(cudaMemsetAsync(s->ring, 0, (size_t)e->ring_floats_per_utt * batch * 4, st));
   CK(cudaMemsetAsync(s->tokens, 0, (size_t)batch * steps * 4, st));
   CK(cudaMemsetAsync(s->sampled, 0, (size_t)batch * steps * 4, st));
+  {
+    const size_t Bz = (size_t)batch, Dz = (size_t)e->D;
+    CK(cudaMemsetAsync(s->xa, 0, Bz * Dz * 8, st));
+    CK(cudaMemsetAsync(s->xb, 0, Bz * Dz * 8, st));
+    CK(cudaMemsetAsync(s->hbuf, 0, Bz * e->F * 8, st));
+    CK(cudaMemsetAsync(s->qbuf, 0, Bz * Dz * 8, st));
+    CK(cudaMemsetAsync(s->abuf, 0, Bz * Dz * 8, st));
+    CK(cudaMemsetAsync(s->logits, 0, Bz * e->Vpad * 8, st));
+    CK(cudaMemsetAsync(s->tok_ll, 0, Bz * 8, st));
+    s->seq_base = 0;
+  }
   CK(cudaMemsetAsync(s->n_tokens, 0, (size_t)batch * 4, st));
   CK(cudaMemsetAsync(s->done, 0, (size_t)batch * 4, st));
   const size_t kv = (size_t)std::max(e->n_attn, 1) * batch * s->Lmax * e->D;
@@ -578,15 +594,17 @@ static int build_tiles(sopro_ar_session* s, int P, int wbuf, cudaStream_t st) {
   return SOPRO_OK;
 }
 
-template <typename WT, int TU>
+template <typename WT, int TU, bool LL>
 static int launch_ar_tu(sopro_ar_session* s, ArParams& p, size_t smem, int grid, cudaStream_t st) {
-  CK(cudaFuncSetAttribute(ar_persistent_kernel<WT, TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kern = ar_persistent_kernel<WT, TU, LL>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ar_persistent_kernel<WT, TU>, kThreads, smem));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kThreads, smem));
   if (occ < 1) return fail(SOPRO_ERR_CUDA, "persistent kernel does not fit an SM (smem %zu)", smem);
   CK(cudaMemsetAsync(s->barrier, 0, (size_t)s->e->n_sms * 32 * 4, st));
   void* args[] = {(void*)&p};
-  CK(cudaLaunchCooperativeKernel((const void*)ar_persistent_kernel<WT, TU>, dim3(grid), dim3(kThreads), args, smem, st));
+  CK(cudaLaunchCooperativeKernel((const void*)kern, dim3(grid), dim3(kThreads), args, smem, st));
+  s->seq_base += (unsigned)((p.t_end - p.t_begin) * p.n_stage);
   return SOPRO_OK;
 }
 
@@ -641,6 +659,8 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.trace_blocks = s->trace_blocks;
   p.trace_logits = s->trace_logits;
   p.barrier = s->barrier;
+  p.tok_ll = s->tok_ll;
+  p.seq_base = s->seq_base;
   p.timing = s->timing;
   p.timing_step = s->timing_step;
   // ---- team geometry: g teams x P CTAs, Bt utterances per team
@@ -720,10 +740,23 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
     p.n_stage = n;
   }
   const int grid = g * P;
-  if (Bt >= 8) return launch_ar_tu<WT, 8>(s, p, smem, grid, st);
-  if (Bt >= 4) return launch_ar_tu<WT, 4>(s, p, smem, grid, st);
-  if (Bt >= 2) return launch_ar_tu<WT, 2>(s, p, smem, grid, st);
-  return launch_ar_tu<WT, 1>(s, p, smem, grid, st);
+  // activation exchange: LL protocol (flag-in-data, no barrier) for small teams, where the step is latency
+  // bound; team barrier for large teams, where LL's doubled activation traffic costs more than the barrier
+  // (measured: B=64 429k vs 446k cycles/step).  SOPRO_AR_SYNC=ll|barrier overrides.
+  const char* sync_env = getenv("SOPRO_AR_SYNC");
+  bool ll = Bt <= 4;
+  if (sync_env && strcmp(sync_env, "barrier") == 0) ll = false;
+  if (sync_env && strcmp(sync_env, "ll") == 0) ll = true;
+  if (ll) {
+    if (Bt >= 8) return launch_ar_tu<WT, 8, true>(s, p, smem, grid, st);
+    if (Bt >= 4) return launch_ar_tu<WT, 4, true>(s, p, smem, grid, st);
+    if (Bt >= 2) return launch_ar_tu<WT, 2, true>(s, p, smem, grid, st);
+    return launch_ar_tu<WT, 1, true>(s, p, smem, grid, st);
+  }
+  if (Bt >= 8) return launch_ar_tu<WT, 8, false>(s, p, smem, grid, st);
+  if (Bt >= 4) return launch_ar_tu<WT, 4, false>(s, p, smem, grid, st);
+  if (Bt >= 2) return launch_ar_tu<WT, 2, false>(s, p, smem, grid, st);
+  return launch_ar_tu<WT, 1, false>(s, p, smem, grid, st);
 }
 
 extern "C" {

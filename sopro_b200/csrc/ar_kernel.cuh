@@ -131,6 +131,8 @@ struct ArParams {
   const SamplingDev* samp;
   float* trace_blocks;
   float* trace_logits;
+  unsigned* tok_ll;       // [B][2] LL mode: {token | done << 30, flag}
+  unsigned seq_base;      // LL mode: flags of this launch are seq_base + 1 ...
   unsigned* barrier;      // [g][32]
   const TileDesc* tiles;  // [P][kMaxTilesPerStep]
   const int* n_tiles;     // [P] tiles per step of each rank
@@ -176,6 +178,41 @@ __device__ __forceinline__ float4 ldw4(const __nv_bfloat16* p) {
 // activations written by other CTAs: L2 only (never a stale L1 line)
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ float ldcg1(const float* p) { return __ldcg(p); }
+
+// ---------------------------------------------------------------------------
+// LL ("low latency") exchange for small batches: every activation element is an 8-byte pair
+// {value bits, flag}; the producer writes both with ONE 8-byte store, the consumer polls the data
+// itself until the flag equals the producing stage's sequence number.  No fence, no atomic, no
+// separate barrier: one L2 round trip per stage.  (Same idea as NCCL's LL protocol.)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void ll_store(float* p, float v, unsigned flag) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(flag) : "memory");
+}
+__device__ __forceinline__ uint4 ll_load2(const float* p) {  // two consecutive elements, 16-byte aligned
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint2 ll_load1(const float* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+// all threads: poll n_el (even) LL elements starting at src into dst (plain floats, shared memory)
+__device__ __forceinline__ void ll_fetch(const float* __restrict__ src, int n_el, int n_valid, unsigned seq,
+                                         float* __restrict__ dst) {
+  for (int e = threadIdx.x * 2; e < n_el; e += kThreads * 2) {
+    const bool first = e < n_valid, second = e + 1 < n_valid;  // padding elements are never written: do not wait
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (first) {
+      do {
+        v = ll_load2(src + (size_t)e * 2);
+      } while (v.y != seq || (second && v.w != seq));
+    }
+    dst[e] = __uint_as_float(v.x);
+    dst[e + 1] = second ? __uint_as_float(v.z) : 0.f;
+  }
+}
 
 struct Stamp {
   long long* buf;  // this CTA's slots, or null
@@ -440,10 +477,12 @@ __device__ __forceinline__ float pick2(const float (&a)[2][TU], int r, int u) {
 // L2 round trip, no registers); the norm weights are requested before the wait so both latencies
 // overlap.  src == nullptr: the rows are already in `dst` (layer 0), normalise in place.
 // ---------------------------------------------------------------------------
+template <bool LL = false>
 __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int nb, int K, float* __restrict__ dst,
-                                           const float* __restrict__ norm_w, float* __restrict__ raw_copy) {
+                                           const float* __restrict__ norm_w, float* __restrict__ raw_copy,
+                                           unsigned seq = 0) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (src) {
+  if (src && !LL) {
     const unsigned dst_s = smem_u32(dst);
     const int total = nb * K;
     for (int e = threadIdx.x * 4; e < total; e += kThreads * 4) cp_async16(dst_s + (unsigned)e * 4u, src + e);
@@ -456,6 +495,7 @@ __device__ __forceinline__ void stage_rows(const float* __restrict__ src, int nb
     const int k = lane * 4 + c * 128;
     nw[c] = (pre && k < K) ? __ldg(reinterpret_cast<const float4*>(norm_w + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  if (src && LL) ll_fetch(src, nb * K, nb * K, seq, dst);  // src points at LL pairs
   cp_async_wait0();
   __syncthreads();
   if (!norm_w && !raw_copy) return;
@@ -519,7 +559,7 @@ struct TeamCtx {
 // smem: sc[Lmax] scores, part[kWarps][Dh] per-warp partial outputs, [kWarps][2][4][Dh] K/V rows.
 // ---------------------------------------------------------------------------
 __device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank, int P, int b0, int nb,
-                                             float* __restrict__ smem) {
+                                             float* __restrict__ smem, int ll, unsigned q_seq, unsigned out_seq) {
   const LayerDev& L = p.layer[li];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, Dh = p.Dh, D = p.D, Lmax = p.Lmax;
@@ -552,7 +592,17 @@ __device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank
           cp_async16(vS + (unsigned)(i * Dh + d4) * 4u, Vp + (size_t)l * Dh + d4);
         }
       }
-      q4 = ldcg4(p.qbuf + (size_t)b * D + (size_t)h * Dh + d4);
+      const size_t qoff = (size_t)b * D + (size_t)h * Dh + d4;
+      if (ll) {
+        uint4 a, c;
+        do {
+          a = ll_load2(p.qbuf + qoff * 2);
+          c = ll_load2(p.qbuf + qoff * 2 + 4);
+        } while (a.y != q_seq || a.w != q_seq || c.y != q_seq || c.w != q_seq);
+        q4 = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(c.x), __uint_as_float(c.z));
+      } else {
+        q4 = ldcg4(p.qbuf + qoff);
+      }
     }
     cp_async_commit();
     cp_async_wait0();
@@ -604,7 +654,9 @@ __device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank
       for (int w = 0; w < kWarps; ++w) acc += part[(size_t)w * Dh + d];
       acc = acc / sum;
       if (!isfinite(acc)) acc = 0.f;
-      p.abuf[(size_t)b * D + (size_t)h * Dh + d] = acc;
+      const size_t aoff = (size_t)b * D + (size_t)h * Dh + d;
+      if (ll) ll_store(p.abuf + aoff * 2, acc, out_seq);
+      else p.abuf[aoff] = acc;
     }
     __syncthreads();
   }
@@ -836,7 +888,7 @@ __device__ __noinline__ int argmax_logits_cold(const float* __restrict__ sx, int
 // sx, sp: smem [Vpad] floats; flags: smem [Vpad] bytes
 __device__ __noinline__ void sample_utterance(const ArParams& p, int b, int t, float* __restrict__ sx,
                                               float* __restrict__ sp, unsigned char* __restrict__ flags,
-                                              SamplerSmem& sm) {
+                                              SamplerSmem& sm, int ll, unsigned lg_seq, unsigned out_seq) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = p.V;
   long long* dbg = (p.timing && t == p.timing_step && tid == 0) ? p.timing + (size_t)blockIdx.x * kTimingSlots + 160 : nullptr;
@@ -846,7 +898,10 @@ __device__ __noinline__ void sample_utterance(const ArParams& p, int b, int t, f
   const UttState st = p.st[b];
   const SamplingDev spar = p.samp[b];
   int* toks = p.tokens + (size_t)b * p.steps;
-  if (st.done) return;  // CTA-uniform
+  if (st.done) {  // CTA-uniform
+    if (ll && tid == 0) ll_store(reinterpret_cast<float*>(p.tok_ll) + (size_t)b * 2, __uint_as_float(1u << 30), out_seq);
+    return;
+  }
   const float top_p = st.recovery ? spar.rec_top_p : spar.top_p;
   const float temp = st.recovery ? spar.rec_temp : spar.temperature;
   const float rep = spar.rep_pen;
@@ -855,11 +910,13 @@ __device__ __noinline__ void sample_utterance(const ArParams& p, int b, int t, f
   // 1. repetition-penalty flags from set(hist[-50:]); logits -> nan_to_num -> /T -> penalty.
   //    The logits row is fetched with one wave of 16-byte cp.async (a single L2 round trip).
   const float* lg = p.logits + (size_t)b * p.Vpad;
-  {
+  if (ll) {
+    ll_fetch(p.logits + (size_t)b * p.Vpad * 2, p.Vpad, V, lg_seq, sx);
+  } else {
     const unsigned sx_s = smem_u32(sx);
     for (int v = tid * 4; v < p.Vpad; v += kThreads * 4) cp_async16(sx_s + (unsigned)v * 4u, lg + v);
-    cp_async_commit();
   }
+  cp_async_commit();
   for (int v = tid; v < p.Vpad; v += kThreads) flags[v] = 0;
   if (tid < kCand) {
     sm.topv[tid] = -1.f;
@@ -1113,6 +1170,7 @@ __device__ __noinline__ void sample_utterance(const ArParams& p, int b, int t, f
       p.st[b] = ns;
       p.n_tokens[b] = len;
       p.done[b] = done;
+      if (ll) ll_store(reinterpret_cast<float*>(p.tok_ll) + (size_t)b * 2, __uint_as_float((unsigned)token | ((unsigned)done << 30)), out_seq);
     }
   }
   SMARK();  // 9: bookkeeping
@@ -1122,11 +1180,15 @@ __device__ __noinline__ void sample_utterance(const ArParams& p, int b, int t, f
 // ---------------------------------------------------------------------------
 // the persistent kernel: an interpreter over p.prog with one shared GEMV body
 // ---------------------------------------------------------------------------
-template <typename WT, int TU>
+template <typename WT, int TU, bool LL>
 __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid_constant__ ArParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ SamplerSmem ssm;
   __shared__ __align__(8) unsigned long long wbars[kMaxWBuf];
+  __shared__ unsigned char stage_tiles[kMaxStages];
+  __shared__ int conv_phase[kMaxLayers], conv_slot[kMaxLayers];
+  __shared__ int s_tok[kMaxUttPerTeam], s_done[kMaxUttPerTeam];
+  constexpr int EL = LL ? 2 : 1;  // floats per activation element in the exchange buffers
   float* act = reinterpret_cast<float*>(smem_raw);  // [nb][max(D,F)] (or 2 x [nb][D] + tap scratch)
   TeamCtx tc;
   tc.team = blockIdx.x / p.P;
@@ -1151,6 +1213,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
     const int nt = p.n_tiles[tc.rank];
     const TileDesc* gt = p.tiles + (size_t)tc.rank * kMaxTilesPerStep;
     for (int i = threadIdx.x; i < nt; i += kThreads) tab[i] = gt[i];
+    for (int i = threadIdx.x; i < p.n_stage; i += kThreads) stage_tiles[i] = p.stage_tiles[(size_t)tc.rank * kMaxStages + i];
     if (threadIdx.x == 0) {
       for (int i = 0; i < p.nbuf; ++i) mbar_init(&wbars[i], 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1164,20 +1227,27 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
     ring.n_tiles = nt;
     ring.start((p.t_end - p.t_begin) * nt);
   }
-  // per-stage tile counts of this rank + per-layer conv phase bookkeeping (shared, refreshed every step)
-  __shared__ unsigned char stage_tiles[kMaxStages];
-  __shared__ int conv_phase[kMaxLayers], conv_slot[kMaxLayers];
-  for (int i = threadIdx.x; i < p.n_stage; i += kThreads)
-    stage_tiles[i] = p.stage_tiles[(size_t)tc.rank * kMaxStages + i];
-  __syncthreads();
 
 #pragma unroll 1
   for (int t = p.t_begin; t < p.t_end; ++t) {
-    // team-uniform early exit: all utterances of the team finished
-    {
-      int live = 0;
-      for (int u = 0; u < tc.nb; ++u) live |= (__ldcg(&p.st[tc.b0 + u].done) == 0);
-      if (!live) break;
+    const unsigned seq0 = p.seq_base + (unsigned)((t - p.t_begin) * p.n_stage);  // stage si writes flag seq0 + si + 1
+    // ---- previous tokens + done flags of the team; team-uniform early exit when every utterance finished
+    if (threadIdx.x < tc.nb) {
+      const int b = tc.b0 + threadIdx.x;
+      int tok = 0, dn = 0;
+      if (LL && t > p.t_begin) {
+        uint2 w;
+        do {
+          w = ll_load1(reinterpret_cast<const float*>(p.tok_ll) + (size_t)b * 2);
+        } while (w.y != seq0);  // written by the SAMPLE stage of step t-1 (its flag is seq0)
+        tok = (int)(w.x & 0x3fffffffu);
+        dn = (int)(w.x >> 30);
+      } else {
+        dn = __ldcg(&p.st[b].done);
+        tok = (t == 0) ? 0 : __ldcg(&p.tokens[(size_t)b * p.steps + t - 1]);
+      }
+      s_tok[threadIdx.x] = tok;
+      s_done[threadIdx.x] = dn;
     }
     if (threadIdx.x < p.n_layers) {  // the only integer divisions of the step: one thread per layer
       const int dl = p.layer[threadIdx.x].dil;
@@ -1185,8 +1255,14 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
       conv_slot[threadIdx.x] = (t / dl) % p.Kc;
     }
     __syncthreads();
+    {
+      int live = 0;
+      for (int u = 0; u < tc.nb; ++u) live |= (s_done[u] == 0);
+      if (!live) break;
+    }
     float* cur = p.xa;
     float* nxt = p.xb;
+    unsigned x_seq = 0;  // flag of the last full write of `cur`
     Stamp ts;
     ts.buf = (p.timing && t == p.timing_step && threadIdx.x == 0) ? p.timing + (size_t)blockIdx.x * kTimingSlots : nullptr;
     ts.n = 0;
@@ -1194,11 +1270,13 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
 #pragma unroll 1
     for (int si = 0; si < p.n_stage; ++si) {
       const int kind = p.prog[si].kind, li = p.prog[si].layer;
+      const unsigned seq = seq0 + (unsigned)si + 1u;  // flag written by this stage
       if (kind <= K_HEAD) {
         const LayerDev& L = p.layer[li];
         // ---- decode the stage: y[N] = W[N][K] . act, epilogue by kind
         int N = D, K = D, ld_dst = D;
         const float* src = cur;
+        unsigned src_seq = x_seq;
         const float* norm_w = nullptr;
         float* dst = cur;
         float* trace = nullptr;
@@ -1214,6 +1292,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
           ld_dst = F;
         } else if (kind == K_FFN2) {  // W2 + b2 -> + x (in place, own slice) (nn/blocks.py:132,161)
           src = p.hbuf;
+          src_seq = seq - 1;
           K = F;
           if (p.trace_blocks && !L.has_attn) trace = p.trace_blocks + (((size_t)t * p.n_layers + li) * p.B) * D;
         } else if (kind == K_Q) {     // q = Wq . RMSNorm_q(x)                (nn/text.py:93-94)
@@ -1221,6 +1300,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
           dst = p.qbuf;
         } else if (kind == K_O) {     // x += tanh(gate) * Wo . a            (nn/text.py:129-131)
           src = p.abuf;
+          src_seq = seq - 1;
           scale = L.gate_tanh;
           if (p.trace_blocks) trace = p.trace_blocks + (((size_t)t * p.n_layers + li) * p.B) * D;
         } else {                      // logits = Wh . RMSNorm(x) + bh       (nn/generator.py:127-128)
@@ -1237,7 +1317,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
             const int b = tc.b0 + u;
             const float* cr = p.cond + ((size_t)b * p.steps + t) * D;
             for (int k = lane * 4; k < D; k += 128) cp_async16(act_s + (unsigned)(u * D + k) * 4u, cr + k);
-            const int row = (t == 0) ? p.V : __ldcg(&p.tokens[(size_t)b * p.steps + t - 1]);
+            const int row = (t == 0) ? p.V : s_tok[u];
             const float* er = p.emb + (size_t)row * D;
             for (int k = lane * 4; k < D; k += 128) cp_async16(act_s + (unsigned)((tc.nb + u) * D + k) * 4u, er + k);
           }
@@ -1255,7 +1335,8 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
           }
           __syncwarp();
         }
-        stage_rows(src ? src + (size_t)tc.b0 * K : nullptr, tc.nb, K, act, norm_w, (kind == K_GLU && src) ? xraw : nullptr);
+        stage_rows<LL>(src ? src + (size_t)tc.b0 * K * EL : nullptr, tc.nb, K, act, norm_w,
+                       (kind == K_GLU && src) ? xraw : nullptr, src_seq);
         __syncthreads();
         ts.mark();  // activations staged
         // ---- this CTA's rows, tile by tile from the weight ring
@@ -1290,7 +1371,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
             const bool mine = writer && (glu ? i == 0 : true) && ri < nr && u >= u0 && u < tc.nb;
             const int r = td->row0 + ri;  // output feature (GLU: channel)
             const int b = tc.b0 + (mine ? u : 0);
-            float* d = dst + (size_t)b * ld_dst + (mine ? r : td->row0);
+            float* d = dst + ((size_t)b * ld_dst + (mine ? r : td->row0)) * EL;
             // operands of the epilogue are requested before the K loop: their latency hides under it
             float res_v = 0.f;
             float* rb = nullptr;
@@ -1301,7 +1382,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
               if (mine)
                 for (int q = 0; q < p.KcP; q += 4) cp_async16(tap_w + (unsigned)q * 4u, rb + q);
             } else if (mine && (kind == K_FFN2 || kind == K_O)) {
-              res_v = ldcg1(d);
+              res_v = ldcg1(d);  // own slice: written by this CTA at an earlier stage (value word)
             }
             cp_async_commit();
             float v = warp_rows_s<TU, WT>(w0, w1, act_s + (unsigned)ub * (unsigned)K * 4u, K, lane);
@@ -1326,27 +1407,24 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
                 }
                 y += h * lds32(er + (unsigned)(Kc - 1) * 4u);
                 y += lds32(er + (unsigned)Kc * 4u);
-                *d = xraw[(size_t)u * D + r] + y;
+                v = xraw[(size_t)u * D + r] + y;
               } else {
                 const float bias_v = (kind == K_Q || kind == K_O) ? 0.f : lds32(epi_s + (unsigned)(td->off2 + ri) * 4u);
                 if (kind == K_FFN1) {
-                  *d = gelu_erf(v + bias_v);
+                  v = gelu_erf(v + bias_v);
                 } else if (kind == K_FFN2) {
                   v = res_v + (v + bias_v);
-                  *d = v;
                   if (trace) trace[(size_t)b * D + r] = v;
-                } else if (kind == K_Q) {
-                  *d = v;
                 } else if (kind == K_O) {
                   v = res_v + scale * v;
-                  *d = v;
                   if (trace) trace[(size_t)b * D + r] = v;
-                } else {
+                } else if (kind == K_HEAD) {
                   v += bias_v;
-                  *d = v;
                   if (trace) trace[(size_t)b * p.V + r] = v;
                 }
               }
+              if (LL) ll_store(d, v, seq);
+              else *d = v;
             }
             __syncwarp();  // the tap scratch is reused by the next task of this warp
           }
@@ -1358,10 +1436,11 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
           cur = nxt;
           nxt = tmp;
         }
+        if (kind == K_GLU || kind == K_FFN2 || kind == K_O) x_seq = seq;
       } else if (kind == K_ATT) {
         ts.mark();
         ts.mark();
-        stage_attention(p, li, tc.rank, tc.P, tc.b0, tc.nb, act);
+        stage_attention(p, li, tc.rank, tc.P, tc.b0, tc.nb, act, LL ? 1 : 0, seq - 1, seq);
       } else {  // K_SAMPLE: utterances round-robin over the team's CTAs
         ts.mark();
         ts.mark();
@@ -1369,11 +1448,18 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
         float* sp = act + p.Vpad;
         unsigned char* flags = reinterpret_cast<unsigned char*>(act + 2 * p.Vpad);
         for (int u = tc.rank; u < tc.nb; u += tc.P) {
-          sample_utterance(p, tc.b0 + u, t, sx, sp, flags, ssm);
+          sample_utterance(p, tc.b0 + u, t, sx, sp, flags, ssm, LL ? 1 : 0, seq - 1, seq);
           __syncthreads();
         }
       }
-      team_barrier(bar, tc.P, epoch, ts);
+      if (LL) {
+        __syncthreads();  // shared-memory reuse between stages (no team barrier in LL mode)
+        ts.mark();
+        ts.mark();
+        ts.mark();
+      } else {
+        team_barrier(bar, tc.P, epoch, ts);
+      }
     }
   }
   ring.drain();  // early team exit: prefetched tiles must land before the CTA exits
