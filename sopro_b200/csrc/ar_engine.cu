@@ -668,7 +668,7 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   if (Bt <= 0) {
     if (const char* env = getenv("SOPRO_AR_UTTS_PER_TEAM")) Bt = atoi(env);
   }
-  if (Bt <= 0) Bt = s->B <= 8 ? s->B : 16;
+  if (Bt <= 0) Bt = std::min(s->B, 8);  // measured at B=64: 8 utterances/team + LL = 362k cycles/step, 16 + barrier = 429k
   // activations ([Bt][F] fp32) may use at most ~120 KB of shared memory; the rest is the weight ring
   const int bt_cap = std::min(kMaxUttPerTeam, std::max(1, (int)((120 * 1024) / ((size_t)e->F * 4))));
   Bt = std::min(Bt, bt_cap);
@@ -744,7 +744,7 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   // bound; team barrier for large teams, where LL's doubled activation traffic costs more than the barrier
   // (measured: B=64 429k vs 446k cycles/step).  SOPRO_AR_SYNC=ll|barrier overrides.
   const char* sync_env = getenv("SOPRO_AR_SYNC");
-  bool ll = Bt <= 4;
+  bool ll = Bt <= 8;
   if (sync_env && strcmp(sync_env, "barrier") == 0) ll = false;
   if (sync_env && strcmp(sync_env, "ll") == 0) ll = true;
   if (ll) {

@@ -198,19 +198,42 @@ __device__ __forceinline__ uint2 ll_load1(const float* p) {
   asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
-// all threads: poll n_el (even) LL elements starting at src into dst (plain floats, shared memory)
+// all threads: poll n_el (even) LL elements starting at src into dst (plain floats, shared memory).
+// Four lines per thread are requested together (memory-level parallelism), then re-requested until valid.
 __device__ __forceinline__ void ll_fetch(const float* __restrict__ src, int n_el, int n_valid, unsigned seq,
                                          float* __restrict__ dst) {
-  for (int e = threadIdx.x * 2; e < n_el; e += kThreads * 2) {
-    const bool first = e < n_valid, second = e + 1 < n_valid;  // padding elements are never written: do not wait
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (first) {
-      do {
-        v = ll_load2(src + (size_t)e * 2);
-      } while (v.y != seq || (second && v.w != seq));
+  constexpr int NB = 4;
+  for (int base = threadIdx.x * 2; base < n_el; base += kThreads * 2 * NB) {
+    uint4 v[NB];
+    unsigned pending = 0;
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int e = base + j * kThreads * 2;
+      v[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (e < n_valid) {  // padding elements are never written: do not wait for them
+        v[j] = ll_load2(src + (size_t)e * 2);
+        pending |= 1u << j;
+      }
     }
-    dst[e] = __uint_as_float(v.x);
-    dst[e + 1] = second ? __uint_as_float(v.z) : 0.f;
+    while (pending) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        if (pending & (1u << j)) {
+          const int e = base + j * kThreads * 2;
+          const bool second = e + 1 < n_valid;
+          if (v[j].y == seq && (!second || v[j].w == seq)) pending &= ~(1u << j);
+          else v[j] = ll_load2(src + (size_t)e * 2);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int e = base + j * kThreads * 2;
+      if (e < n_el) {
+        dst[e] = __uint_as_float(v[j].x);
+        dst[e + 1] = (e + 1 < n_valid) ? __uint_as_float(v[j].z) : 0.f;
+      }
+    }
   }
 }
 
@@ -407,30 +430,35 @@ __device__ __forceinline__ float reduce_transposed<1>(float (&v)[1], int lane) {
   return warp_sum(v[0]);
 }
 
-template <int TU, typename WT>
-__device__ __forceinline__ float warp_rows_s(unsigned w0, unsigned w1, unsigned act, int K, int lane) {
-  float2 acc[2][TU];
+template <int R, int TU, typename WT>
+__device__ __forceinline__ float warp_rows_s(const unsigned (&w)[R], unsigned act, int K, int lane) {
+  float2 acc[R][TU];
 #pragma unroll
-  for (int u = 0; u < TU; ++u) acc[0][u] = acc[1][u] = make_float2(0.f, 0.f);
-#pragma unroll 3
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int u = 0; u < TU; ++u) acc[r][u] = make_float2(0.f, 0.f);
+  // big register tiles (64 float2 accumulators) leave no room for unrolled loads
+#pragma unroll(R * TU >= 32 ? 1 : 3)
   for (int k = lane * 4; k < K; k += 128) {
-    const float4 wa = ldsw4<WT>(w0 + (unsigned)k * (unsigned)sizeof(WT));
-    const float4 wb = ldsw4<WT>(w1 + (unsigned)k * (unsigned)sizeof(WT));
+    float4 wv[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) wv[r] = ldsw4<WT>(w[r] + (unsigned)k * (unsigned)sizeof(WT));
 #pragma unroll
     for (int u = 0; u < TU; ++u) {
       const float4 x = lds128(act + ((unsigned)u * (unsigned)K + (unsigned)k) * 4u);
-      acc[0][u] = __ffma2_rn(make_float2(wa.x, wa.y), make_float2(x.x, x.y), acc[0][u]);
-      acc[0][u] = __ffma2_rn(make_float2(wa.z, wa.w), make_float2(x.z, x.w), acc[0][u]);
-      acc[1][u] = __ffma2_rn(make_float2(wb.x, wb.y), make_float2(x.x, x.y), acc[1][u]);
-      acc[1][u] = __ffma2_rn(make_float2(wb.z, wb.w), make_float2(x.z, x.w), acc[1][u]);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        acc[r][u] = __ffma2_rn(make_float2(wv[r].x, wv[r].y), make_float2(x.x, x.y), acc[r][u]);
+        acc[r][u] = __ffma2_rn(make_float2(wv[r].z, wv[r].w), make_float2(x.z, x.w), acc[r][u]);
+      }
     }
   }
-  float v[2 * TU];
+  float v[R * TU];
 #pragma unroll
-  for (int r = 0; r < 2; ++r)
+  for (int r = 0; r < R; ++r)
 #pragma unroll
     for (int u = 0; u < TU; ++u) v[r * TU + u] = acc[r][u].x + acc[r][u].y;
-  return reduce_transposed<2 * TU>(v, lane);
+  return reduce_transposed<R * TU>(v, lane);
 }
 
 // same, weights from global memory (K/V builder only)
@@ -1350,25 +1378,36 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
           const TileDesc* td;
           const unsigned wb = ring.acquire(td);
           const int nr = td->nrows;
-          const int n_rt = glu ? nr : (nr + 1) / 2;
+          // a task = R weight rows x TU utterances; GLU: R/2 channels (value rows, then their gate rows)
+          constexpr int R = (TU == 8) ? 4 : 2;
+          constexpr int RC = R / 2;
+          const int n_rt = glu ? (nr + RC - 1) / RC : (nr + R - 1) / R;
           const unsigned epi_s = wb + td->bytes0 + td->bytes1;
 #pragma unroll 1
           for (int task = warp; task < n_rt * n_ut; task += kWarps) {
             const int rt = n_ut == 1 ? task : (int)((unsigned)task / (unsigned)n_ut);
             const int u0 = (task - rt * n_ut) * TU;
-            const unsigned w0 = wb + (unsigned)(glu ? rt : min(2 * rt, nr - 1)) * row_bytes;
-            const unsigned w1 = glu ? wb + td->bytes0 + (unsigned)rt * row_bytes
-                                    : wb + (unsigned)min(2 * rt + 1, nr - 1) * row_bytes;
+            unsigned wr[R];
+#pragma unroll
+            for (int jr = 0; jr < R; ++jr) {
+              if (glu) {
+                const int ch = min(rt * RC + (jr % RC), nr - 1);
+                wr[jr] = wb + (jr < RC ? 0u : td->bytes0) + (unsigned)ch * row_bytes;
+              } else {
+                wr[jr] = wb + (unsigned)min(rt * R + jr, nr - 1) * row_bytes;
+              }
+            }
             const int ub = min(u0, max(tc.nb - TU, 0));
-            // after the transposed reduction lane L owns output o = (L >> SH) & (2*TU-1) = i*TU + uu
-            constexpr int LOG2N = (TU == 1 ? 1 : TU == 2 ? 2 : TU == 4 ? 3 : 4);
+            // after the transposed reduction lane L owns output o = (L >> SH) & (R*TU-1) = i*TU + uu
+            constexpr int NOUT = R * TU;
+            constexpr int LOG2N = (NOUT == 2 ? 1 : NOUT == 4 ? 2 : NOUT == 8 ? 3 : NOUT == 16 ? 4 : 5);
             constexpr int SH = 5 - LOG2N;
-            const int o = (lane >> SH) & (2 * TU - 1);
+            const int o = (lane >> SH) & (NOUT - 1);
             const int i = o / TU, uu = o % TU;
             const bool writer = (lane & ((1 << SH) - 1)) == 0;
-            const int ri = glu ? rt : 2 * rt + i;
+            const int ri = glu ? rt * RC + i : rt * R + i;
             const int u = ub + uu;
-            const bool mine = writer && (glu ? i == 0 : true) && ri < nr && u >= u0 && u < tc.nb;
+            const bool mine = writer && (glu ? i < RC : true) && ri < nr && u >= u0 && u < tc.nb;
             const int r = td->row0 + ri;  // output feature (GLU: channel)
             const int b = tc.b0 + (mine ? u : 0);
             float* d = dst + ((size_t)b * ld_dst + (mine ? r : td->row0)) * EL;
@@ -1385,9 +1424,9 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
               res_v = ldcg1(d);  // own slice: written by this CTA at an earlier stage (value word)
             }
             cp_async_commit();
-            float v = warp_rows_s<TU, WT>(w0, w1, act_s + (unsigned)ub * (unsigned)K * 4u, K, lane);
-            // GLU: the gate total of utterance uu lives in the lanes of output TU + uu
-            const float gate_v = __shfl_sync(0xffffffffu, v, ((TU + uu) << SH) & 31);
+            float v = warp_rows_s<R, TU, WT>(wr, act_s + (unsigned)ub * (unsigned)K * 4u, K, lane);
+            // GLU: the gate total of (channel i, utterance uu) lives in the lanes of output (RC + i)*TU + uu
+            const float gate_v = __shfl_sync(0xffffffffu, v, (((RC + (i % RC)) * TU + uu) << SH) & 31);
             cp_async_wait0();
             if (mine) {
               if (glu) {

@@ -56,5 +56,8 @@ def run(B, wdtype, team=0, steps=64, L=52, step=40):
 
 
 if __name__ == "__main__":
-    for B, wd, team in [(1, "fp32", 0), (64, "bf16", 0)]:
+    cfgs = [(1, "fp32", 0), (64, "bf16", 0)]
+    if len(sys.argv) > 1:  # e.g. 64:bf16:8 1:fp32:0
+        cfgs = [(int(a.split(":")[0]), a.split(":")[1], int(a.split(":")[2])) for a in sys.argv[1:]]
+    for B, wd, team in cfgs:
         run(B, wd, team)
