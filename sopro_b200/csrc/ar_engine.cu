@@ -687,7 +687,10 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.t_begin = t_begin;
   p.t_end = t_end;
   const size_t need_act = std::max((size_t)Bt * e->F * 4, (size_t)2 * Bt * e->D * 4 + (size_t)kWarps * 8 * e->KcP * 4);
-  const size_t need_att = ((size_t)s->Lmax + (size_t)kWarps * e->Dh + (size_t)kWarps * 8 * e->Dh) * 4;
+  const int att_lc = std::min(128, s->Lmax);
+  const size_t need_att_long = ((size_t)s->Lmax + (size_t)kWarps * e->Dh + (size_t)kWarps * 8 * e->Dh) * 4;
+  const size_t need_att_fast = ((size_t)e->Dh + att_lc + (size_t)16 * e->Dh + (size_t)2 * att_lc * e->Dh) * 4;
+  const size_t need_att = std::max(need_att_fast, s->Lmax > att_lc ? need_att_long : (size_t)0);
   const size_t need_smp = (size_t)e->Vpad * 8 + e->Vpad + 16;
   const size_t act_bytes = align_up(std::max(need_act, std::max(need_att, need_smp)), 128);
   const size_t kSmemCap = 214 * 1024;  // 227 KB minus static shared memory (sampler scratch, mbarriers)
@@ -721,6 +724,7 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.nbuf = nbuf;
   p.wbuf_bytes = (int)wbuf;
   p.act_bytes = (int)act_bytes;
+  p.att_lc = att_lc;
   const size_t smem = act_bytes + (size_t)nbuf * wbuf + table_bytes;
   // ---- stage program of one step
   {

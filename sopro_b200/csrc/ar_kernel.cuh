@@ -138,6 +138,7 @@ struct ArParams {
   const int* n_tiles;     // [P] tiles per step of each rank
   const unsigned char* stage_tiles;  // [P][kMaxStages] tiles of each stage
   int nbuf, wbuf_bytes, act_bytes;
+  int att_lc;  // keys whose K/V fit the attention stage's shared memory (longer texts take the cold path)
   long long* timing;  // debug: [grid][kTimingSlots] clock64 stamps of step `timing_step` (null = off)
   int timing_step;
   int g, P, Bt;
@@ -580,14 +581,12 @@ struct TeamCtx {
 };
 
 // ---------------------------------------------------------------------------
-// Cached text cross-attention core (nn/text.py:101-128): softmax(q.K^T / sqrt(Dh)) . V in fp32
-// over the keys l < text_len.  One CTA per (utterance, head) item; the 16 warps split the keys,
-// lanes split the head dimension (float4 each), so every K/V row is one coalesced load and all
-// loads of an item are independent (one L2 round trip).
+// COLD path of the cross-attention: texts longer than the shared-memory K/V capacity (p.att_lc keys).
+// One item; the 16 warps split the keys, lanes split the head dimension, K/V rows stream from L2.
 // smem: sc[Lmax] scores, part[kWarps][Dh] per-warp partial outputs, [kWarps][2][4][Dh] K/V rows.
 // ---------------------------------------------------------------------------
-__device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank, int P, int b0, int nb,
-                                             float* __restrict__ smem, int ll, unsigned q_seq, unsigned out_seq) {
+__device__ __noinline__ void attention_item_long(const ArParams& p, int li, int item, int b0,
+                                                 float* __restrict__ smem, int ll, unsigned q_seq, unsigned out_seq) {
   const LayerDev& L = p.layer[li];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H = p.H, Dh = p.Dh, D = p.D, Lmax = p.Lmax;
@@ -595,11 +594,10 @@ __device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank
   float* part = smem + Lmax;
   const unsigned kv_s = smem_u32(part + (size_t)kWarps * Dh);
   const float scale = 1.0f / sqrtf((float)Dh);
-  const int n_items = nb * H;
   const int d4 = lane * 4;
   const bool act_lane = d4 < Dh;
   constexpr int PF = 4;
-  for (int item = rank; item < n_items; item += P) {
+  {
     const int u = item / H, h = item % H;
     const int b = b0 + u;
     const int len = p.text_len[b];
@@ -683,6 +681,116 @@ __device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank
       acc = acc / sum;
       if (!isfinite(acc)) acc = 0.f;
       const size_t aoff = (size_t)b * D + (size_t)h * Dh + d;
+      if (ll) ll_store(p.abuf + aoff * 2, acc, out_seq);
+      else p.abuf[aoff] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Cached text cross-attention core (nn/text.py:101-128): softmax(q.K^T / sqrt(Dh)) . V in fp32
+// over the keys l < text_len.  One CTA per (utterance, head) item:
+//   1. the item's K and V rows ([len][Dh] each) are copied to shared memory by all threads with one
+//      wave of cp.async (a single L2 round trip); q is read (LL: polled) by the first Dh/4 threads;
+//   2. scores: 8 lanes per key (64 keys per pass), 3-step shuffle reduction;
+//   3. max / sum: every warp, redundantly, from shared memory;
+//   4. output: thread (d, g) accumulates the keys l = g mod G, G = 512 / Dh groups;
+//   5. fixed-order sum over the groups, normalise, nan_to_num (nn/text.py:128), store.
+// smem (floats): qs[Dh] | sc[LC] | part[16][Dh] | Ks[LC][Dh] | Vs[LC][Dh],  LC = p.att_lc
+// ---------------------------------------------------------------------------
+__device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank, int P, int b0, int nb,
+                                             float* __restrict__ smem, int ll, unsigned q_seq, unsigned out_seq) {
+  const LayerDev& L = p.layer[li];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int H = p.H, Dh = p.Dh, D = p.D, LC = p.att_lc;
+  float* qs = smem;
+  float* sc = qs + Dh;
+  float* part = sc + LC;
+  float* Ks = part + 16 * Dh;
+  float* Vs = Ks + (size_t)LC * Dh;
+  const unsigned Ks_s = smem_u32(Ks), Vs_s = smem_u32(Vs);
+  const float scale = 1.0f / sqrtf((float)Dh);
+  const int G = min(kThreads / Dh, 16);
+  const int n_items = nb * H;
+  for (int item = rank; item < n_items; item += P) {
+    const int u = item / H, h = item % H;
+    const int b = b0 + u;
+    const int len = p.text_len[b];
+    if (len > LC) {
+      attention_item_long(p, li, item, b0, smem, ll, q_seq, out_seq);
+      continue;
+    }
+    const size_t kv_off = ((((size_t)L.attn_slot * p.B + b) * H + h) * p.Lmax) * Dh;
+    const float* Kp = p.kc + kv_off;
+    const float* Vp = p.vc + kv_off;
+    const int n4 = len * Dh / 4;
+    for (int e = tid; e < n4; e += kThreads) {
+      cp_async16(Ks_s + (unsigned)e * 16u, Kp + (size_t)e * 4);
+      cp_async16(Vs_s + (unsigned)e * 16u, Vp + (size_t)e * 4);
+    }
+    cp_async_commit();
+    if (tid * 4 < Dh) {
+      const size_t qoff = (size_t)b * D + (size_t)h * Dh + tid * 4;
+      float4 q4;
+      if (ll) {
+        uint4 a, c;
+        do {
+          a = ll_load2(p.qbuf + qoff * 2);
+          c = ll_load2(p.qbuf + qoff * 2 + 4);
+        } while (a.y != q_seq || a.w != q_seq || c.y != q_seq || c.w != q_seq);
+        q4 = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(c.x), __uint_as_float(c.z));
+      } else {
+        q4 = ldcg4(p.qbuf + qoff);
+      }
+      *reinterpret_cast<float4*>(qs + tid * 4) = q4;
+    }
+    cp_async_wait0();
+    __syncthreads();
+    // 2. scores
+    {
+      const int sub = tid & 7;
+      for (int l0 = 0; l0 < len; l0 += kThreads / 8) {
+        const int l = l0 + (tid >> 3);
+        float sdot = 0.f;
+        if (l < len) {
+          for (int d = sub * 4; d < Dh; d += 32) {
+            const float4 kk = *reinterpret_cast<const float4*>(Ks + (size_t)l * Dh + d);
+            const float4 qq = *reinterpret_cast<const float4*>(qs + d);
+            sdot += kk.x * qq.x + kk.y * qq.y + kk.z * qq.z + kk.w * qq.w;
+          }
+        }
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+        if (sub == 0 && l < len) sc[l] = sdot * scale;
+      }
+    }
+    __syncthreads();
+    // 3. softmax statistics
+    float mx = -INFINITY;
+    for (int l = lane; l < len; l += 32) mx = fmaxf(mx, sc[l]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int l = lane; l < len; l += 32) sum += expf(sc[l] - mx);
+    sum = warp_sum(sum);
+    // 4. partial outputs
+    {
+      const int g = tid / Dh, d = tid - g * Dh;
+      if (g < G) {
+        float o = 0.f;
+        for (int l = g; l < len; l += G) o += expf(sc[l] - mx) * Vs[(size_t)l * Dh + d];
+        part[g * Dh + d] = o;
+      }
+    }
+    __syncthreads();
+    // 5. combine
+    if (tid < Dh) {
+      float acc = 0.f;
+      for (int g = 0; g < G; ++g) acc += part[g * Dh + tid];
+      acc = acc / sum;
+      if (!isfinite(acc)) acc = 0.f;
+      const size_t aoff = (size_t)b * D + (size_t)h * Dh + tid;
       if (ll) ll_store(p.abuf + aoff * 2, acc, out_seq);
       else p.abuf[aoff] = acc;
     }
@@ -1486,7 +1594,9 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
         float* sx = act;
         float* sp = act + p.Vpad;
         unsigned char* flags = reinterpret_cast<unsigned char*>(act + 2 * p.Vpad);
-        for (int u = tc.rank; u < tc.nb; u += tc.P) {
+        // samplers run on the team's LAST ranks, attention items on the first ones: at small batch no CTA
+        // has to keep both code paths in its instruction cache
+        for (int u = tc.P - 1 - tc.rank; u < tc.nb; u += tc.P) {
           sample_utterance(p, tc.b0 + u, t, sx, sp, flags, ssm, LL ? 1 : 0, seq - 1, seq);
           __syncthreads();
         }

@@ -159,6 +159,25 @@ def test_batch_equals_each_utterance_alone(team):
         assert toks[i, : nn[i]].tolist() == want[i], f"utterance {i} (L={lens[i]})"
 
 
+def test_long_text_takes_the_streaming_attention_path():
+    """Texts longer than the shared-memory K/V capacity (128 keys) use the cold attention path; a ragged batch
+    mixes both paths in one launch."""
+    spec = AR_CASES["peaked_fp32"]
+    cfg, sd, _ = ar_case_inputs(spec)
+    eng = _engine(cfg, sd, "fp32", _wkey(spec))
+    lens = [200, 40, 131]
+    n, steps = len(lens), 12
+    cond, txt, tapes = _batch_inputs(cfg, n, steps, lens)
+    samp = O.ArSampling(min_gen_frames=10 ** 9)
+    want = _oracle_batch(sd, cfg, cond, txt, tapes, lens, samp, steps)
+    ses = eng.session(n, steps, max(lens))
+    ses.begin(cond, txt, lens, tapes[:, :, :50].contiguous(), _sampling(samp, cfg))
+    ses.run()
+    toks, nn, done = ses.read()
+    for i in range(n):
+        assert toks[i, : nn[i]].tolist() == want[i], f"utterance {i} (L={lens[i]})"
+
+
 def test_resume_in_chunks_equals_one_launch():
     """Streaming drives the kernel chunk by chunk (stream(): 6 frames); state lives in HBM."""
     spec, cfg, sd, inp, g, eng, steps, tape = _case("peaked_fp32")

@@ -48,7 +48,7 @@ def run(B, wdtype, team=0, steps=64, L=52, step=40):
         tot += [np.median(x) for x in parts]
         print(f"  {nm:9s} stage-in {np.median(parts[0]):6.0f}/{parts[0].max():6.0f}  tiles {np.median(parts[1]):6.0f}/{parts[1].max():6.0f}  "
               f"tail {np.median(parts[2]):6.0f}/{parts[2].max():6.0f}  post {np.median(parts[3]):5.0f}  wait {np.median(parts[4]):6.0f}/{parts[4].max():6.0f} (min {parts[4].min():5.0f})")
-    sm = t[0, 160:170]
+    sm = t[int(np.argmax(t[:, 161] > 0)), 160:170]  # the CTA that ran a sampler
     print("  sampler phases (CTA 0):", [int(b - a) for a, b in zip(sm[:-1], sm[1:])],
           "= fetch, penalise, max, exp+sum, probs, lower bound, compaction, sort/top-p/draw, bookkeeping")
     span = (t[:, 5 * ns] - t[:, 0])
