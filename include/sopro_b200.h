@@ -245,6 +245,23 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
 /* same with HOST buffers; synchronises the stream */
 int sopro_mimi_decode_host(sopro_mimi_t* m, const int32_t* codes_host, int B, int T, float* wav_host, void* stream);
 
+/* Arithmetic of the dense blocks (transformer linears, SEANet Conv1d / ConvTranspose1d).
+ *   SOPRO_MIMI_BF16_TC (default): bf16 operands on the tcgen05 tensor cores, fp32 accumulation in tensor
+ *     memory, fp32 residual streams / LayerNorm / softmax; within 2e-2 * max|wav| of the fp32 reference.
+ *   SOPRO_MIMI_FP32: every contraction in fp32 on the FMA pipe; within 1e-4 of the reference
+ *     (what transformers computes on CPU, modeling_mimi.py). */
+#define SOPRO_MIMI_FP32 0
+#define SOPRO_MIMI_BF16_TC 1
+int sopro_mimi_set_precision(sopro_mimi_t* m, int precision);
+
+/* test hook: one tensor-core implicit GEMM (no reference counterpart).  X bf16 [B][rows][cin] (device),
+ * W bf16 [N][taps*cin] (device); out[b][m][n] = epi(sum_j sum_ci X[b][m + j*dil - pad][ci] * W[n][j*cin+ci] +
+ * bias[n % bias_mod]); epi: 0 none, 1 GELU(erf), 2 R + scale*acc, 3 R + acc; out_f32 / out_bf16 may be null;
+ * out_elu applies ELU to the bf16 copy only. */
+int sopro_debug_tc_gemm(const void* X, int B, int64_t rows, int cin, int taps, int dil, int pad, const void* W, int N,
+                        const float* bias, int bias_mod, int epi, const float* R, const float* scale, float* out_f32,
+                        void* out_bf16, int out_elu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,9 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
 class MimiEngine:
     """Device-resident Mimi decoder built from a ``MimiModel`` state_dict (decode-path tensors only)."""
 
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device, num_quantizers: int = 32):
+    PRECISIONS = {"fp32": 0, "bf16_tc": 1}
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, num_quantizers: int = 32, precision: str = "bf16_tc"):
         self.lib = _lib.load()
         dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
         if dev.type != "cuda":
@@ -84,6 +86,14 @@ class MimiEngine:
         self._h = h
         self.hop = int(self.lib.sopro_mimi_samples_per_frame(h))
         del keep
+        self.set_precision(precision)
+
+    def set_precision(self, precision: str) -> None:
+        """"bf16_tc": dense blocks on the tcgen05 tensor cores (bf16 operands, fp32 accumulate); "fp32": exact mode."""
+        if precision not in self.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(self.PRECISIONS)}")
+        _lib.check(self.lib.sopro_mimi_set_precision(self._h, self.PRECISIONS[precision]))
+        self.precision = precision
 
     def decode(self, codes_bqt: torch.Tensor) -> torch.Tensor:
         """codes [B, Q, T] (any int dtype, any device) -> wav [B, 1, T*hop] f32 on the engine's device."""
@@ -122,7 +132,7 @@ class MimiCodec:
     """reference codec/mimi.py:18-72.  ``hf_model`` (a transformers MimiModel) is only used by ``encode_file``."""
 
     def __init__(self, num_quantizers: int, device: str = "cuda", model_id: str = "kyutai/mimi", *,
-                 state_dict: Optional[Dict[str, torch.Tensor]] = None, hf_model=None):
+                 state_dict: Optional[Dict[str, torch.Tensor]] = None, hf_model=None, precision: str = "bf16_tc"):
         self.device = torch.device(device)
         self.model = hf_model
         if state_dict is None:
@@ -134,7 +144,7 @@ class MimiCodec:
                 self.model = hf_model
             state_dict = hf_model.state_dict()
         self._num_quantizers = int(num_quantizers)
-        self.engine = MimiEngine(state_dict, self.device, num_quantizers=self._num_quantizers)
+        self.engine = MimiEngine(state_dict, self.device, num_quantizers=self._num_quantizers, precision=precision)
 
     @property
     def codebook_size(self) -> int:

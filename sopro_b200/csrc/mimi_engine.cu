@@ -12,7 +12,11 @@
 // ConvTranspose1d (stride s, kernel 2s == a 2-tap conv producing s*Cout columns, which IS the
 // channel-last upsampled tensor), with ELU fused on the operand load and bias / GELU / LayerScale
 // residual fused in the epilogue.  This first version runs the contractions in fp32 on the FFMA2
-// pipe (parity 1e-4 against the fp32 oracle); the tcgen05/TMEM bf16 path is the next step.
+// pipe (parity 1e-4 against the fp32 oracle).  SOPRO_MIMI_BF16_TC mode (mimi_tc.cuh) runs every
+// contraction whose channel count allows it on the tcgen05 tensor cores with bf16 operands, fp32
+// accumulation in tensor memory and the same fused epilogues; the fp32 kernels stay for the exact mode
+// and for the few narrow layers (Cin < 64).
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -24,6 +28,7 @@
 #include <vector>
 
 #include "../../include/sopro_b200.h"
+#include "mimi_tc.cuh"
 
 namespace mimi {
 
@@ -183,8 +188,12 @@ __global__ void upsample_kernel(const float* __restrict__ x, const float* __rest
 }
 
 // LayerNorm over C (one warp per row)
+__device__ __forceinline__ void put(float* p, float v) { *p = v; }
+__device__ __forceinline__ void put(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <typename OutT>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bb,
-                                 float* __restrict__ y, long long rows, int C, float eps) {
+                                 OutT* __restrict__ y, long long rows, int C, float eps) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -202,7 +211,15 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const float inv = 1.0f / sqrtf(v / (float)C + eps);
-  for (int c = lane; c < C; c += 32) y[row * C + c] = (xr[c] - mean) * inv * __ldg(w + c) + __ldg(bb + c);
+  for (int c = lane; c < C; c += 32) put(y + row * C + c, (xr[c] - mean) * inv * __ldg(w + c) + __ldg(bb + c));
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+  reinterpret_cast<uint2*>(y)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
 
 // RoPE in place on the q and k thirds of QKV [rows][3C]; rope table [T2][Dh/2] cos, then sin
@@ -225,7 +242,8 @@ __global__ void rope_kernel(float* __restrict__ qkv, const float* __restrict__ c
 }
 
 // causal sliding-window attention, one warp per (b, h, query); QKV rotated; out [B][T2][C]
-__global__ void __launch_bounds__(256) attn_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T2, int C,
+template <typename OutT>
+__global__ void __launch_bounds__(256) attn_kernel(const float* __restrict__ qkv, OutT* __restrict__ out, int T2, int C,
                                                    int H, int window) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -268,7 +286,7 @@ __global__ void __launch_bounds__(256) attn_kernel(const float* __restrict__ qkv
   for (int d = lane; d < Dh; d += 32) {
     float o = 0.f;
     for (int jj = 0; jj < nk; ++jj) o += (sc[jj] * inv) * base[(size_t)(j0 + jj) * 3 * C + 2 * C + h * Dh + d];
-    out[((size_t)b * T2 + i) * C + h * Dh + d] = o;
+    put(out + ((size_t)b * T2 + i) * C + h * Dh + d, o);
   }
 }
 
@@ -314,6 +332,25 @@ int mfail(int code, const char* fmt, ...) {
       return mfail(SOPRO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+uint16_t bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN stays NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// bf16 copies of the GEMM weight matrices (tensor-core mode); offsets in elements, 256-B aligned
+struct Bf16Arena {
+  std::vector<uint16_t> host;
+  size_t add(const float* p, size_t n) {
+    const size_t off = (host.size() + 127) / 128 * 128;
+    host.resize(off + n);
+    for (size_t i = 0; i < n; ++i) host[off + i] = bf16_rne(p[i]);
+    return off;
+  }
+};
+
 struct DevArena {
   std::vector<float> host;
   size_t add(const float* p, size_t n) {
@@ -334,20 +371,24 @@ struct sopro_mimi {
   size_t embed = 0, rvq_w = 0, up_w = 0;
   struct Layer {
     size_t ln1w, ln1b, qkv, wo, ls1, ln2w, ln2b, fc1, fc2, ls2;
+    size_t qkv_h, wo_h, fc1_h, fc2_h;  // bf16 arena
   };
   std::vector<Layer> layers;
-  size_t c0w = 0, c0b = 0;
+  size_t c0w = 0, c0b = 0, c0w_h = 0;
   struct Stage {
     size_t tw, tb, r1w, r1b, r2w, r2b;
+    size_t tw_h, r1w_h, r2w_h;  // bf16 arena
     int ratio, cin, cout;
   };
+  __nv_bfloat16* dev_h = nullptr;  // bf16 weight arena
+  int precision = SOPRO_MIMI_BF16_TC;
   std::vector<Stage> stages;
   size_t lw = 0, lb = 0;
   // rope table + workspace
   float* rope = nullptr;
   int rope_T2 = 0;
   float* ws = nullptr;
-  size_t ws_floats = 0;
+  size_t ws_bytes = 0;
   int* codes_dev = nullptr;
   size_t codes_cap = 0;
 };
@@ -373,6 +414,7 @@ int sopro_mimi_create(const sopro_mimi_config_t* cfg, const sopro_mimi_weights_t
   m->device = device;
   m->cfg = *cfg;
   DevArena A;
+  Bf16Arena Hh;
   m->embed = A.add(w->embed, (size_t)Q * V * Dc);
   {  // [C][2*Dc] = [W_sem | W_ac]
     std::vector<float> cat((size_t)C * 2 * Dc);
@@ -394,7 +436,11 @@ int sopro_mimi_create(const sopro_mimi_config_t* cfg, const sopro_mimi_weights_t
     memcpy(qkv.data() + (size_t)C * C, L.k_w, (size_t)C * C * 4);
     memcpy(qkv.data() + (size_t)2 * C * C, L.v_w, (size_t)C * C * 4);
     d.qkv = A.add(qkv.data(), qkv.size());
+    d.qkv_h = Hh.add(qkv.data(), qkv.size());
     d.wo = A.add(L.o_w, (size_t)C * C);
+    d.wo_h = Hh.add(L.o_w, (size_t)C * C);
+    d.fc1_h = Hh.add(L.fc1_w, (size_t)FF * C);
+    d.fc2_h = Hh.add(L.fc2_w, (size_t)C * FF);
     d.ls1 = A.add(L.ls1, C);
     d.ln2w = A.add(L.ln2_w, C);
     d.ln2b = A.add(L.ln2_b, C);
@@ -404,15 +450,16 @@ int sopro_mimi_create(const sopro_mimi_config_t* cfg, const sopro_mimi_weights_t
     m->layers.push_back(d);
   }
   // conv weights [Cout][Cin][k] -> [Cout][(tap, ci)]
-  auto repack_conv = [&](const float* src, int cout, int cin, int k) {
+  auto repack_conv = [&](const float* src, int cout, int cin, int k, size_t* half_off) {
     std::vector<float> r((size_t)cout * k * cin);
     for (int co = 0; co < cout; ++co)
       for (int ci = 0; ci < cin; ++ci)
         for (int j = 0; j < k; ++j) r[((size_t)co * k + j) * cin + ci] = src[((size_t)co * cin + ci) * k + j];
+    if (half_off) *half_off = Hh.add(r.data(), r.size());
     return A.add(r.data(), r.size());
   };
   int ch = cfg->num_filters << cfg->n_ratios;  // 1024
-  m->c0w = repack_conv(w->conv0_w, ch, C, cfg->kernel);
+  m->c0w = repack_conv(w->conv0_w, ch, C, cfg->kernel, &m->c0w_h);
   m->c0b = A.add(w->conv0_b, ch);
   for (int s = 0; s < cfg->n_ratios; ++s) {
     const sopro_mimi_stage_weights_t& S = w->stage[s];
@@ -431,21 +478,31 @@ int sopro_mimi_create(const sopro_mimi_config_t* cfg, const sopro_mimi_weights_t
           tw[(n * 2 + 1) * cin + ci] = S.convt_w[((size_t)ci * cout + co) * 2 * r + ph];
         }
     d.tw = A.add(tw.data(), tw.size());
+    d.tw_h = Hh.add(tw.data(), tw.size());
     d.tb = A.add(S.convt_b, cout);
-    d.r1w = repack_conv(S.res1_w, cout / cfg->compress, cout, cfg->res_kernel);
+    d.r1w = repack_conv(S.res1_w, cout / cfg->compress, cout, cfg->res_kernel, &d.r1w_h);
     d.r1b = A.add(S.res1_b, cout / cfg->compress);
-    d.r2w = repack_conv(S.res2_w, cout, cout / cfg->compress, 1);
+    d.r2w = repack_conv(S.res2_w, cout, cout / cfg->compress, 1, &d.r2w_h);
     d.r2b = A.add(S.res2_b, cout);
     m->stages.push_back(d);
     ch = cout;
   }
-  m->lw = repack_conv(w->last_w, 1, ch, cfg->last_kernel);
+  m->lw = repack_conv(w->last_w, 1, ch, cfg->last_kernel, nullptr);
   m->lb = A.add(w->last_b, 1);
   m->n_floats = A.host.size();
   cudaError_t err = cudaMalloc(&m->dev, m->n_floats * 4);
   if (err == cudaSuccess) err = cudaMemcpy(m->dev, A.host.data(), m->n_floats * 4, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMalloc(&m->dev_h, Hh.host.size() * 2);
+  if (err == cudaSuccess) err = cudaMemcpy(m->dev_h, Hh.host.data(), Hh.host.size() * 2, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess && !tc::encode_tiled_fn()) {
+    cudaFree(m->dev);
+    cudaFree(m->dev_h);
+    delete m;
+    return mfail(SOPRO_ERR_UNSUPPORTED, "driver has no cuTensorMapEncodeTiled entry point");
+  }
   if (err != cudaSuccess) {
     if (m->dev) cudaFree(m->dev);
+    if (m->dev_h) cudaFree(m->dev_h);
     delete m;
     return mfail(SOPRO_ERR_CUDA, "Mimi weight upload failed: %s", cudaGetErrorString(err));
   }
@@ -457,6 +514,7 @@ int sopro_mimi_destroy(sopro_mimi_t* m) {
   if (!m) return SOPRO_OK;
   cudaSetDevice(m->device);
   cudaFree(m->dev);
+  cudaFree(m->dev_h);
   cudaFree(m->rope);
   cudaFree(m->ws);
   cudaFree(m->codes_dev);
@@ -484,14 +542,24 @@ static int launch_gemm(const GemmOp& op, int B, cudaStream_t st) {
   return SOPRO_OK;
 }
 
+int sopro_mimi_set_precision(sopro_mimi_t* m, int precision) {
+  if (!m) return mfail(SOPRO_ERR_INVALID, "null argument");
+  if (precision != SOPRO_MIMI_FP32 && precision != SOPRO_MIMI_BF16_TC) return mfail(SOPRO_ERR_INVALID, "unknown precision %d", precision);
+  m->precision = precision;
+  return SOPRO_OK;
+}
+
 int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float* wav, void* stream) {
   if (!m || !codes || !wav) return mfail(SOPRO_ERR_INVALID, "null argument");
   if (B < 1 || T < 1) return mfail(SOPRO_ERR_INVALID, "B and T must be >= 1");
+  if (B > 65535) return mfail(SOPRO_ERR_INVALID, "B must be <= 65535");
   MCK(cudaSetDevice(m->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const sopro_mimi_config_t& c = m->cfg;
   const int C = c.hidden, T2 = 2 * T, H = c.n_heads, Dh = C / H, FF = c.ffn;
   const float* Wd = m->dev;
+  const __nv_bfloat16* Wh = m->dev_h;
+  const bool use_tc = m->precision == SOPRO_MIMI_BF16_TC;
   // ---- rope table
   if (m->rope_T2 < T2) {
     cudaFree(m->rope);
@@ -509,27 +577,32 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
     MCK(cudaStreamSynchronize(st));
     m->rope_T2 = T2;
   }
-  // ---- workspace: three ping-pong buffers sized for the widest SEANet activation + transformer scratch
+  // ---- workspace: three fp32 ping-pong buffers sized for the widest SEANet activation + transformer
+  //      scratch, the residual stream and its normalised copy; tensor-core mode adds three bf16 buffers
   long long up = 2;
   for (int i = 0; i < c.n_ratios; ++i) up *= c.ratios[i];
   const size_t big = (size_t)B * T * up * c.num_filters;                     // [T*1920][64]
   const size_t tr = (size_t)B * T2 * (size_t)std::max(3 * C, FF);            // QKV / MLP hidden
-  const size_t bufsz = std::max(std::max(big, tr), (size_t)B * T2 * (c.num_filters << c.n_ratios));
-  const size_t need = 3 * bufsz + (size_t)B * T2 * C * 2;
-  if (m->ws_floats < need) {
+  const size_t bufsz = (std::max(std::max(big, tr), (size_t)B * T2 * (c.num_filters << c.n_ratios)) + 63) / 64 * 64;
+  const size_t xsz = ((size_t)B * T2 * C + 63) / 64 * 64;
+  const size_t need = (3 * bufsz + 2 * xsz) * 4 + (use_tc ? 3 * bufsz * 2 : 0);
+  if (m->ws_bytes < need) {
     cudaFree(m->ws);
     m->ws = nullptr;
-    m->ws_floats = 0;
-    cudaError_t e = cudaMalloc(&m->ws, need * 4);
-    if (e != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "Mimi workspace %zu MB: %s", need * 4 >> 20, cudaGetErrorString(e));
-    m->ws_floats = need;
+    m->ws_bytes = 0;
+    cudaError_t e = cudaMalloc(&m->ws, need);
+    if (e != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "Mimi workspace %zu MB: %s", need >> 20, cudaGetErrorString(e));
+    m->ws_bytes = need;
   }
   float* b0 = m->ws;
   float* b1 = b0 + bufsz;
   float* b2 = b1 + bufsz;
-  float* x = b2 + bufsz;               // residual stream [B][T2][C]
-  float* ln = x + (size_t)B * T2 * C;  // normalised copy
-  // ---- RVQ + projection + upsample
+  float* x = b2 + bufsz;    // residual stream [B][T2][C]
+  float* ln = x + xsz;      // normalised copy (fp32 mode)
+  __nv_bfloat16* h0 = reinterpret_cast<__nv_bfloat16*>(ln + xsz);
+  __nv_bfloat16* h1 = h0 + bufsz;
+  __nv_bfloat16* h2 = h1 + bufsz;
+  // ---- RVQ + projection + upsample (small; fp32 in both modes)
   rvq_gather_kernel<<<dim3(T, B), 256, 0, st>>>(codes, Wd + m->embed, b0, c.n_q, T, c.codebook_dim, c.vocab, c.n_sem);
   MCK(cudaGetLastError());
   GemmOp g{};
@@ -540,25 +613,6 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
     g.a_bs = (long long)M * K; g.c_bs = (long long)M * N; g.r_bs = (long long)M * N;
     return launch_gemm(g, B, st);
   };
-  int rc;
-  if ((rc = lin(b0, T, C, Wd + m->rvq_w, C, b1, EPI_NONE, nullptr, nullptr))) return rc;
-  upsample_kernel<<<dim3(T2, B), 256, 0, st>>>(b1, Wd + m->up_w, x, T, C);
-  MCK(cudaGetLastError());
-  // ---- transformer
-  const long long rows = (long long)B * T2;
-  for (const sopro_mimi::Layer& L : m->layers) {
-    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, Wd + L.ln1w, Wd + L.ln1b, ln, rows, C, c.norm_eps);
-    if ((rc = lin(ln, T2, C, Wd + L.qkv, 3 * C, b0, EPI_NONE, nullptr, nullptr))) return rc;
-    rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H);
-    const size_t asm_bytes = (size_t)8 * (Dh + c.window) * 4;
-    attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, b1, T2, C, H, c.window);
-    MCK(cudaGetLastError());
-    if ((rc = lin(b1, T2, C, Wd + L.wo, C, x, EPI_RES_SCALE, x, Wd + L.ls1))) return rc;
-    layernorm_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, Wd + L.ln2w, Wd + L.ln2b, ln, rows, C, c.norm_eps);
-    if ((rc = lin(ln, T2, C, Wd + L.fc1, FF, b0, EPI_GELU, nullptr, nullptr))) return rc;
-    if ((rc = lin(b0, T2, FF, Wd + L.fc2, C, x, EPI_RES_SCALE, x, Wd + L.ls2))) return rc;
-  }
-  // ---- SEANet decoder
   auto conv = [&](const float* A, long long Tin, int cin, int taps, int pad, const float* W, const float* bias, int N, int bias_mod,
                   float* Cc, int elu, int epi, const float* R) {
     g = GemmOp{};
@@ -568,25 +622,155 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
     g.a_bs = Tin * cin; g.c_bs = Tin * N; g.r_bs = Tin * N;
     return launch_gemm(g, B, st);
   };
+  // tensor-core implicit GEMM: X bf16 [B][rows][cin] (ELU already applied by its producer where the layer wants it)
+  auto tcg = [&](const __nv_bfloat16* X, long long rows, int cin, int taps, int pad, const __nv_bfloat16* W, const float* bias,
+                 int N, int bias_mod, int epi, const float* R, const float* scale, float* of, __nv_bfloat16* oh, int out_elu) {
+    tc::TcOp o{};
+    o.bias = bias; o.R = R; o.scale = scale; o.out_f32 = of; o.out_bf16 = oh;
+    o.c_bs = rows * N; o.M = (int)rows; o.N = N; o.K = taps * cin; o.Cin = cin; o.dil = 1; o.pad = pad;
+    o.bias_mod = bias_mod; o.epi = epi; o.out_elu = out_elu;
+    cudaError_t e = tc::launch(X, rows, W, o, B, st);
+    if (e != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "tensor-core GEMM (N=%d K=%d): %s", N, o.K, cudaGetErrorString(e));
+    return (int)SOPRO_OK;
+  };
+  int rc;
+  if ((rc = lin(b0, T, C, Wd + m->rvq_w, C, b1, EPI_NONE, nullptr, nullptr))) return rc;
+  upsample_kernel<<<dim3(T2, B), 256, 0, st>>>(b1, Wd + m->up_w, x, T, C);
+  MCK(cudaGetLastError());
+  // ---- transformer
+  const long long rows = (long long)B * T2;
+  const unsigned ln_grid = (unsigned)((rows + 7) / 8);
+  const size_t asm_bytes = (size_t)8 * (Dh + c.window) * 4;
+  const bool tc_tr = use_tc && tc::supported(3 * C, C, C) && tc::supported(C, C, C) && tc::supported(FF, C, C) && tc::supported(C, FF, FF);
+  for (const sopro_mimi::Layer& L : m->layers) {
+    if (tc_tr) {
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln1w, Wd + L.ln1b, h0, rows, C, c.norm_eps);
+      if ((rc = tcg(h0, T2, C, 1, 0, Wh + L.qkv_h, nullptr, 3 * C, 3 * C, tc::EPI_NONE, nullptr, nullptr, b0, nullptr, 0))) return rc;
+      rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H);
+      attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, h1, T2, C, H, c.window);
+      MCK(cudaGetLastError());
+      if ((rc = tcg(h1, T2, C, 1, 0, Wh + L.wo_h, nullptr, C, C, tc::EPI_RES_SCALE, x, Wd + L.ls1, x, nullptr, 0))) return rc;
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln2w, Wd + L.ln2b, h0, rows, C, c.norm_eps);
+      if ((rc = tcg(h0, T2, C, 1, 0, Wh + L.fc1_h, nullptr, FF, FF, tc::EPI_GELU, nullptr, nullptr, nullptr, h2, 0))) return rc;
+      if ((rc = tcg(h2, T2, FF, 1, 0, Wh + L.fc2_h, nullptr, C, C, tc::EPI_RES_SCALE, x, Wd + L.ls2, x, nullptr, 0))) return rc;
+    } else {
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln1w, Wd + L.ln1b, ln, rows, C, c.norm_eps);
+      if ((rc = lin(ln, T2, C, Wd + L.qkv, 3 * C, b0, EPI_NONE, nullptr, nullptr))) return rc;
+      rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H);
+      attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, b1, T2, C, H, c.window);
+      MCK(cudaGetLastError());
+      if ((rc = lin(b1, T2, C, Wd + L.wo, C, x, EPI_RES_SCALE, x, Wd + L.ls1))) return rc;
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln2w, Wd + L.ln2b, ln, rows, C, c.norm_eps);
+      if ((rc = lin(ln, T2, C, Wd + L.fc1, FF, b0, EPI_GELU, nullptr, nullptr))) return rc;
+      if ((rc = lin(b0, T2, FF, Wd + L.fc2, C, x, EPI_RES_SCALE, x, Wd + L.ls2))) return rc;
+    }
+  }
+  // ---- SEANet decoder
   long long Tn = T2;
   int ch = c.num_filters << c.n_ratios;
-  if ((rc = conv(x, Tn, C, c.kernel, c.kernel - 1, Wd + m->c0w, Wd + m->c0b, ch, ch, b0, 0, EPI_NONE, nullptr))) return rc;
-  float* cur = b0;
-  float* o1 = b1;
-  float* o2 = b2;
-  for (const sopro_mimi::Stage& S : m->stages) {
+  if (!use_tc) {
+    if ((rc = conv(x, Tn, C, c.kernel, c.kernel - 1, Wd + m->c0w, Wd + m->c0b, ch, ch, b0, 0, EPI_NONE, nullptr))) return rc;
+    float* cur = b0;
+    float* o1 = b1;
+    float* o2 = b2;
+    for (const sopro_mimi::Stage& S : m->stages) {
+      if (Tn * S.ratio > 0x7fffffffLL) return mfail(SOPRO_ERR_INVALID, "sequence too long for one launch");
+      // ELU -> ConvTranspose(stride r, kernel 2r) as a 2-tap implicit GEMM with r*Cout columns
+      if ((rc = conv(cur, Tn, S.cin, 2, 1, Wd + S.tw, Wd + S.tb, S.ratio * S.cout, S.cout, o1, 1, EPI_NONE, nullptr))) return rc;
+      Tn *= S.ratio;
+      // ResnetBlock: o1 + conv1(ELU(conv3(ELU(o1))))
+      const int hid = S.cout / c.compress;
+      if ((rc = conv(o1, Tn, S.cout, c.res_kernel, c.res_kernel - 1, Wd + S.r1w, Wd + S.r1b, hid, hid, o2, 1, EPI_NONE, nullptr))) return rc;
+      if ((rc = conv(o2, Tn, hid, 1, 0, Wd + S.r2w, Wd + S.r2b, S.cout, S.cout, cur, 1, EPI_RES, o1))) return rc;
+      ch = S.cout;
+    }
+    final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
+    MCK(cudaGetLastError());
+    return SOPRO_OK;
+  }
+  // tensor-core mode.  Activations that feed a contraction travel as bf16 with the consumer's ELU already
+  // applied; only the ConvTranspose output (the ResnetBlock skip) and whatever a fp32 kernel reads are fp32.
+  //   curh: bf16 operand of the next ConvTranspose;  z (b1): fp32 skip;  b0: fp32 block output when needed
+  __nv_bfloat16* curh = h0;
+  __nv_bfloat16* ha = h1;
+  __nv_bfloat16* hb = h2;
+  float* cur32 = nullptr;  // set when the running activation lives in fp32 (b0) instead of curh
+  if (tc::supported(ch, c.kernel * C, C)) {
+    const long long n4 = (long long)B * T2 * C / 4;
+    cast_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, hb, n4);
+    MCK(cudaGetLastError());
+    if ((rc = tcg(hb, Tn, C, c.kernel, c.kernel - 1, Wh + m->c0w_h, Wd + m->c0b, ch, ch, tc::EPI_NONE, nullptr, nullptr, nullptr, curh, 1)))
+      return rc;
+  } else {
+    if ((rc = conv(x, Tn, C, c.kernel, c.kernel - 1, Wd + m->c0w, Wd + m->c0b, ch, ch, b0, 0, EPI_NONE, nullptr))) return rc;
+    cur32 = b0;
+  }
+  for (size_t si = 0; si < m->stages.size(); ++si) {
+    const sopro_mimi::Stage& S = m->stages[si];
     if (Tn * S.ratio > 0x7fffffffLL) return mfail(SOPRO_ERR_INVALID, "sequence too long for one launch");
-    // ELU -> ConvTranspose(stride r, kernel 2r) as a 2-tap implicit GEMM with r*Cout columns
-    if ((rc = conv(cur, Tn, S.cin, 2, 1, Wd + S.tw, Wd + S.tb, S.ratio * S.cout, S.cout, o1, 1, EPI_NONE, nullptr))) return rc;
+    const int hid = S.cout / c.compress, NT = S.ratio * S.cout;
+    const bool last = si + 1 == m->stages.size();
+    const bool t_ok = !cur32 && tc::supported(NT, 2 * S.cin, S.cin);
+    const bool r1_ok = tc::supported(hid, c.res_kernel * S.cout, S.cout);
+    const bool r2_ok = tc::supported(S.cout, hid, hid);
+    // the consumer of this stage's output: the next ConvTranspose on tensor cores wants bf16 ELU(x); the
+    // final conv and the fp32 kernels read fp32
+    bool next_tc = false;
+    if (!last) {
+      const sopro_mimi::Stage& Nx = m->stages[si + 1];
+      next_tc = tc::supported(Nx.ratio * Nx.cout, 2 * Nx.cin, Nx.cin);
+    }
+    // ConvTranspose -> z fp32 (b1) [+ bf16 ELU(z) in ha when res1 runs on tensor cores]
+    if (t_ok) {
+      if ((rc = tcg(curh, Tn, S.cin, 2, 1, Wh + S.tw_h, Wd + S.tb, NT, S.cout, tc::EPI_NONE, nullptr, nullptr, b1, r1_ok ? ha : nullptr, 1)))
+        return rc;
+    } else {
+      if (!cur32) return mfail(SOPRO_ERR_INVALID, "internal: stage %zu has no fp32 input", si);
+      if ((rc = conv(cur32, Tn, S.cin, 2, 1, Wd + S.tw, Wd + S.tb, NT, S.cout, b1, 1, EPI_NONE, nullptr))) return rc;
+    }
     Tn *= S.ratio;
-    // ResnetBlock: o1 + conv1(ELU(conv3(ELU(o1))))
-    const int hid = S.cout / c.compress;
-    if ((rc = conv(o1, Tn, S.cout, c.res_kernel, c.res_kernel - 1, Wd + S.r1w, Wd + S.r1b, hid, hid, o2, 1, EPI_NONE, nullptr))) return rc;
-    if ((rc = conv(o2, Tn, hid, 1, 0, Wd + S.r2w, Wd + S.r2b, S.cout, S.cout, cur, 1, EPI_RES, o1))) return rc;
+    const bool ha_valid = t_ok && r1_ok;
+    // res conv k=3 -> ELU(h) bf16 (hb) for a tensor-core res2, else raw h fp32 (b2)
+    if (ha_valid) {
+      if ((rc = tcg(ha, Tn, S.cout, c.res_kernel, c.res_kernel - 1, Wh + S.r1w_h, Wd + S.r1b, hid, hid, tc::EPI_NONE, nullptr, nullptr,
+                    r2_ok ? nullptr : b2, r2_ok ? hb : nullptr, 1)))
+        return rc;
+    } else {
+      if ((rc = conv(b1, Tn, S.cout, c.res_kernel, c.res_kernel - 1, Wd + S.r1w, Wd + S.r1b, hid, hid, b2, 1, EPI_NONE, nullptr))) return rc;
+    }
+    // res conv k=1 + skip
+    if (ha_valid && r2_ok) {
+      if ((rc = tcg(hb, Tn, hid, 1, 0, Wh + S.r2w_h, Wd + S.r2b, S.cout, S.cout, tc::EPI_RES, b1, nullptr, next_tc ? nullptr : b0,
+                    next_tc ? curh : nullptr, 1)))
+        return rc;
+      cur32 = next_tc ? nullptr : b0;
+    } else {
+      if ((rc = conv(b2, Tn, hid, 1, 0, Wd + S.r2w, Wd + S.r2b, S.cout, S.cout, b0, 1, EPI_RES, b1))) return rc;
+      cur32 = b0;
+      if (next_tc) {  // fp32 block output feeding a tensor-core ConvTranspose: not reachable with Mimi's geometry
+        return mfail(SOPRO_ERR_UNSUPPORTED, "unsupported channel geometry for tensor-core mode (stage %zu)", si);
+      }
+    }
     ch = S.cout;
   }
-  final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
+  if (!cur32) return mfail(SOPRO_ERR_UNSUPPORTED, "internal: final conv needs an fp32 input");
+  final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur32, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
   MCK(cudaGetLastError());
+  return SOPRO_OK;
+}
+
+int sopro_debug_tc_gemm(const void* X, int B, int64_t rows, int cin, int taps, int dil, int pad, const void* W, int N,
+                        const float* bias, int bias_mod, int epi, const float* R, const float* scale, float* out_f32,
+                        void* out_bf16, int out_elu, void* stream) {
+  if (!X || !W || (!out_f32 && !out_bf16)) return mfail(SOPRO_ERR_INVALID, "null argument");
+  if (B < 1 || B > 65535 || rows < 1 || rows > 0x7fffffffLL || !tc::supported(N, taps * cin, cin))
+    return mfail(SOPRO_ERR_INVALID, "tc gemm: unsupported shape (rows=%lld cin=%d taps=%d N=%d)", (long long)rows, cin, taps, N);
+  tc::TcOp o{};
+  o.bias = bias; o.R = R; o.scale = scale; o.out_f32 = out_f32; o.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  o.c_bs = rows * N; o.M = (int)rows; o.N = N; o.K = taps * cin; o.Cin = cin; o.dil = dil; o.pad = pad;
+  o.bias_mod = bias_mod > 0 ? bias_mod : N; o.epi = epi; o.out_elu = out_elu;
+  cudaError_t e = tc::launch(X, rows, W, o, B, reinterpret_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "tensor-core GEMM launch: %s", cudaGetErrorString(e));
   return SOPRO_OK;
 }
 

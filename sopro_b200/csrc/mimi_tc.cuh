@@ -1,0 +1,342 @@
+// tcgen05 / TMEM / TMA implicit GEMM for the Mimi decoder's dense blocks (sm_100a only).
+//
+//   C[b][m][n] = epi( sum_{j<taps} sum_{ci<Cin} X[b][m + j*dil - pad][ci] * W[n][j*Cin + ci] + bias[n % bias_mod] )
+//
+// X is a channel-last bf16 activation [B][Min][Cin] (already passed through ELU by its producer when
+// the layer wants ELU(x)), W is a bf16 weight matrix [N][K] (K = taps*Cin, K-major), accumulation is
+// fp32 in tensor memory.  This covers Linear, the causal Conv1d and the causal ConvTranspose1d of
+// transformers' modeling_mimi.py (:331-351, :402-409) exactly as mimi_engine.cu's fp32 path does.
+//
+// One CTA computes one 128 x BN tile:
+//   warp 0    TMA producer: per 64-wide K chunk one 3-D box of X (rows shifted by the tap; rows outside
+//             [0, Min) are zero-filled by the TMA unit == the causal left pad) and one 2-D box of W,
+//             both landing 128B-swizzled in a ring of shared-memory stages, completion on mbarriers
+//   warp 1    allocates BN tensor-memory columns, one lane issues tcgen05.mma (M=128, N=BN, K=16) four
+//             times per chunk; tcgen05.commit releases the stage / signals the accumulator
+//   warps 2-5 epilogue: tcgen05.ld 32 lanes x 32 columns, bias / GELU / LayerScale-residual / skip,
+//             writes fp32 and/or bf16 (optionally ELU'd: the next layer's operand)
+// Two CTAs are resident per SM (<= 100 KB of stages each), so one tile's epilogue overlaps the other's
+// main loop.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace tc {
+
+enum { EPI_NONE = 0, EPI_GELU = 1, EPI_RES_SCALE = 2, EPI_RES = 3 };
+
+struct TcOp {
+  const float* bias;   // [bias_mod] or null
+  const float* R;      // residual fp32 [B][M][N] or null
+  const float* scale;  // LayerScale [N] or null
+  float* out_f32;      // [B][M][N] or null
+  __nv_bfloat16* out_bf16;  // [B][M][N] or null
+  long long c_bs;      // batch stride of R / outputs (elements)
+  int M, N, K, Cin, dil, pad, bias_mod, epi, out_elu;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "W_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra W_%=;\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> one row slice per thread
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor, K-major operand, 128-byte swizzle, rows of 64 bf16 (128 B) stacked
+// densely: 8-row groups are 1024 B apart (SBO), one swizzle atom along K (LBO unused).
+// Bit layout: cute/arch/mma_sm100_desc.hpp (SmemDescriptor): addr>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type [61,64) with SWIZZLE_128B = 2.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::f16: D fp32 (bits [4,6) = 1), A/B bf16 ([7,10) = [10,13) = 1), both
+// K-major (bits 15, 16 = 0), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+constexpr int kBM = 128, kBK = 64, kThreads = 192;
+template <int BN>
+struct TileCfg {
+  static constexpr int kStages = BN >= 128 ? 3 : 4;
+  static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
+  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmem = kStages * kStageBytes + 1024;  // + alignment slack
+  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads) igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmW, const TcOp op) {
+  using Cfg = TileCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * S + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]), accbar = smem_u32(&bars[2 * S]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN, b = blockIdx.z;
+  const int nk = op.K / kBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (uint32_t)(kc / S) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        mbar_expect_tx(full0 + 8 * s, Cfg::kStageBytes);
+        const int k0 = kc * kBK;
+        const int j = k0 / op.Cin, ci = k0 - j * op.Cin;
+        const uint32_t sa = tiles + s * Cfg::kStageBytes;
+        tma_load_3d(sa, &tmA, full0 + 8 * s, ci, m0 + j * op.dil - op.pad, b);
+        tma_load_2d(sa + Cfg::kABytes, &tmW, full0 + 8 * s, k0, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc_bf16(kBM, BN);
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (uint32_t)(kc / S) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = tiles + s * Cfg::kStageBytes;
+        const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k)  // +32 B per K=16 slice inside the swizzle atom
+          tc_mma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0);
+        tc_commit(empty0 + 8 * s);
+      }
+      tc_commit(accbar);
+    }
+  } else {
+    mbar_wait(accbar, 0);
+    tc_fence_after();
+    const int q = warp & 3;  // tensor-memory lane quarter this warp may read
+    const int m = m0 + 32 * q + lane;
+    const bool row_ok = m < op.M;
+    const size_t row = (size_t)b * (size_t)op.c_bs + (size_t)m * op.N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r);
+      if (!row_ok) continue;
+      const int n = n0 + c0;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+      if (op.bias) {
+        const int nb = n % op.bias_mod;  // bias_mod is a multiple of 32 whenever N > bias_mod
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 bv = __ldg(reinterpret_cast<const float4*>(op.bias + nb + i));
+          v[i] += bv.x;
+          v[i + 1] += bv.y;
+          v[i + 2] += bv.z;
+          v[i + 3] += bv.w;
+        }
+      }
+      if (op.epi == EPI_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+      } else if (op.epi == EPI_RES_SCALE || op.epi == EPI_RES) {
+        const float4* rp = reinterpret_cast<const float4*>(op.R + row + n);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 rv = rp[i >> 2];
+          float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
+          if (op.epi == EPI_RES_SCALE) sv = __ldg(reinterpret_cast<const float4*>(op.scale + n + i));
+          v[i] = rv.x + sv.x * v[i];
+          v[i + 1] = rv.y + sv.y * v[i + 1];
+          v[i + 2] = rv.z + sv.z * v[i + 2];
+          v[i + 3] = rv.w + sv.w * v[i + 3];
+        }
+      }
+      if (op.out_f32) {
+        float4* o = reinterpret_cast<float4*>(op.out_f32 + row + n);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) o[i >> 2] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      if (op.out_bf16) {
+        uint4* o = reinterpret_cast<uint4*>(op.out_bf16 + row + n);
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float a = v[i + 2 * e], c = v[i + 2 * e + 1];
+            if (op.out_elu) {
+              a = elu1(a);
+              c = elu1(c);
+            }
+            const __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&h);
+          }
+          o[i >> 3] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// activations [B][rows][cin] bf16, box = 64 channels x 128 rows x 1 batch
+inline bool make_act_map(CUtensorMap* tm, const void* base, int B, long long rows, int cin) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)rows, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)rows * (cuuint64_t)cin * 2};
+  const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kBM, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// weights [N][K] bf16, box = 64 x BN
+inline bool make_weight_map(CUtensorMap* tm, const void* base, int N, int K, int BN) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+  const cuuint32_t es[2] = {1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline int pick_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : (N % 32 == 0 ? 32 : 0)); }
+
+// supported when every K chunk stays inside one tap and the tile shapes divide
+inline bool supported(int N, int K, int Cin) { return Cin % kBK == 0 && K % kBK == 0 && pick_bn(N) != 0; }
+
+template <int BN>
+inline cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcOp& op, int B, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::kSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid((unsigned)((op.M + kBM - 1) / kBM), (unsigned)(op.N / BN), (unsigned)B);
+  igemm_tc_kernel<BN><<<grid, kThreads, TileCfg<BN>::kSmem, st>>>(tmA, tmW, op);
+  return cudaGetLastError();
+}
+
+// X: bf16 [B][Min][Cin]; W: bf16 [N][K]
+inline cudaError_t launch(const void* X, long long Min, const void* W, const TcOp& op, int B, cudaStream_t st) {
+  const int BN = pick_bn(op.N);
+  CUtensorMap tmA, tmW;
+  if (!make_act_map(&tmA, X, B, Min, op.Cin) || !make_weight_map(&tmW, W, op.N, op.K, BN)) return cudaErrorInvalidValue;
+  switch (BN) {
+    case 128: return launch_bn<128>(tmA, tmW, op, B, st);
+    case 64: return launch_bn<64>(tmA, tmW, op, B, st);
+    default: return launch_bn<32>(tmA, tmW, op, B, st);
+  }
+}
+
+}  // namespace tc

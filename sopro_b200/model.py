@@ -203,7 +203,8 @@ class SoproTTS:
     # ---- construction
     @classmethod
     def from_pretrained(cls, repo_id: str, *, revision: Optional[str] = None, cache_dir: Optional[str] = None,
-                        token: Optional[str] = None, device: Optional[str] = None, weight_dtype: str = "fp32") -> "SoproTTS":
+                        token: Optional[str] = None, device: Optional[str] = None, weight_dtype: str = "fp32",
+                        mimi_precision: str = "bf16_tc") -> "SoproTTS":
         """reference model.py:419-451: HF snapshot -> cfg from the safetensors header -> tokenizer -> weights -> Mimi."""
         from huggingface_hub import snapshot_download
 
@@ -218,16 +219,17 @@ class SoproTTS:
         cfg = read_safetensors_cfg(model_path)
         tokenizer = TextTokenizer(model_name=local_dir)
         model = SoproModel(cfg, load_safetensors(model_path), device, weight_dtype)
-        codec = MimiCodec(num_quantizers=cfg.num_codebooks, device=device)
+        codec = MimiCodec(num_quantizers=cfg.num_codebooks, device=device, precision=mimi_precision)
         return cls(model=model, cfg=cfg, tokenizer=tokenizer, codec=codec, device=device)
 
     @classmethod
     def from_state_dict(cls, cfg: SoproTTSConfig, state_dict: Dict[str, torch.Tensor], tokenizer,
                         mimi_state_dict: Dict[str, torch.Tensor], *, device: str = "cuda", weight_dtype: str = "fp32",
-                        mimi_hf_model=None) -> "SoproTTS":
+                        mimi_hf_model=None, mimi_precision: str = "bf16_tc") -> "SoproTTS":
         """Offline constructor (synthetic or locally stored checkpoints): no hub access."""
         model = SoproModel(cfg, state_dict, device, weight_dtype)
-        codec = MimiCodec(int(cfg.num_codebooks), device=device, state_dict=mimi_state_dict, hf_model=mimi_hf_model)
+        codec = MimiCodec(int(cfg.num_codebooks), device=device, state_dict=mimi_state_dict, hf_model=mimi_hf_model,
+                          precision=mimi_precision)
         return cls(model=model, cfg=cfg, tokenizer=tokenizer, codec=codec, device=device)
 
     # ---- reference plumbing (model.py:453-529)

@@ -54,6 +54,14 @@ def test_synthesize_matches_oracle_pipeline():
     # Mimi: decode the product's own tokens with the oracle
     ref_wav = M.mimi_decode(mimi_sd, toks.cpu().permute(1, 0).unsqueeze(0))
     err = float((wav.cpu() - ref_wav).abs().max())
+    assert tts.codec.engine.precision == "bf16_tc"  # the default: tensor-core contractions, stated tolerance 2e-2 of peak
+    assert err <= 2e-2 * float(ref_wav.abs().max()), err
+    tts.codec.engine.set_precision("fp32")
+    try:
+        wav32 = tts.codec.decode_full(toks)
+    finally:
+        tts.codec.engine.set_precision("bf16_tc")
+    err = float((wav32.cpu() - ref_wav).abs().max())
     assert err <= 2e-4 * max(1.0, float(ref_wav.abs().max())), err
 
 
