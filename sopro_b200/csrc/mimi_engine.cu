@@ -241,6 +241,38 @@ __global__ void rope_kernel(float* __restrict__ qkv, const float* __restrict__ c
   }
 }
 
+// Tensor-core attention operands from the fp32 QKV rows [B][T2][3C]: rotated q and k as bf16 [B][T2][C], v transposed
+// as bf16 [B][C][T2p] (keys contiguous: the K-major B operand of P.V).  32 rows per block.
+__global__ void __launch_bounds__(256) rope_pack_kernel(const float* __restrict__ qkv, const float* __restrict__ cs,
+                                                        __nv_bfloat16* __restrict__ qh, __nv_bfloat16* __restrict__ kh,
+                                                        __nv_bfloat16* __restrict__ vt, int T2, long long T2p, int tab_T2, int C, int H) {
+  extern __shared__ __nv_bfloat16 sv[];  // [32][C + 2]
+  const int t0 = blockIdx.x * 32, b = blockIdx.y;
+  const int Dh = C / H, half = Dh / 2, nrot = H * half;
+  const int rows = min(32, T2 - t0);
+  for (int idx = threadIdx.x; idx < rows * 2 * nrot; idx += blockDim.x) {
+    const int tt = idx / (2 * nrot), i = idx - tt * 2 * nrot;
+    const int which = i / nrot, rem = i - which * nrot;
+    const int h = rem / half, d = rem - h * half;
+    const int t = t0 + tt;
+    const float* p = qkv + ((size_t)b * T2 + t) * 3 * C + which * C + h * Dh;
+    const float x1 = p[d], x2 = p[d + half];
+    const float c = cs[(size_t)t * half + d], s = cs[(size_t)(tab_T2 + t) * half + d];
+    __nv_bfloat16* o = (which ? kh : qh) + ((size_t)b * T2 + t) * C + h * Dh;
+    o[d] = __float2bfloat16_rn(x1 * c - x2 * s);
+    o[d + half] = __float2bfloat16_rn(x2 * c + x1 * s);
+  }
+  for (int idx = threadIdx.x; idx < rows * C; idx += blockDim.x) {
+    const int tt = idx / C, c = idx - tt * C;
+    sv[tt * (C + 2) + c] = __float2bfloat16_rn(qkv[((size_t)b * T2 + t0 + tt) * 3 * C + 2 * C + c]);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < 32 * C; idx += blockDim.x) {
+    const int c = idx >> 5, tt = idx & 31;
+    if (t0 + tt < T2p) vt[((size_t)b * C + c) * T2p + t0 + tt] = tt < rows ? sv[tt * (C + 2) + c] : __float2bfloat16_rn(0.f);  // pad stays finite
+  }
+}
+
 // causal sliding-window attention, one warp per (b, h, query); QKV rotated; out [B][T2][C]
 template <typename OutT>
 __global__ void __launch_bounds__(256) attn_kernel(const float* __restrict__ qkv, OutT* __restrict__ out, int T2, int C,
@@ -642,14 +674,25 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
   const unsigned ln_grid = (unsigned)((rows + 7) / 8);
   const size_t asm_bytes = (size_t)8 * (Dh + c.window) * 4;
   const bool tc_tr = use_tc && tc::supported(3 * C, C, C) && tc::supported(C, C, C) && tc::supported(FF, C, C) && tc::supported(C, FF, FF);
+  const bool tc_attn = tc_tr && tc::attn_supported(C, H, c.window) && (size_t)32 * (C + 2) * 2 <= 48 * 1024;
+  const long long T2p = (T2 + 7) / 8 * 8;  // v^T row pitch: tensor-map strides are multiples of 16 bytes
   for (const sopro_mimi::Layer& L : m->layers) {
     if (tc_tr) {
       layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln1w, Wd + L.ln1b, h0, rows, C, c.norm_eps);
       if ((rc = tcg(h0, T2, C, 1, 0, Wh + L.qkv_h, nullptr, 3 * C, 3 * C, tc::EPI_NONE, nullptr, nullptr, b0, nullptr, 0))) return rc;
-      rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H);
-      attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, h1, T2, C, H, c.window);
-      MCK(cudaGetLastError());
-      if ((rc = tcg(h1, T2, C, 1, 0, Wh + L.wo_h, nullptr, C, C, tc::EPI_RES_SCALE, x, Wd + L.ls1, x, nullptr, 0))) return rc;
+      __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(b1);  // b1 is idle during the transformer
+      if (tc_attn) {
+        // q -> h0 (the LayerNorm copy is dead), k -> h1, v^T -> h2
+        rope_pack_kernel<<<dim3((T2 + 31) / 32, B), 256, (size_t)32 * (C + 2) * 2, st>>>(b0, m->rope, h0, h1, h2, T2, T2p, m->rope_T2, C, H);
+        MCK(cudaGetLastError());
+        cudaError_t ae = tc::launch_attn(h0, h1, h2, att, B, T2, T2p, C, H, c.window, st);
+        if (ae != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "tensor-core attention: %s", cudaGetErrorString(ae));
+      } else {
+        rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H);
+        attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, att, T2, C, H, c.window);
+        MCK(cudaGetLastError());
+      }
+      if ((rc = tcg(att, T2, C, 1, 0, Wh + L.wo_h, nullptr, C, C, tc::EPI_RES_SCALE, x, Wd + L.ls1, x, nullptr, 0))) return rc;
       layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln2w, Wd + L.ln2b, h0, rows, C, c.norm_eps);
       if ((rc = tcg(h0, T2, C, 1, 0, Wh + L.fc1_h, nullptr, FF, FF, tc::EPI_GELU, nullptr, nullptr, nullptr, h2, 0))) return rc;
       if ((rc = tcg(h2, T2, FF, 1, 0, Wh + L.fc2_h, nullptr, C, C, tc::EPI_RES_SCALE, x, Wd + L.ls2, x, nullptr, 0))) return rc;

@@ -22,6 +22,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdint>
 
 namespace tc {
@@ -267,6 +268,171 @@ __global__ void __launch_bounds__(kThreads) igemm_tc_kernel(const __grid_constan
 }
 
 // ---------------------------------------------------------------------------------------------
+// Causal sliding-window attention on the tensor cores (MimiAttention.forward, modeling_mimi.py:681-738,
+// head_dim 64, window <= 257).  One CTA = 128 queries of one (batch, head):
+//   S = Q K^T over the 384 keys [q0-256, q0+128) -> 384 fp32 columns of tensor memory (3 x M128 N128 K64)
+//   softmax with thread == query row (no shuffles): two passes over tensor memory, P rounded to bf16 and
+//   written 128B-swizzled into shared memory as the next A operand (over the dead Q/K tiles)
+//   O = P V with V^T [d][key] tiles as the K-major B operand -> 64 more columns; scaled by 1/sum on the way out
+// Inputs are the rotated bf16 q / k [B][T2][C] and v transposed [B][C][T2p] written by rope_pack_kernel.
+// ---------------------------------------------------------------------------------------------
+struct AttnOp {
+  __nv_bfloat16* out;  // [B][T2][C]
+  int T2, C, window;
+  float scale_log2e;   // log2(e) / sqrt(head_dim)
+};
+
+constexpr int kAttnKeys = 384, kAttnDh = 64;
+constexpr int kAttnSmem = 65536 + 49152 + 32768 + 1024;
+
+__global__ void __launch_bounds__(kThreads) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                                                           const __grid_constant__ CUtensorMap tmVt, const AttnOp op) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[5];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = tiles, sK = tiles + 16384, sV = tiles + 65536;
+  const uint32_t qk_full = smem_u32(&bars[0]), v_full = smem_u32(&bars[1]), s_full = smem_u32(&bars[2]),
+                 p_full = smem_u32(&bars[3]), o_full = smem_u32(&bars[4]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int kbase = q0 + 128 - kAttnKeys;
+  auto p_block = [&](int kb) -> uint32_t { return kb < 4 ? tiles + kb * 16384 : tiles + 65536 + 49152 + (kb - 4) * 16384; };
+
+  if (threadIdx.x == 0) {
+    mbar_init(qk_full, 1);
+    mbar_init(v_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(qk_full, 65536);
+      tma_load_3d(sQ, &tmQ, qk_full, h * kAttnDh, q0, b);
+      for (int kt = 0; kt < 3; ++kt) tma_load_3d(sK + kt * 16384, &tmK, qk_full, h * kAttnDh, kbase + kt * 128, b);
+      mbar_expect_tx(v_full, 49152);
+      for (int kb = 0; kb < 6; ++kb) tma_load_3d(sV + kb * 8192, &tmVt, v_full, kbase + kb * 64, h * kAttnDh, b);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(qk_full, 0);
+      tc_fence_after();
+      const uint64_t dq = smem_desc_sw128(sQ);
+      for (int kt = 0; kt < 3; ++kt) {
+        const uint64_t dk = smem_desc_sw128(sK + kt * 16384);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem + kt * 128, dq + 2 * k, dk + 2 * k, instr_desc_bf16(128, 128), k != 0);
+      }
+      tc_commit(s_full);
+      mbar_wait(p_full, 0);
+      mbar_wait(v_full, 0);
+      tc_fence_after();
+      for (int kb = 0; kb < 6; ++kb) {
+        const uint64_t dp = smem_desc_sw128(p_block(kb)), dv = smem_desc_sw128(sV + kb * 8192);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem + kAttnKeys, dp + 2 * k, dv + 2 * k, instr_desc_bf16(128, 64), (kb | k) != 0);
+      }
+      tc_commit(o_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = 32 * q + lane;   // row of the tile == tensor-memory lane
+    const int i = q0 + r;          // query position
+    const bool row_ok = i < op.T2;
+    // valid key columns of this row / of the whole warp (slices outside the warp's band are skipped uniformly)
+    const int clo = row_ok ? max(0, i - op.window + 1) - kbase : 1, chi = row_ok ? i - kbase : 0;
+    const int i_first = q0 + 32 * q, i_last = min(i_first + 31, op.T2 - 1);
+    const int wlo = max(0, i_first - op.window + 1) - kbase, whi = i_last - kbase;  // whi < wlo when the warp has no rows
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    float mx = -INFINITY;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kAttnKeys; c0 += 32) {
+      if (c0 + 31 < wlo || c0 > whi) continue;
+      uint32_t v[32];
+      tc_ld32(trow + c0, v);
+#pragma unroll
+      for (int e = 0; e < 32; ++e)
+        if (c0 + e >= clo && c0 + e <= chi) mx = fmaxf(mx, __uint_as_float(v[e]));
+    }
+    float sum = 0.f;
+    const float mxs = mx * op.scale_log2e;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kAttnKeys; c0 += 32) {
+      const bool live = !(c0 + 31 < wlo || c0 > whi);
+      uint32_t pk[16];
+      if (live) {
+        uint32_t v[32];
+        tc_ld32(trow + c0, v);
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = 0.f, p1 = 0.f;
+          if (c0 + e >= clo && c0 + e <= chi) p0 = exp2f(fmaf(__uint_as_float(v[e]), op.scale_log2e, -mxs));
+          if (c0 + e + 1 >= clo && c0 + e + 1 <= chi) p1 = exp2f(fmaf(__uint_as_float(v[e + 1]), op.scale_log2e, -mxs));
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+          sum += __low2float(hh) + __high2float(hh);
+          pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pk[e] = 0u;
+      }
+      // 32 keys = 4 sixteen-byte chunks of row r in P block c0/64, chunk index XOR (r & 7)
+      const uint32_t rowaddr = p_block(c0 >> 6) + r * 128;
+      const int ch0 = (c0 & 63) >> 3;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const uint32_t a = rowaddr + (uint32_t)(((ch0 + cc) ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * cc]), "r"(pk[4 * cc + 1]), "r"(pk[4 * cc + 2]),
+                     "r"(pk[4 * cc + 3])
+                     : "memory");
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(p_full) : "memory");
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    const float inv = row_ok ? 1.0f / sum : 0.f;
+    __nv_bfloat16* orow = op.out + ((size_t)b * op.T2 + (row_ok ? i : 0)) * op.C + h * kAttnDh;
+#pragma unroll 1
+    for (int c0 = 0; c0 < kAttnDh; c0 += 32) {
+      uint32_t v[32];
+      tc_ld32(trow + kAttnKeys + c0, v);
+      if (!row_ok) continue;
+#pragma unroll
+      for (int e = 0; e < 32; e += 8) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(v[e + 2 * u]) * inv, __uint_as_float(v[e + 2 * u + 1]) * inv);
+          w4[u] = *reinterpret_cast<const uint32_t*>(&hh);
+        }
+        *reinterpret_cast<uint4*>(orow + c0 + e) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -307,6 +473,38 @@ inline bool make_weight_map(CUtensorMap* tm, const void* base, int N, int K, int
   const cuuint32_t es[2] = {1, 1};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// v transposed [B][C][T2p] bf16, box = 64 keys x 64 channels
+inline bool make_vt_map(CUtensorMap* tm, const void* base, int B, int C, long long T2, long long T2p) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)T2, (cuuint64_t)C, (cuuint64_t)B};
+  const cuuint64_t strides[2] = {(cuuint64_t)T2p * 2, (cuuint64_t)C * (cuuint64_t)T2p * 2};
+  const cuuint32_t box[3] = {64, 64, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline bool attn_supported(int C, int H, int window) { return H > 0 && C == H * kAttnDh && window >= 1 && window <= kAttnKeys - 127; }
+
+// q, k: bf16 [B][T2][C] (rotated); vt: bf16 [B][C][T2p]; out: bf16 [B][T2][C]
+inline cudaError_t launch_attn(const void* q, const void* k, const void* vt, __nv_bfloat16* out, int B, int T2, long long T2p, int C,
+                               int H, int window, cudaStream_t st) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  CUtensorMap tmQ, tmK, tmV;
+  if (!make_act_map(&tmQ, q, B, T2, C) || !make_act_map(&tmK, k, B, T2, C) || !make_vt_map(&tmV, vt, B, C, T2, T2p))
+    return cudaErrorInvalidValue;
+  AttnOp op{out, T2, C, window, 1.4426950408889634f / sqrtf((float)kAttnDh)};
+  dim3 grid((unsigned)((T2 + 127) / 128), (unsigned)H, (unsigned)B);
+  attn_tc_kernel<<<grid, kThreads, kAttnSmem, st>>>(tmQ, tmK, tmV, op);
+  return cudaGetLastError();
 }
 
 inline int pick_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : (N % 32 == 0 ? 32 : 0)); }

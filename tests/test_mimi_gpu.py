@@ -33,7 +33,7 @@ def test_decode_matches_oracle(B, T):
     assert float((got - want).abs().max()) <= 2e-4 * max(1.0, peak)
 
 
-@pytest.mark.parametrize("B,T", [(1, 1), (2, 9), (1, 37), (3, 16), (1, 150)])
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 9), (1, 37), (3, 16), (1, 150), (2, 203)])
 def test_decode_tensor_core_mode(B, T):
     """Default mode: bf16 operands on the tcgen05 tensor cores, fp32 accumulation.  Stated tolerance: max error
     2e-2 of the waveform's peak and relative RMS error 1e-2 against the fp32 oracle."""
