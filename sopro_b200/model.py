@@ -37,22 +37,42 @@ def center_crop_tokens(ref_tq: torch.Tensor, win_frames: int) -> torch.Tensor:
 
 class _Noise:
     """The Exp(1) draws `steps` successive torch.multinomial calls would consume (see sopro_b200/sampling.py),
-    with the bookkeeping needed to leave the generator exactly where the reference would leave it."""
+    produced block by block as the kernel launches need them (a [n, V] draw equals n successive [V] draws), with
+    the bookkeeping needed to leave the generator exactly where the reference would leave it."""
 
     def __init__(self, steps: int, vocab: int, seed: Optional[int], generator: Optional[torch.Generator]):
-        self.vocab = vocab
+        self.steps, self.vocab = int(steps), int(vocab)
         self.private = seed is not None
         self.gen = torch.Generator().manual_seed(int(seed)) if seed is not None else (generator or torch.default_generator)
-        self.state = self.gen.get_state()
-        self.tape = torch.empty(int(steps), int(vocab)).exponential_(1.0, generator=self.gen)
+        self.marks: List[Tuple[int, torch.Tensor]] = []  # (first row of a block, generator state before it)
+        self.drawn = 0
+
+    def rows(self, upto: int) -> torch.Tensor:
+        """Draw rows [drawn, upto) -> [n, V] (empty when already drawn)."""
+        upto = min(int(upto), self.steps)
+        n = upto - self.drawn
+        if n <= 0:
+            return torch.empty(0, self.vocab)
+        if not self.private:
+            self.marks.append((self.drawn, self.gen.get_state()))
+        self.drawn = upto
+        return torch.empty(n, self.vocab).exponential_(1.0, generator=self.gen)
+
+    @property
+    def tape(self) -> torch.Tensor:
+        """All rows at once (only valid before any block has been drawn)."""
+        assert self.drawn == 0
+        return self.rows(self.steps)
 
     def settle(self, steps_used: int) -> None:
         """Rewind to the state after exactly `steps_used` draws (the reference stops drawing when it stops stepping)."""
-        if self.private:
+        if self.private or steps_used >= self.drawn:
             return
-        self.gen.set_state(self.state)
-        if steps_used > 0:
-            torch.empty(int(steps_used), int(self.vocab)).exponential_(1.0, generator=self.gen)
+        start, state = [m for m in self.marks if m[0] <= steps_used][-1]
+        self.gen.set_state(state)
+        if steps_used > start:
+            torch.empty(int(steps_used - start), self.vocab).exponential_(1.0, generator=self.gen)
+        self.drawn = int(steps_used)
 
 
 class SoproModel:
@@ -72,6 +92,10 @@ class SoproModel:
         self.text_pos = P.sinusoid_table(int(cfg.max_text_len) + 8, int(cfg.d_model), self.device)
         self.frame_pos = P.sinusoid_table(int(cfg.pos_emb_max) + 8, int(cfg.d_model), self.device)
         self._sessions: Dict[Tuple[int, int, int], ArSession] = {}
+        self._nar_cache: dict = {}
+        self._nar_graphs: Dict[Tuple[int, int], tuple] = {}
+        self._nar_seen: Dict[Tuple[int, int], int] = {}
+        self.use_cuda_graphs = os.environ.get("SOPRO_CUDA_GRAPHS", "1") != "0"
 
     # ---- geometry helpers (reference model.py:119-131)
     def rf_ar(self) -> int:
@@ -104,7 +128,36 @@ class SoproModel:
 
     @torch.no_grad()
     def nar_refine(self, cond_seq: torch.Tensor, rvq1_1xT: torch.Tensor) -> torch.Tensor:
-        return P.nar_refine(self.sd, self.cfg, cond_seq, rvq1_1xT)
+        """reference model.py:307-347.  The refiner is ~600 small torch kernels; a (B, T) shape seen twice is captured
+        into a CUDA graph and replayed from then on (same kernels, same results, one launch)."""
+        key = (int(cond_seq.size(0)), int(cond_seq.size(1)))
+        if not self.use_cuda_graphs or key[1] == 0:
+            return P.nar_refine(self.sd, self.cfg, cond_seq, rvq1_1xT, self._nar_cache)
+        ent = self._nar_graphs.get(key)
+        if ent is None:
+            self._nar_seen[key] = self._nar_seen.get(key, 0) + 1
+            if self._nar_seen[key] < 2:
+                return P.nar_refine(self.sd, self.cfg, cond_seq, rvq1_1xT, self._nar_cache)
+            if len(self._nar_graphs) >= 12:
+                self._nar_graphs.pop(next(iter(self._nar_graphs)))
+            c_in = cond_seq.detach().clone().contiguous()
+            t_in = rvq1_1xT.detach().to(torch.long).clone().contiguous()
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                P.nar_refine(self.sd, self.cfg, c_in, t_in, self._nar_cache)  # warm-up: cuBLAS workspaces, caches
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = P.nar_refine(self.sd, self.cfg, c_in, t_in, self._nar_cache)
+            ent = (graph, c_in, t_in, out)
+            self._nar_graphs[key] = ent
+        graph, c_in, t_in, out = ent
+        c_in.copy_(cond_seq)
+        t_in.copy_(rvq1_1xT)
+        graph.replay()
+        return out.clone()
 
     # ---- the hot path
     def _sampling(self, top_p, temperature, anti_loop, loop_streak, recovery_top_p, recovery_temp, min_gen_frames,
@@ -130,12 +183,18 @@ class SoproModel:
         noise = _Noise(steps, self.cfg.ar_vocab(), seed, generator)
         ses = self._session(1, steps, L)
         samp = self._sampling(top_p, temperature, anti_loop, loop_streak, recovery_top_p, recovery_temp, min_gen_frames, False)
-        ses.begin(cond[:, :steps], txt, [L], noise.tape[:, : samp.top_k].contiguous().unsqueeze(0), samp)
+        # the session keeps a pointer to this device tape; each launch's rows are drawn and uploaded just before it
+        tape = torch.zeros(1, steps, samp.top_k, device=self.device)
+        ses.begin(cond[:, :steps], txt, [L], tape, samp)
         per = steps if launch_frames <= 0 else int(launch_frames)
         t = 0
         used = 0
         try:
             while t < steps:
+                lo = noise.drawn
+                blk = noise.rows(t + per)
+                if blk.size(0):
+                    tape[0, lo: lo + blk.size(0)].copy_(blk[:, : samp.top_k])
                 ses.run(per)
                 toks, n, done = ses.read()
                 upto = int(n[0])
@@ -164,7 +223,13 @@ class SoproModel:
         txt = torch.zeros(B, Ls, D, device=self.device)
         for i, p in enumerate(preps):
             txt[i, : lens[i]] = p["txt_seq"][0]
-        tapes = [_Noise(steps, V, None if seeds is None else int(seeds[i]), None).tape[:, :50] for i in range(B)]
+        if seeds is None:  # one shared generator: utterance after utterance
+            tapes = [_Noise(steps, V, None, None).tape[:, :50] for _ in range(B)]
+        else:  # independent private generators: draw them on a few host threads (the draws release the GIL)
+            from concurrent.futures import ThreadPoolExecutor
+
+            with ThreadPoolExecutor(max_workers=min(B, max(1, len(os.sched_getaffinity(0))))) as ex:
+                tapes = list(ex.map(lambda sd_: _Noise(steps, V, int(sd_), None).tape[:, :50].contiguous(), seeds))
         ses = self._session(B, steps, Ls)
         samp = self._sampling(top_p, temperature, anti_loop, 8, 0.85, 1.2, min_gen_frames, stop_on_first_eos)
         ses.begin(cond, txt, lens, torch.stack(tapes).contiguous(), samp)
@@ -290,15 +355,35 @@ class SoproTTS:
         preps = [self.model.prepare_conditioning(self.encode_text(t), ref, max_frames=max_frames, style_strength=st) for t in texts]
         hists = self.model.ar_generate_batch(preps, max_frames=max_frames, top_p=top_p, temperature=temperature,
                                              anti_loop=anti_loop, min_gen_frames=min_gen_frames, seeds=seeds)
-        out = []
         eos = self.model.eos_id
-        for prep, h in zip(preps, hists):
-            T = h.index(eos) if eos in h else len(h)
-            if T <= 0:
-                out.append(torch.zeros(1, 1, 0, device=self.device))
-                continue
-            rvq1 = torch.tensor(h[:T], device=self.device, dtype=torch.long).unsqueeze(0)
-            out.append(self.codec.decode_full(self.model.nar_refine(prep["cond_ar"][:, :T], rvq1).squeeze(0)))
+        Ts = [(h.index(eos) if eos in h else len(h)) for h in hists]
+        # NAR refiner: not causal, so only utterances of equal length share a batch
+        codes: List[Optional[torch.Tensor]] = [None] * len(texts)
+        by_len: Dict[int, List[int]] = {}
+        for i, T in enumerate(Ts):
+            if T > 0:
+                by_len.setdefault(T, []).append(i)
+        for T, idx in by_len.items():
+            cond = torch.cat([preps[i]["cond_ar"][:, :T] for i in idx], dim=0)
+            rvq1 = torch.tensor([hists[i][:T] for i in idx], device=self.device, dtype=torch.long)
+            full = self.model.nar_refine(cond, rvq1)  # [n, T, Q]
+            for j, i in enumerate(idx):
+                codes[i] = full[j]
+        # Mimi decode is causal and per-utterance: right-pad to the longest of a chunk, decode together, cut
+        out: List[torch.Tensor] = [torch.zeros(1, 1, 0, device=self.device) for _ in texts]
+        live = [i for i, T in enumerate(Ts) if T > 0]
+        hop = self.codec.engine.hop
+        while live:
+            chunk, frames = [], 0
+            while live and (not chunk or (len(chunk) + 1) * max(frames, Ts[live[0]]) <= 8192):
+                frames = max(frames, Ts[live[0]])
+                chunk.append(live.pop(0))
+            batch = torch.zeros(len(chunk), int(self.cfg.num_codebooks), frames, dtype=torch.int32, device=self.device)
+            for j, i in enumerate(chunk):
+                batch[j, :, : Ts[i]] = codes[i].permute(1, 0)
+            wav = self.codec.engine.decode(batch)
+            for j, i in enumerate(chunk):
+                out[i] = wav[j: j + 1, :, : Ts[i] * hop].clone()
         return out
 
     def stream(self, text: str, **kwargs) -> Iterator[torch.Tensor]:

@@ -185,7 +185,9 @@ def prepare_conditioning(sd: SD, cfg: SoproTTSConfig, text_ids_1d: Tensor, ref: 
     return {"txt_seq": txt_seq, "text_mask": mask, "txt_pool": txt_pool, "sv_ref": sv, "cond_ar": cond}
 
 
-def nar_refine(sd: SD, cfg: SoproTTSConfig, cond_seq: Tensor, rvq1_bt: Tensor) -> Tensor:
+def nar_refine(sd: SD, cfg: SoproTTSConfig, cond_seq: Tensor, rvq1_bt: Tensor, cache: Optional[dict] = None) -> Tensor:
+    """`cache` (optional) keeps the per-stage codebook-index tensors on the device between calls, which also makes
+    the whole function capturable in a CUDA graph (no host->device copy inside)."""
     B, T, D = cond_seq.shape
     Q, V = int(cfg.num_codebooks), int(cfg.codebook_size)
     out = torch.zeros((B, T, Q), device=cond_seq.device, dtype=torch.long)
@@ -197,7 +199,12 @@ def nar_refine(sd: SD, cfg: SoproTTSConfig, cond_seq: Tensor, rvq1_bt: Tensor) -
     for sid, (name, idxs) in enumerate(stages):
         toks = torch.cat(prev_tok, dim=-1)
         cbs = sum(prev_cb, [])
-        cbt = torch.tensor(cbs, device=toks.device, dtype=torch.long)
+        ck = ("nar_cbt", sid, str(toks.device))
+        cbt = cache.get(ck) if cache is not None else None
+        if cbt is None:
+            cbt = torch.tensor(cbs, device=toks.device, dtype=torch.long)
+            if cache is not None:
+                cache[ck] = cbt
         e = emb[cbt.view(1, 1, -1) * V + toks]
         w = F.softmax(sd["nar_prev_cb_weights"].float().index_select(0, cbt), dim=0)
         prev_sum = (e * w.view(1, 1, -1, 1)).sum(dim=2)

@@ -120,3 +120,29 @@ def test_wav_roundtrip(tmp_path):
     assert float((back[0] - wav).abs().max()) < 1e-3
     trimmed = trim_silence_energy(back, sr)
     assert sr * 0.9 < trimmed.shape[-1] < wav.numel()
+
+
+def test_noise_blocks_equal_one_tape_and_settle_rewinds():
+    """ar_stream draws the sampler's Exp(1) rows launch by launch: the blocks must concatenate to the one-shot tape
+    (== what `steps` multinomial calls consume) and settle() must leave the global generator after exactly the
+    consumed rows."""
+    from sopro_b200.model import _Noise
+
+    V = 2049
+    torch.manual_seed(3)
+    full = torch.empty(20, V).exponential_(1.0)
+    after_full = torch.get_rng_state()
+    torch.manual_seed(3)
+    n = _Noise(20, V, None, None)
+    got = torch.cat([n.rows(up) for up in (6, 12, 18, 24)])
+    assert torch.equal(got, full) and torch.equal(torch.get_rng_state(), after_full)
+    n.settle(8)
+    state = torch.get_rng_state()
+    torch.manual_seed(3)
+    torch.empty(8, V).exponential_(1.0)
+    assert torch.equal(state, torch.get_rng_state())
+    # a private seed never touches the global generator
+    before = torch.get_rng_state()
+    p = _Noise(5, V, 11, None)
+    assert torch.equal(p.tape, torch.empty(5, V).exponential_(1.0, generator=torch.Generator().manual_seed(11)))
+    assert torch.equal(before, torch.get_rng_state())
