@@ -343,6 +343,53 @@ __global__ void final_conv_kernel(const float* __restrict__ x, const float* __re
   y[(size_t)b * Tn + t] = acc;
 }
 
+// final conv on the bf16 activation [B][Tn][Cin] that already went through ELU (tensor-core mode): one thread per
+// input row computes the row's dot product with every tap's weights (each row is read once), the taps are combined
+// through shared memory.  256 - (taps-1) outputs per block.
+__global__ void __launch_bounds__(256) final_conv_h_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ bias, float* __restrict__ y, long long Tn,
+                                                           int Cin, int taps) {
+  extern __shared__ float fsm[];  // [taps][256] partial dots, then [taps*Cin] weights
+  float* sp = fsm;
+  float* sw = fsm + taps * 256;
+  const int tid = threadIdx.x, halo = taps - 1, per = 256 - halo, b = blockIdx.y;
+  for (int i = tid; i < taps * Cin; i += 256) sw[i] = __ldg(w + i);
+  __syncthreads();
+  const long long r = (long long)blockIdx.x * per - halo + tid;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (r >= 0 && r < Tn) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + ((size_t)b * Tn + r) * Cin);
+    for (int c = 0; c < Cin; c += 8) {
+      const uint4 v = xr[c >> 3];
+      const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        f[2 * e] = __uint_as_float(u[e] << 16);
+        f[2 * e + 1] = __uint_as_float(u[e] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < taps) {
+          const float* wj = sw + j * Cin + c;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[j] = fmaf(f[e], wj[e], acc[j]);
+        }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < taps) sp[j * 256 + tid] = acc[j];
+  __syncthreads();
+  if (tid >= halo && r < Tn) {  // output sample r: tap j reads row r + j - halo
+    float o = __ldg(bias);
+    for (int j = 0; j < taps; ++j) o += sp[j * 256 + tid - halo + j];
+    y[(size_t)b * Tn + r] = o;
+  }
+}
+
 }  // namespace mimi
 
 using namespace mimi;
@@ -748,6 +795,7 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
     if ((rc = conv(x, Tn, C, c.kernel, c.kernel - 1, Wd + m->c0w, Wd + m->c0b, ch, ch, b0, 0, EPI_NONE, nullptr))) return rc;
     cur32 = b0;
   }
+  const bool final_h = c.num_filters % 8 == 0 && c.last_kernel <= 8;  // final conv reads the bf16 ELU'd activation
   for (size_t si = 0; si < m->stages.size(); ++si) {
     const sopro_mimi::Stage& S = m->stages[si];
     if (Tn * S.ratio > 0x7fffffffLL) return mfail(SOPRO_ERR_INVALID, "sequence too long for one launch");
@@ -758,7 +806,7 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
     const bool r2_ok = tc::supported(S.cout, hid, hid);
     // the consumer of this stage's output: the next ConvTranspose on tensor cores wants bf16 ELU(x); the
     // final conv and the fp32 kernels read fp32
-    bool next_tc = false;
+    bool next_tc = final_h;  // after the last stage: the bf16 final conv
     if (!last) {
       const sopro_mimi::Stage& Nx = m->stages[si + 1];
       next_tc = tc::supported(Nx.ratio * Nx.cout, 2 * Nx.cin, Nx.cin);
@@ -790,14 +838,19 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
     } else {
       if ((rc = conv(b2, Tn, hid, 1, 0, Wd + S.r2w, Wd + S.r2b, S.cout, S.cout, b0, 1, EPI_RES, b1))) return rc;
       cur32 = b0;
-      if (next_tc) {  // fp32 block output feeding a tensor-core ConvTranspose: not reachable with Mimi's geometry
+      if (next_tc && !last) {  // fp32 block output feeding a tensor-core ConvTranspose: not reachable with Mimi's geometry
         return mfail(SOPRO_ERR_UNSUPPORTED, "unsupported channel geometry for tensor-core mode (stage %zu)", si);
       }
     }
     ch = S.cout;
   }
-  if (!cur32) return mfail(SOPRO_ERR_UNSUPPORTED, "internal: final conv needs an fp32 input");
-  final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur32, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
+  if (cur32) {
+    final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur32, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
+  } else {
+    const int per = 256 - (c.last_kernel - 1);
+    final_conv_h_kernel<<<dim3((unsigned)((Tn + per - 1) / per), B), 256, (size_t)(c.last_kernel * 256 + c.last_kernel * ch) * 4, st>>>(
+        curh, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
+  }
   MCK(cudaGetLastError());
   return SOPRO_OK;
 }

@@ -107,6 +107,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
   return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// same for rows of 32 bf16 (64 B), 64-byte swizzle: 8-row groups 512 B apart, layout_type SWIZZLE_64B = 4
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(512u >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+template <int BK>
+__device__ __forceinline__ uint64_t smem_desc_k(uint32_t addr) {
+  return BK == 64 ? smem_desc_sw128(addr) : smem_desc_sw64(addr);
+}
 // instruction descriptor, kind::f16: D fp32 (bits [4,6) = 1), A/B bf16 ([7,10) = [10,13) = 1), both
 // K-major (bits 15, 16 = 0), N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
@@ -114,23 +122,27 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
 }
 
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU whose result is rounded to bf16 right away: exp(x) - 1 with the fast exponential is exact to well below
+// half a bf16 ulp (absolute error ~1e-7 against a result of magnitude >= |x|/2)
+__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 constexpr int kBM = 128, kBK = 64, kThreads = 192;
-template <int BN>
+constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps (2 per tensor-memory lane quarter)
+template <int BN, int BK>
 struct TileCfg {
   static constexpr int kStages = BN >= 128 ? 3 : 4;
-  static constexpr int kABytes = kBM * kBK * 2;  // 16 KB
-  static constexpr int kBBytes = BN * kBK * 2;
+  static constexpr int kABytes = kBM * BK * 2;  // 16 KB at BK = 64
+  static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kSmem = kStages * kStageBytes + 1024;  // + alignment slack
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads) igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                            const __grid_constant__ CUtensorMap tmW, const TcOp op) {
-  using Cfg = TileCfg<BN>;
+template <int BN, int BK>
+__global__ void __launch_bounds__(kGemmThreads) igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmW, const TcOp op) {
+  using Cfg = TileCfg<BN, BK>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * S + 1];
@@ -139,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) igemm_tc_kernel(const __grid_constan
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]), accbar = smem_u32(&bars[2 * S]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN, b = blockIdx.z;
-  const int nk = op.K / kBK;
+  const int nk = op.K / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(kThreads) igemm_tc_kernel(const __grid_constan
         const uint32_t ph = (uint32_t)(kc / S) & 1u;
         mbar_wait(empty0 + 8 * s, ph ^ 1u);
         mbar_expect_tx(full0 + 8 * s, Cfg::kStageBytes);
-        const int k0 = kc * kBK;
+        const int k0 = kc * BK;
         const int j = k0 / op.Cin, ci = k0 - j * op.Cin;
         const uint32_t sa = tiles + s * Cfg::kStageBytes;
         tma_load_3d(sa, &tmA, full0 + 8 * s, ci, m0 + j * op.dil - op.pad, b);
@@ -183,9 +195,9 @@ __global__ void __launch_bounds__(kThreads) igemm_tc_kernel(const __grid_constan
         mbar_wait(full0 + 8 * s, ph);
         tc_fence_after();
         const uint32_t sa = tiles + s * Cfg::kStageBytes;
-        const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + Cfg::kABytes);
+        const uint64_t da = smem_desc_k<BK>(sa), db = smem_desc_k<BK>(sa + Cfg::kABytes);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k)  // +32 B per K=16 slice inside the swizzle atom
+        for (int k = 0; k < BK / 16; ++k)  // +32 B per K=16 slice inside the swizzle atom
           tc_mma_bf16(tmem, da + 2 * k, db + 2 * k, idesc, (kc | k) != 0);
         tc_commit(empty0 + 8 * s);
       }
@@ -198,8 +210,11 @@ __global__ void __launch_bounds__(kThreads) igemm_tc_kernel(const __grid_constan
     const int m = m0 + 32 * q + lane;
     const bool row_ok = m < op.M;
     const size_t row = (size_t)b * (size_t)op.c_bs + (size_t)m * op.N;
+    // the two warps of a quarter split the columns (a 32-column tile is done by the first alone)
+    constexpr int kColsPerWarp = BN >= 64 ? BN / 2 : BN;
+    const int cbeg = BN >= 64 ? ((warp - 2) >> 2) * kColsPerWarp : ((warp - 2) >> 2) * BN;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = cbeg; c0 < cbeg + kColsPerWarp && c0 < BN; c0 += 32) {
       uint32_t r[32];
       tc_ld32(tmem + ((uint32_t)(32 * q) << 16) + (uint32_t)c0, r);
       if (!row_ok) continue;
@@ -248,8 +263,8 @@ __global__ void __launch_bounds__(kThreads) igemm_tc_kernel(const __grid_constan
           for (int e = 0; e < 4; ++e) {
             float a = v[i + 2 * e], c = v[i + 2 * e + 1];
             if (op.out_elu) {
-              a = elu1(a);
-              c = elu1(c);
+              a = elu_fast(a);
+              c = elu_fast(c);
             }
             const __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
             pk[e] = *reinterpret_cast<const uint32_t*>(&h);
@@ -451,28 +466,30 @@ inline EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// activations [B][rows][cin] bf16, box = 64 channels x 128 rows x 1 batch
-inline bool make_act_map(CUtensorMap* tm, const void* base, int B, long long rows, int cin) {
+// activations [B][rows][cin] bf16, box = bk channels x 128 rows x 1 batch
+inline bool make_act_map(CUtensorMap* tm, const void* base, int B, long long rows, int cin, int bk = kBK) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)cin, (cuuint64_t)rows, (cuuint64_t)B};
   const cuuint64_t strides[2] = {(cuuint64_t)cin * 2, (cuuint64_t)rows * (cuuint64_t)cin * 2};
-  const cuuint32_t box[3] = {(cuuint32_t)kBK, (cuuint32_t)kBM, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)kBM, 1};
   const cuuint32_t es[3] = {1, 1, 1};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// weights [N][K] bf16, box = 64 x BN
-inline bool make_weight_map(CUtensorMap* tm, const void* base, int N, int K, int BN) {
+// weights [N][K] bf16, box = bk x BN
+inline bool make_weight_map(CUtensorMap* tm, const void* base, int N, int K, int BN, int bk = kBK) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
   const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+  const cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)BN};
   const cuuint32_t es[2] = {1, 1};
   return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // v transposed [B][C][T2p] bf16, box = 64 keys x 64 channels
@@ -509,31 +526,41 @@ inline cudaError_t launch_attn(const void* q, const void* k, const void* vt, __n
 
 inline int pick_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : (N % 32 == 0 ? 32 : 0)); }
 
-// supported when every K chunk stays inside one tap and the tile shapes divide
-inline bool supported(int N, int K, int Cin) { return Cin % kBK == 0 && K % kBK == 0 && pick_bn(N) != 0; }
+// K chunk width: 64 channels (128-byte rows) when the channel count allows, else 32 (64-byte rows)
+inline int pick_bk(int Cin) { return Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 0); }
 
-template <int BN>
+// supported when every K chunk stays inside one tap and the tile shapes divide
+inline bool supported(int N, int K, int Cin) { return pick_bk(Cin) != 0 && K % Cin == 0 && pick_bn(N) != 0; }
+
+template <int BN, int BK>
 inline cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcOp& op, int B, cudaStream_t st) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN, BK>::kSmem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
   dim3 grid((unsigned)((op.M + kBM - 1) / kBM), (unsigned)(op.N / BN), (unsigned)B);
-  igemm_tc_kernel<BN><<<grid, kThreads, TileCfg<BN>::kSmem, st>>>(tmA, tmW, op);
+  igemm_tc_kernel<BN, BK><<<grid, kGemmThreads, TileCfg<BN, BK>::kSmem, st>>>(tmA, tmW, op);
   return cudaGetLastError();
 }
 
 // X: bf16 [B][Min][Cin]; W: bf16 [N][K]
 inline cudaError_t launch(const void* X, long long Min, const void* W, const TcOp& op, int B, cudaStream_t st) {
-  const int BN = pick_bn(op.N);
+  const int BN = pick_bn(op.N), BK = pick_bk(op.Cin);
   CUtensorMap tmA, tmW;
-  if (!make_act_map(&tmA, X, B, Min, op.Cin) || !make_weight_map(&tmW, W, op.N, op.K, BN)) return cudaErrorInvalidValue;
-  switch (BN) {
-    case 128: return launch_bn<128>(tmA, tmW, op, B, st);
-    case 64: return launch_bn<64>(tmA, tmW, op, B, st);
-    default: return launch_bn<32>(tmA, tmW, op, B, st);
+  if (!make_act_map(&tmA, X, B, Min, op.Cin, BK) || !make_weight_map(&tmW, W, op.N, op.K, BN, BK)) return cudaErrorInvalidValue;
+  if (BK == 64) {
+    switch (BN) {
+      case 128: return launch_bn<128, 64>(tmA, tmW, op, B, st);
+      case 64: return launch_bn<64, 64>(tmA, tmW, op, B, st);
+      default: return launch_bn<32, 64>(tmA, tmW, op, B, st);
+    }
+  }
+  switch (BN) {  // narrow layers (Cin = 32)
+    case 128: return launch_bn<128, 32>(tmA, tmW, op, B, st);
+    case 64: return launch_bn<64, 32>(tmA, tmW, op, B, st);
+    default: return launch_bn<32, 32>(tmA, tmW, op, B, st);
   }
 }
 

@@ -71,6 +71,8 @@ TC_GEMM_CASES = [
     (1, 260, 2048, 1, 1, 0, 512, 0, 2, 0),      # fc2 + LayerScale residual
     (2, 5, 512, 1, 1, 0, 2048, 0, 1, 0),        # fc1 + GELU, fewer rows than one tile
     (1, 200, 128, 3, 2, 4, 640, 128, 0, 0),     # dilation 2, N = 10 x 64
+    (1, 500, 32, 1, 1, 0, 64, 64, 3, 1),        # last ResnetBlock's k=1 conv: 32 channels -> 64-byte rows, K = 32
+    (2, 100, 32, 3, 1, 2, 128, 0, 0, 0),        # 32-channel input with taps
 ]
 
 
