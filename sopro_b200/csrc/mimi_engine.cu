@@ -243,28 +243,39 @@ __global__ void rope_kernel(float* __restrict__ qkv, const float* __restrict__ c
 
 // Tensor-core attention operands from the fp32 QKV rows [B][T2][3C]: rotated q and k as bf16 [B][T2][C], v transposed
 // as bf16 [B][C][T2p] (keys contiguous: the K-major B operand of P.V).  32 rows per block.
+template <int DH>
 __global__ void __launch_bounds__(256) rope_pack_kernel(const float* __restrict__ qkv, const float* __restrict__ cs,
                                                         __nv_bfloat16* __restrict__ qh, __nv_bfloat16* __restrict__ kh,
                                                         __nv_bfloat16* __restrict__ vt, int T2, long long T2p, int tab_T2, int C, int H) {
   extern __shared__ __nv_bfloat16 sv[];  // [32][C + 2]
+  constexpr int half = DH / 2;
   const int t0 = blockIdx.x * 32, b = blockIdx.y;
-  const int Dh = C / H, half = Dh / 2, nrot = H * half;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows = min(32, T2 - t0);
-  for (int idx = threadIdx.x; idx < rows * 2 * nrot; idx += blockDim.x) {
-    const int tt = idx / (2 * nrot), i = idx - tt * 2 * nrot;
-    const int which = i / nrot, rem = i - which * nrot;
-    const int h = rem / half, d = rem - h * half;
+  for (int tt = warp; tt < rows; tt += 8) {  // one warp per row
     const int t = t0 + tt;
-    const float* p = qkv + ((size_t)b * T2 + t) * 3 * C + which * C + h * Dh;
-    const float x1 = p[d], x2 = p[d + half];
-    const float c = cs[(size_t)t * half + d], s = cs[(size_t)(tab_T2 + t) * half + d];
-    __nv_bfloat16* o = (which ? kh : qh) + ((size_t)b * T2 + t) * C + h * Dh;
-    o[d] = __float2bfloat16_rn(x1 * c - x2 * s);
-    o[d + half] = __float2bfloat16_rn(x2 * c + x1 * s);
-  }
-  for (int idx = threadIdx.x; idx < rows * C; idx += blockDim.x) {
-    const int tt = idx / C, c = idx - tt * C;
-    sv[tt * (C + 2) + c] = __float2bfloat16_rn(qkv[((size_t)b * T2 + t0 + tt) * 3 * C + 2 * C + c]);
+    const float* row = qkv + ((size_t)b * T2 + t) * 3 * C;
+    const float* cosr = cs + (size_t)t * half;
+    const float* sinr = cs + (size_t)(tab_T2 + t) * half;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* o = (which ? kh : qh) + ((size_t)b * T2 + t) * C;
+      for (int i = lane; i < H * half; i += 32) {
+        const int h = i / half, d = i % half;
+        const float x1 = row[which * C + h * DH + d], x2 = row[which * C + h * DH + d + half];
+        const float c = cosr[d], s = sinr[d];
+        o[h * DH + d] = __float2bfloat16_rn(x1 * c - x2 * s);
+        o[h * DH + d + half] = __float2bfloat16_rn(x2 * c + x1 * s);
+      }
+    }
+    for (int c = lane * 4; c < C; c += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(row + 2 * C + c);
+      __nv_bfloat16* d = sv + tt * (C + 2) + c;
+      d[0] = __float2bfloat16_rn(v.x);
+      d[1] = __float2bfloat16_rn(v.y);
+      d[2] = __float2bfloat16_rn(v.z);
+      d[3] = __float2bfloat16_rn(v.w);
+    }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < 32 * C; idx += blockDim.x) {
@@ -730,7 +741,7 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
       __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(b1);  // b1 is idle during the transformer
       if (tc_attn) {
         // q -> h0 (the LayerNorm copy is dead), k -> h1, v^T -> h2
-        rope_pack_kernel<<<dim3((T2 + 31) / 32, B), 256, (size_t)32 * (C + 2) * 2, st>>>(b0, m->rope, h0, h1, h2, T2, T2p, m->rope_T2, C, H);
+        rope_pack_kernel<tc::kAttnDh><<<dim3((T2 + 31) / 32, B), 256, (size_t)32 * (C + 2) * 2, st>>>(b0, m->rope, h0, h1, h2, T2, T2p, m->rope_T2, C, H);
         MCK(cudaGetLastError());
         cudaError_t ae = tc::launch_attn(h0, h1, h2, att, B, T2, T2p, C, H, c.window, st);
         if (ae != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "tensor-core attention: %s", cudaGetErrorString(ae));

@@ -37,6 +37,7 @@ struct TcOp {
   __nv_bfloat16* out_bf16;  // [B][M][N] or null
   long long c_bs;      // batch stride of R / outputs (elements)
   int M, N, K, Cin, dil, pad, bias_mod, epi, out_elu;
+  int stages;          // filled in by launch()
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -121,6 +122,18 @@ __host__ __device__ constexpr uint32_t instr_desc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// 256-bit global accesses (one full 32-byte sector per thread per instruction)
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]),
+               "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, float (&v)[8]) {
+  asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+               : "l"(p));
+}
+
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 // ELU whose result is rounded to bf16 right away: exp(x) - 1 with the fast exponential is exact to well below
 // half a bf16 ulp (absolute error ~1e-7 against a result of magnitude >= |x|/2)
@@ -131,24 +144,25 @@ constexpr int kBM = 128, kBK = 64, kThreads = 192;
 constexpr int kGemmThreads = 320;  // TMA warp, MMA warp, 8 epilogue warps (2 per tensor-memory lane quarter)
 template <int BN, int BK>
 struct TileCfg {
-  static constexpr int kStages = BN >= 128 ? 3 : 4;
+  static constexpr int kMaxStages = BN >= 128 ? 3 : 4;
   static constexpr int kABytes = kBM * BK * 2;  // 16 KB at BK = 64
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmem = kStages * kStageBytes + 1024;  // + alignment slack
+  static constexpr int smem(int stages) { return stages * kStageBytes + 1024; }  // + alignment slack
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
 };
 
 template <int BN, int BK>
-__global__ void __launch_bounds__(kGemmThreads) igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(kGemmThreads, 3) igemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmW, const TcOp op) {
   using Cfg = TileCfg<BN, BK>;
-  constexpr int S = Cfg::kStages;
+  constexpr int SM = Cfg::kMaxStages;
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * S + 1];
+  __shared__ __align__(8) uint64_t bars[2 * SM + 1];
   __shared__ uint32_t tmem_slot;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[S]), accbar = smem_u32(&bars[2 * S]);
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[SM]), accbar = smem_u32(&bars[2 * SM]);
+  const int S = op.stages;  // min(kMaxStages, K chunks): short-K layers take less shared memory -> more CTAs per SM
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * BN, b = blockIdx.z;
   const int nk = op.K / BK;
@@ -237,30 +251,40 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_tc_kernel(const __grid_con
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
       } else if (op.epi == EPI_RES_SCALE || op.epi == EPI_RES) {
-        const float4* rp = reinterpret_cast<const float4*>(op.R + row + n);
+        const float* rp = op.R + row + n;
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 rv = rp[i >> 2];
-          float4 sv = make_float4(1.f, 1.f, 1.f, 1.f);
-          if (op.epi == EPI_RES_SCALE) sv = __ldg(reinterpret_cast<const float4*>(op.scale + n + i));
-          v[i] = rv.x + sv.x * v[i];
-          v[i + 1] = rv.y + sv.y * v[i + 1];
-          v[i + 2] = rv.z + sv.z * v[i + 2];
-          v[i + 3] = rv.w + sv.w * v[i + 3];
+        for (int i = 0; i < 32; i += 8) {
+          float rv[8];
+          ldg256(rp + i, rv);
+          if (op.epi == EPI_RES_SCALE) {
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(op.scale + n + i));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(op.scale + n + i + 4));
+            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[i + e] = fmaf(sv[e], v[i + e], rv[e]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[i + e] += rv[e];
+          }
         }
       }
       if (op.out_f32) {
-        float4* o = reinterpret_cast<float4*>(op.out_f32 + row + n);
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) o[i >> 2] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-      }
-      if (op.out_bf16) {
-        uint4* o = reinterpret_cast<uint4*>(op.out_bf16 + row + n);
+        float* o = op.out_f32 + row + n;
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          uint32_t pk[4];
+          uint32_t w8[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
+          for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(v[i + e]);
+          stg256(o + i, w8);
+        }
+      }
+      if (op.out_bf16) {
+        __nv_bfloat16* o = op.out_bf16 + row + n;
+#pragma unroll
+        for (int i = 0; i < 32; i += 16) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
             float a = v[i + 2 * e], c = v[i + 2 * e + 1];
             if (op.out_elu) {
               a = elu_fast(a);
@@ -269,7 +293,7 @@ __global__ void __launch_bounds__(kGemmThreads) igemm_tc_kernel(const __grid_con
             const __nv_bfloat162 h = __floats2bfloat162_rn(a, c);
             pk[e] = *reinterpret_cast<const uint32_t*>(&h);
           }
-          o[i >> 3] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          stg256(o + i, pk);
         }
       }
     }
@@ -534,14 +558,18 @@ inline bool supported(int N, int K, int Cin) { return pick_bk(Cin) != 0 && K % C
 
 template <int BN, int BK>
 inline cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcOp& op, int B, cudaStream_t st) {
+  using Cfg = TileCfg<BN, BK>;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, TileCfg<BN, BK>::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem(Cfg::kMaxStages));
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
+  TcOp o = op;
+  const int nk = op.K / BK;
+  o.stages = nk < Cfg::kMaxStages ? nk : Cfg::kMaxStages;
   dim3 grid((unsigned)((op.M + kBM - 1) / kBM), (unsigned)(op.N / BN), (unsigned)B);
-  igemm_tc_kernel<BN, BK><<<grid, kGemmThreads, TileCfg<BN, BK>::kSmem, st>>>(tmA, tmW, op);
+  igemm_tc_kernel<BN, BK><<<grid, kGemmThreads, Cfg::smem(o.stages), st>>>(tmA, tmW, o);
   return cudaGetLastError();
 }
 
