@@ -253,6 +253,10 @@ int sopro_mimi_decode_host(sopro_mimi_t* m, const int32_t* codes_host, int B, in
 #define SOPRO_MIMI_FP32 0
 #define SOPRO_MIMI_BF16_TC 1
 int sopro_mimi_set_precision(sopro_mimi_t* m, int precision);
+/* Decodes of at most 64 frames (B*T: streaming chunks, time-to-first-audio) are launch-bound (~100 kernels); they
+ * are captured once per (B, T, precision) into a CUDA graph over internal static buffers and replayed (default on).
+ * Results are identical to the plain path. */
+int sopro_mimi_set_graphs(sopro_mimi_t* m, int enabled);
 
 /* test hook: one tensor-core implicit GEMM (no reference counterpart).  X bf16 [B][rows][cin] (device),
  * W bf16 [N][taps*cin] (device); out[b][m][n] = epi(sum_j sum_ci X[b][m + j*dil - pad][ci] * W[n][j*cin+ci] +

@@ -104,6 +104,7 @@ SYMBOLS = {
     "sopro_mimi_decode": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
     "sopro_mimi_decode_host": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
     "sopro_mimi_set_precision": (_I, [_VP, _I]),
+    "sopro_mimi_set_graphs": (_I, [_VP, _I]),
     "sopro_debug_tc_gemm": (_I, [_VP, _I, C.c_int64, _I, _I, _I, _I, _VP, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
 }
 

@@ -95,6 +95,10 @@ class MimiEngine:
         _lib.check(self.lib.sopro_mimi_set_precision(self._h, self.PRECISIONS[precision]))
         self.precision = precision
 
+    def set_graphs(self, enabled: bool) -> None:
+        """CUDA-graph replay of small (<= 64 frame) decodes inside the library; on by default."""
+        _lib.check(self.lib.sopro_mimi_set_graphs(self._h, 1 if enabled else 0))
+
     def decode(self, codes_bqt: torch.Tensor) -> torch.Tensor:
         """codes [B, Q, T] (any int dtype, any device) -> wav [B, 1, T*hop] f32 on the engine's device."""
         codes = codes_bqt.to(device=self.device, dtype=torch.int32).contiguous()

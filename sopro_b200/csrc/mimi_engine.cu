@@ -481,6 +481,17 @@ struct sopro_mimi {
   size_t ws_bytes = 0;
   int* codes_dev = nullptr;
   size_t codes_cap = 0;
+  // launch-bound small decodes (streaming chunks, time-to-first-audio) are replayed from CUDA graphs captured over
+  // internal static buffers; every graph dies when the workspace or the rope table is reallocated
+  struct Replay {
+    int B, T, precision;
+    cudaGraphExec_t exec;
+  };
+  std::vector<Replay> replays;
+  int* g_codes = nullptr;   // [kGraphFrames * n_q]
+  float* g_wav = nullptr;   // [kGraphFrames * hop]
+  bool graphs = true;
+  cudaStream_t cap_stream = nullptr;
 };
 
 extern "C" {
@@ -608,6 +619,10 @@ int sopro_mimi_destroy(sopro_mimi_t* m) {
   cudaFree(m->rope);
   cudaFree(m->ws);
   cudaFree(m->codes_dev);
+  for (auto& r : m->replays) cudaGraphExecDestroy(r.exec);
+  cudaFree(m->g_codes);
+  cudaFree(m->g_wav);
+  if (m->cap_stream) cudaStreamDestroy(m->cap_stream);
   delete m;
   return SOPRO_OK;
 }
@@ -639,21 +654,25 @@ int sopro_mimi_set_precision(sopro_mimi_t* m, int precision) {
   return SOPRO_OK;
 }
 
-int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float* wav, void* stream) {
-  if (!m || !codes || !wav) return mfail(SOPRO_ERR_INVALID, "null argument");
-  if (B < 1 || T < 1) return mfail(SOPRO_ERR_INVALID, "B and T must be >= 1");
-  if (B > 65535) return mfail(SOPRO_ERR_INVALID, "B must be <= 65535");
-  MCK(cudaSetDevice(m->device));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+}  // extern "C"
+
+namespace {
+constexpr long long kGraphFrames = 64;  // decodes of at most this many frames (B*T) go through the graph cache
+
+void drop_replays(sopro_mimi* m) {
+  for (auto& r : m->replays) cudaGraphExecDestroy(r.exec);
+  m->replays.clear();
+}
+
+// Allocations and table uploads a decode of [B, T] needs; never called inside a stream capture.
+int mimi_prepare(sopro_mimi* m, int B, int T, cudaStream_t st) {
   const sopro_mimi_config_t& c = m->cfg;
-  const int C = c.hidden, T2 = 2 * T, H = c.n_heads, Dh = C / H, FF = c.ffn;
-  const float* Wd = m->dev;
-  const __nv_bfloat16* Wh = m->dev_h;
-  const bool use_tc = m->precision == SOPRO_MIMI_BF16_TC;
-  // ---- rope table
+  const int C = c.hidden, T2 = 2 * T, Dh = C / c.n_heads, FF = c.ffn;
   if (m->rope_T2 < T2) {
+    drop_replays(m);
     cudaFree(m->rope);
     m->rope = nullptr;
+    m->rope_T2 = 0;
     std::vector<float> tab((size_t)2 * T2 * (Dh / 2));
     for (int t = 0; t < T2; ++t)
       for (int d = 0; d < Dh / 2; ++d) {
@@ -667,16 +686,15 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
     MCK(cudaStreamSynchronize(st));
     m->rope_T2 = T2;
   }
-  // ---- workspace: three fp32 ping-pong buffers sized for the widest SEANet activation + transformer
-  //      scratch, the residual stream and its normalised copy; tensor-core mode adds three bf16 buffers
   long long up = 2;
   for (int i = 0; i < c.n_ratios; ++i) up *= c.ratios[i];
-  const size_t big = (size_t)B * T * up * c.num_filters;                     // [T*1920][64]
-  const size_t tr = (size_t)B * T2 * (size_t)std::max(3 * C, FF);            // QKV / MLP hidden
+  const size_t big = (size_t)B * T * up * c.num_filters;
+  const size_t tr = (size_t)B * T2 * (size_t)std::max(3 * C, FF);
   const size_t bufsz = (std::max(std::max(big, tr), (size_t)B * T2 * (c.num_filters << c.n_ratios)) + 63) / 64 * 64;
   const size_t xsz = ((size_t)B * T2 * C + 63) / 64 * 64;
-  const size_t need = (3 * bufsz + 2 * xsz) * 4 + (use_tc ? 3 * bufsz * 2 : 0);
+  const size_t need = (3 * bufsz + 2 * xsz) * 4 + 3 * bufsz * 2;
   if (m->ws_bytes < need) {
+    drop_replays(m);
     cudaFree(m->ws);
     m->ws = nullptr;
     m->ws_bytes = 0;
@@ -684,6 +702,74 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
     if (e != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "Mimi workspace %zu MB: %s", need >> 20, cudaGetErrorString(e));
     m->ws_bytes = need;
   }
+  return SOPRO_OK;
+}
+
+int mimi_enqueue(sopro_mimi* m, const int32_t* codes, int B, int T, float* wav, cudaStream_t st);
+}  // namespace
+
+extern "C" {
+
+int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float* wav, void* stream) {
+  if (!m || !codes || !wav) return mfail(SOPRO_ERR_INVALID, "null argument");
+  if (B < 1 || T < 1) return mfail(SOPRO_ERR_INVALID, "B and T must be >= 1");
+  if (B > 65535) return mfail(SOPRO_ERR_INVALID, "B must be <= 65535");
+  MCK(cudaSetDevice(m->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int rc = mimi_prepare(m, B, T, st);
+  if (rc) return rc;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  MCK(cudaStreamIsCapturing(st, &cap));
+  if (!m->graphs || (long long)B * T > kGraphFrames || cap != cudaStreamCaptureStatusNone) return mimi_enqueue(m, codes, B, T, wav, st);
+  const size_t nc = (size_t)B * m->cfg.n_q * T, nw = (size_t)B * T * (size_t)sopro_mimi_samples_per_frame(m);
+  if (!m->g_codes) {
+    MCK(cudaMalloc(&m->g_codes, (size_t)kGraphFrames * m->cfg.n_q * 4));
+    MCK(cudaMalloc(&m->g_wav, (size_t)kGraphFrames * (size_t)sopro_mimi_samples_per_frame(m) * 4));
+  }
+  cudaGraphExec_t exec = nullptr;
+  for (auto& r : m->replays)
+    if (r.B == B && r.T == T && r.precision == m->precision) exec = r.exec;
+  if (!exec) {
+    if (m->replays.size() >= 32) drop_replays(m);
+    // captured on a private stream (the caller's may be the legacy default stream, which cannot capture)
+    if (!m->cap_stream) MCK(cudaStreamCreateWithFlags(&m->cap_stream, cudaStreamNonBlocking));
+    MCK(cudaStreamBeginCapture(m->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = mimi_enqueue(m, m->g_codes, B, T, m->g_wav, m->cap_stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(m->cap_stream, &graph);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (ce != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "Mimi graph capture: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "Mimi graph instantiate: %s", cudaGetErrorString(ce));
+    m->replays.push_back({B, T, m->precision, exec});
+  }
+  MCK(cudaMemcpyAsync(m->g_codes, codes, nc * 4, cudaMemcpyDeviceToDevice, st));
+  MCK(cudaGraphLaunch(exec, st));
+  MCK(cudaMemcpyAsync(wav, m->g_wav, nw * 4, cudaMemcpyDeviceToDevice, st));
+  return SOPRO_OK;
+}
+
+}  // extern "C"
+
+namespace {
+int mimi_enqueue(sopro_mimi* m, const int32_t* codes, int B, int T, float* wav, cudaStream_t st) {
+  const sopro_mimi_config_t& c = m->cfg;
+  const int C = c.hidden, T2 = 2 * T, H = c.n_heads, Dh = C / H, FF = c.ffn;
+  const float* Wd = m->dev;
+  const __nv_bfloat16* Wh = m->dev_h;
+  const bool use_tc = m->precision == SOPRO_MIMI_BF16_TC;
+  // ---- workspace (mimi_prepare): three fp32 ping-pong buffers sized for the widest SEANet activation + transformer
+  //      scratch, the residual stream and its normalised copy, three bf16 buffers for the tensor-core operands
+  long long up = 2;
+  for (int i = 0; i < c.n_ratios; ++i) up *= c.ratios[i];
+  const size_t big = (size_t)B * T * up * c.num_filters;                     // [T*1920][64]
+  const size_t tr = (size_t)B * T2 * (size_t)std::max(3 * C, FF);            // QKV / MLP hidden
+  const size_t bufsz = (std::max(std::max(big, tr), (size_t)B * T2 * (c.num_filters << c.n_ratios)) + 63) / 64 * 64;
+  const size_t xsz = ((size_t)B * T2 * C + 63) / 64 * 64;
   float* b0 = m->ws;
   float* b1 = b0 + bufsz;
   float* b2 = b1 + bufsz;
@@ -863,6 +949,15 @@ int sopro_mimi_decode(sopro_mimi_t* m, const int32_t* codes, int B, int T, float
         curh, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
   }
   MCK(cudaGetLastError());
+  return SOPRO_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int sopro_mimi_set_graphs(sopro_mimi_t* m, int enabled) {
+  if (!m) return mfail(SOPRO_ERR_INVALID, "null argument");
+  m->graphs = enabled != 0;
   return SOPRO_OK;
 }
 

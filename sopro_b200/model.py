@@ -92,6 +92,8 @@ class SoproModel:
         self.text_pos = P.sinusoid_table(int(cfg.max_text_len) + 8, int(cfg.d_model), self.device)
         self.frame_pos = P.sinusoid_table(int(cfg.pos_emb_max) + 8, int(cfg.d_model), self.device)
         self._sessions: Dict[Tuple[int, int, int], ArSession] = {}
+        self._prep_graphs: Dict[tuple, tuple] = {}
+        self._prep_seen: Dict[tuple, int] = {}
         self._nar_cache: dict = {}
         self._nar_graphs: Dict[Tuple[int, int], tuple] = {}
         self._nar_seen: Dict[Tuple[int, int], int] = {}
@@ -123,8 +125,41 @@ class SoproModel:
     @torch.no_grad()
     def prepare_conditioning(self, text_ids_1d: torch.Tensor, ref: PreparedReference, *, max_frames: int, device=None,
                              style_strength: float = 1.2) -> Dict[str, torch.Tensor]:
-        return P.prepare_conditioning(self.sd, self.cfg, text_ids_1d, ref, max_frames=max_frames, device=self.device,
-                                      style_strength=style_strength, text_pos=self.text_pos, frame_pos=self.frame_pos)
+        """reference model.py:174-216.  ~150 small torch kernels; a (text length, max_frames, style, reference) seen
+        twice is captured into a CUDA graph and replayed (same kernels, same results)."""
+        def eager(ids):
+            return P.prepare_conditioning(self.sd, self.cfg, ids, ref, max_frames=max_frames, device=self.device,
+                                          style_strength=style_strength, text_pos=self.text_pos, frame_pos=self.frame_pos)
+
+        ids = text_ids_1d.to(self.device)
+        on_dev = ref.sv_ref.device == self.device and all(
+            (not isinstance(v, torch.Tensor)) or v.device == self.device for c in ref.ref_kv_caches for v in c.values())
+        if not self.use_cuda_graphs or not on_dev or ids.numel() == 0:
+            return eager(ids)
+        key = (int(ids.numel()), int(max_frames), float(style_strength), id(ref))
+        ent = self._prep_graphs.get(key)
+        if ent is None:
+            self._prep_seen[key] = self._prep_seen.get(key, 0) + 1
+            if self._prep_seen[key] < 2:
+                return eager(ids)
+            if len(self._prep_graphs) >= 8:
+                self._prep_graphs.pop(next(iter(self._prep_graphs)))
+            ids_in = ids.clone()
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                eager(ids_in)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = eager(ids_in)
+            ent = (graph, ids_in, out, ref)  # `ref` kept alive: the graph reads its tensors in place
+            self._prep_graphs[key] = ent
+        graph, ids_in, out, _ = ent
+        ids_in.copy_(ids)
+        graph.replay()
+        return {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
 
     @torch.no_grad()
     def nar_refine(self, cond_seq: torch.Tensor, rvq1_1xT: torch.Tensor) -> torch.Tensor:

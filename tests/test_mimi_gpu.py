@@ -133,6 +133,21 @@ def test_host_buffer_path_and_stream_decoder(precision):
     np.testing.assert_allclose(got[0], full[0, 0], rtol=0, atol=1e-5 * max(1.0, float(np.abs(full).max())))
 
 
+def test_small_decodes_replay_from_graphs_identically():
+    """<= 64 frames go through the library's CUDA-graph cache: first call captures, later calls replay; both equal the
+    plain launches bit for bit, also after a large decode reallocated the workspace (graphs are dropped then)."""
+    eng, _ = _engine("bf16_tc")
+    codes = torch.randint(0, 2048, (2, 32, 7), generator=torch.Generator().manual_seed(9))
+    other = torch.randint(0, 2048, (2, 32, 7), generator=torch.Generator().manual_seed(10))
+    eng.set_graphs(False)
+    want, want_other = eng.decode(codes).cpu(), eng.decode(other).cpu()
+    eng.set_graphs(True)
+    assert torch.equal(eng.decode(codes).cpu(), want)        # capture + first replay
+    assert torch.equal(eng.decode(other).cpu(), want_other)  # replay with new inputs
+    eng.decode(torch.randint(0, 2048, (4, 32, 120)))         # grows the workspace
+    assert torch.equal(eng.decode(codes).cpu(), want)
+
+
 def test_decode_full_signature():
     from sopro_b200.codec import MimiCodec
 
