@@ -226,10 +226,15 @@ def extras(cfg, dev):
     # Mimi standalone: 25 x 400 = 10k frames
     codes = torch.randint(0, 2048, (25, 32, 400), generator=torch.Generator().manual_seed(5)).to(dev)
     t, _ = timed(lambda: tts.codec.engine.decode(codes), 3, warm=1)
+    out["mimi_precision"] = tts.codec.engine.precision  # bf16 operands on tcgen05, fp32 accumulate (default mode)
     out["mimi_frames_per_sec"] = 10000 / t
     out["mimi_ms_per_10k_frames"] = t * 1e3
-    out["mimi_alg_gb_per_s"] = 10000 * 7936 / t / 1e9
-    out["mimi_tflops_fp32"] = 10000 * 431.2e6 / t / 1e12
+    out["mimi_alg_gb_per_s"] = 10000 * 7936 / t / 1e9  # codes in + waveform out only
+    out["mimi_tflops"] = 10000 * 431.2e6 / t / 1e12     # dense-block FLOPs of one frame: 431.2 MFLOP
+    tts.codec.engine.set_precision("fp32")
+    t32, _ = timed(lambda: tts.codec.engine.decode(codes), 1, warm=1)
+    tts.codec.engine.set_precision("bf16_tc")
+    out["mimi_fp32_mode_ms_per_10k_frames"] = t32 * 1e3
     return out
 
 
