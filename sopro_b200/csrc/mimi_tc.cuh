@@ -531,13 +531,21 @@ inline bool make_vt_map(CUtensorMap* tm, const void* base, int B, int C, long lo
 inline bool attn_supported(int C, int H, int window) { return H > 0 && C == H * kAttnDh && window >= 1 && window <= kAttnKeys - 127; }
 
 // q, k: bf16 [B][T2][C] (rotated); vt: bf16 [B][C][T2p]; out: bf16 [B][T2][C]
+// the dynamic shared-memory opt-in is a per-device function attribute: remember it per device
+inline bool attr_needed(unsigned long long& done_mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+  if (done_mask >> dev & 1ull) return false;
+  done_mask |= 1ull << dev;
+  return true;
+}
+
 inline cudaError_t launch_attn(const void* q, const void* k, const void* vt, __nv_bfloat16* out, int B, int T2, long long T2p, int C,
                                int H, int window, cudaStream_t st) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;
+  if (attr_needed(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   CUtensorMap tmQ, tmK, tmV;
   if (!make_act_map(&tmQ, q, B, T2, C) || !make_act_map(&tmK, k, B, T2, C) || !make_vt_map(&tmV, vt, B, C, T2, T2p))
@@ -559,11 +567,10 @@ inline bool supported(int N, int K, int Cin) { return pick_bk(Cin) != 0 && K % C
 template <int BN, int BK>
 inline cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, const TcOp& op, int B, cudaStream_t st) {
   using Cfg = TileCfg<BN, BK>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_done = 0;
+  if (attr_needed(attr_done)) {
     cudaError_t e = cudaFuncSetAttribute(igemm_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem(Cfg::kMaxStages));
     if (e != cudaSuccess) return e;
-    attr_done = true;
   }
   TcOp o = op;
   const int nk = op.K / BK;
