@@ -23,6 +23,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -918,6 +919,25 @@ int mimi_enqueue(sopro_mimi* m, const int32_t* codes, int B, int T, float* wav, 
     }
     Tn *= S.ratio;
     const bool ha_valid = t_ok && r1_ok;
+    // ResnetBlock in one launch when the geometry allows (hidden activation stays on chip), else conv by conv
+    static const bool fuse_res = !(getenv("SOPRO_MIMI_FUSE_RES") && atoi(getenv("SOPRO_MIMI_FUSE_RES")) == 0);
+    if (fuse_res && ha_valid && r2_ok && tc::resblock_supported(hid, S.cout) && (S.cout * c.res_kernel) % 64 == 0) {
+      tc::ResOp ro{};
+      ro.bias1 = Wd + S.r1b;
+      ro.bias2 = Wd + S.r2b;
+      ro.Z = b1;
+      ro.out_f32 = next_tc ? nullptr : b0;
+      ro.out_bf16 = next_tc ? curh : nullptr;
+      ro.M = (int)Tn;
+      ro.taps = c.res_kernel;
+      ro.pad = c.res_kernel - 1;
+      ro.out_elu = 1;
+      cudaError_t fe = tc::launch_resblock(ha, Wh + S.r1w_h, Wh + S.r2w_h, hid, ro, B, st);
+      if (fe != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "fused ResnetBlock (stage %zu): %s", si, cudaGetErrorString(fe));
+      cur32 = next_tc ? nullptr : b0;
+      ch = S.cout;
+      continue;
+    }
     // res conv k=3 -> ELU(h) bf16 (hb) for a tensor-core res2, else raw h fp32 (b2)
     if (ha_valid) {
       if ((rc = tcg(ha, Tn, S.cout, c.res_kernel, c.res_kernel - 1, Wh + S.r1w_h, Wd + S.r1b, hid, hid, tc::EPI_NONE, nullptr, nullptr,

@@ -307,6 +307,218 @@ __global__ void __launch_bounds__(kGemmThreads, 3) igemm_tc_kernel(const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused ResnetBlock (MimiResnetBlock, modeling_mimi.py:437-451): out = z + conv1x1(ELU(conv3(ELU(z)))).
+//   GEMM 1: h[128 x HID] = conv k=3 of the bf16 ELU(z) rows (3-D TMA boxes per tap), accumulators in tensor
+//           memory columns [0, HID)
+//   epilogue A: + bias, ELU, round to bf16, written swizzled into shared memory as the next A operand
+//   GEMM 2: [128 x 2*HID] = h . W2^T (W2 loaded once per CTA) into columns [HID, 3*HID)
+//   epilogue B: + bias + z (fp32 skip, read once), then fp32 and/or bf16(ELU) out
+// The hidden activation never touches HBM and one launch replaces two.  HID in {32, 64, 128}.
+// ---------------------------------------------------------------------------------------------
+struct ResOp {
+  const float* bias1;  // [HID]
+  const float* bias2;  // [2*HID]
+  const float* Z;      // fp32 skip [B][M][2*HID]
+  float* out_f32;      // [B][M][2*HID] or null
+  __nv_bfloat16* out_bf16;  // [B][M][2*HID] or null, through ELU when out_elu
+  int M, taps, pad, out_elu, stages;
+};
+
+template <int HID>
+struct ResCfg {
+  static constexpr int kCout = 2 * HID;
+  static constexpr int kBKH = HID < 64 ? HID : 64;       // K chunk of the second GEMM
+  static constexpr int kNK2 = HID / kBKH;
+  static constexpr int kMaxStages = 3;
+  static constexpr int kABytes = kBM * kBK * 2;           // 16 KB
+  static constexpr int kBBytes = HID * kBK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kHBytes = kBM * HID * 2;           // hidden activation as the A operand of GEMM 2
+  static constexpr int kW2Bytes = kCout * HID * 2;
+  static constexpr int kTmemCols = 3 * HID <= 128 ? 128 : (3 * HID <= 256 ? 256 : 512);
+  static constexpr int smem(int stages) { return stages * kStageBytes + kHBytes + kW2Bytes + 1024; }
+};
+
+template <int HID>
+__global__ void __launch_bounds__(kGemmThreads, HID <= 32 ? 3 : (HID <= 64 ? 2 : 1)) resblock_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                                     const __grid_constant__ CUtensorMap tmW1,
+                                                                                     const __grid_constant__ CUtensorMap tmW2,
+                                                                                     const ResOp op) {
+  using Cfg = ResCfg<HID>;
+  constexpr int SM = Cfg::kMaxStages, COUT = Cfg::kCout, BKH = Cfg::kBKH;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * SM + 4];
+  __shared__ uint32_t tmem_slot;
+  const int S = op.stages;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sH = tiles + S * Cfg::kStageBytes, sW2 = sH + Cfg::kHBytes;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[SM]);
+  const uint32_t w2_full = smem_u32(&bars[2 * SM]), acc1 = smem_u32(&bars[2 * SM + 1]), h_ready = smem_u32(&bars[2 * SM + 2]),
+                 acc2 = smem_u32(&bars[2 * SM + 3]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kBM, b = blockIdx.y;
+  const int nk = op.taps * COUT / kBK;  // K chunks of GEMM 1 (COUT is a multiple of 64)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(w2_full, 1);
+    mbar_init(acc1, 1);
+    mbar_init(h_ready, kGemmThreads - 64);
+    mbar_init(acc2, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w2_full, Cfg::kW2Bytes);
+      for (int c = 0; c < Cfg::kNK2; ++c) tma_load_2d(sW2 + c * (COUT * BKH * 2), &tmW2, w2_full, c * BKH, 0);
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (uint32_t)(kc / S) & 1u;
+        mbar_wait(empty0 + 8 * s, ph ^ 1u);
+        mbar_expect_tx(full0 + 8 * s, Cfg::kStageBytes);
+        const int k0 = kc * kBK;
+        const int j = k0 / COUT, ci = k0 - j * COUT;
+        const uint32_t sa = tiles + s * Cfg::kStageBytes;
+        tma_load_3d(sa, &tmA, full0 + 8 * s, ci, m0 + j - op.pad, b);
+        tma_load_2d(sa + Cfg::kABytes, &tmW1, full0 + 8 * s, k0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int kc = 0; kc < nk; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (uint32_t)(kc / S) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = tiles + s * Cfg::kStageBytes;
+        const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + Cfg::kABytes);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) tc_mma_bf16(tmem, da + 2 * k, db + 2 * k, instr_desc_bf16(kBM, HID), (kc | k) != 0);
+        tc_commit(empty0 + 8 * s);
+      }
+      tc_commit(acc1);
+      mbar_wait(w2_full, 0);
+      mbar_wait(h_ready, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < Cfg::kNK2; ++c) {
+        const uint64_t dh = smem_desc_k<BKH>(sH + c * (kBM * BKH * 2)), dw = smem_desc_k<BKH>(sW2 + c * (COUT * BKH * 2));
+#pragma unroll
+        for (int k = 0; k < BKH / 16; ++k) tc_mma_bf16(tmem + HID, dh + 2 * k, dw + 2 * k, instr_desc_bf16(kBM, COUT), (c | k) != 0);
+      }
+      tc_commit(acc2);
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int r = 32 * q + lane;  // tile row == tensor-memory lane
+    const int m = m0 + r;
+    const bool row_ok = m < op.M;
+    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16);
+    // ---- epilogue A: hidden activation -> shared memory (bf16, swizzled K-major rows of BKH elements)
+    mbar_wait(acc1, 0);
+    tc_fence_after();
+    constexpr int kColsA = HID >= 64 ? HID / 2 : HID;
+    const int abeg = HID >= 64 ? half * kColsA : half * HID;
+#pragma unroll 1
+    for (int c0 = abeg; c0 < abeg + kColsA && c0 < HID; c0 += 32) {
+      uint32_t v[32];
+      tc_ld32(trow + (uint32_t)c0, v);
+      uint32_t pk[16];
+#pragma unroll
+      for (int e = 0; e < 32; e += 4) {
+        const float4 bv = __ldg(reinterpret_cast<const float4*>(op.bias1 + c0 + e));
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(elu_fast(__uint_as_float(v[e]) + bv.x), elu_fast(__uint_as_float(v[e + 1]) + bv.y));
+        const __nv_bfloat162 h1 = __floats2bfloat162_rn(elu_fast(__uint_as_float(v[e + 2]) + bv.z), elu_fast(__uint_as_float(v[e + 3]) + bv.w));
+        pk[e >> 1] = *reinterpret_cast<const uint32_t*>(&h0);
+        pk[(e >> 1) + 1] = *reinterpret_cast<const uint32_t*>(&h1);
+      }
+      // 32 columns = 4 sixteen-byte chunks of row r inside K chunk c0 / BKH; chunk index XOR row bits (swizzle)
+      const uint32_t blk = sH + (uint32_t)(c0 / BKH) * (kBM * BKH * 2) + (uint32_t)r * (BKH * 2);
+      const int ch0 = (c0 % BKH) >> 3;
+      const int sw = BKH == 64 ? (r & 7) : ((r >> 1) & 3);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const uint32_t a = blk + (uint32_t)(((ch0 + cc) ^ sw) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(pk[4 * cc]), "r"(pk[4 * cc + 1]), "r"(pk[4 * cc + 2]),
+                     "r"(pk[4 * cc + 3])
+                     : "memory");
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(h_ready) : "memory");
+    // ---- epilogue B: + bias + skip, outputs
+    mbar_wait(acc2, 0);
+    tc_fence_after();
+    const size_t row = ((size_t)b * (size_t)op.M + (size_t)(row_ok ? m : 0)) * COUT;
+    constexpr int kColsB = COUT / 2;
+#pragma unroll 1
+    for (int c0 = half * kColsB; c0 < (half + 1) * kColsB; c0 += 32) {
+      uint32_t rr[32];
+      tc_ld32(trow + (uint32_t)(HID + c0), rr);
+      if (!row_ok) continue;
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        float zv[8];
+        ldg256(op.Z + row + c0 + i, zv);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(op.bias2 + c0 + i));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(op.bias2 + c0 + i + 4));
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i + e] = zv[e] + (__uint_as_float(rr[i + e]) + bb[e]);
+      }
+      if (op.out_f32) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          uint32_t w8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) w8[e] = __float_as_uint(v[i + e]);
+          stg256(op.out_f32 + row + c0 + i, w8);
+        }
+      }
+      if (op.out_bf16) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 16) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float a = v[i + 2 * e], c = v[i + 2 * e + 1];
+            if (op.out_elu) {
+              a = elu_fast(a);
+              c = elu_fast(c);
+            }
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(a, c);
+            pk[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+          stg256(op.out_bf16 + row + c0 + i, pk);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)Cfg::kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Causal sliding-window attention on the tensor cores (MimiAttention.forward, modeling_mimi.py:681-738,
 // head_dim 64, window <= 257).  One CTA = 128 queries of one (batch, head):
 //   S = Q K^T over the 384 keys [q0-256, q0+128) -> 384 fp32 columns of tensor memory (3 x M128 N128 K64)
@@ -557,6 +769,36 @@ inline cudaError_t launch_attn(const void* q, const void* k, const void* vt, __n
 }
 
 inline int pick_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : (N % 32 == 0 ? 32 : 0)); }
+
+// ---- fused ResnetBlock launcher.  X: bf16 ELU(z) [B][M][2*hid]; W1: bf16 [hid][taps*2*hid]; W2: bf16 [2*hid][hid]
+inline bool resblock_supported(int hid, int cout) { return cout == 2 * hid && (hid == 32 || hid == 64 || hid == 128); }
+
+template <int HID>
+inline cudaError_t launch_resblock_t(const void* X, const void* W1, const void* W2, ResOp op, int B, cudaStream_t st) {
+  using Cfg = ResCfg<HID>;
+  static unsigned long long attr_done = 0;
+  if (attr_needed(attr_done)) {
+    cudaError_t e = cudaFuncSetAttribute(resblock_tc_kernel<HID>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::smem(Cfg::kMaxStages));
+    if (e != cudaSuccess) return e;
+  }
+  const int cout = Cfg::kCout, K1 = op.taps * cout, nk = K1 / kBK;
+  op.stages = nk < Cfg::kMaxStages ? nk : Cfg::kMaxStages;
+  CUtensorMap tmA, tmW1, tmW2;
+  if (!make_act_map(&tmA, X, B, op.M, cout) || !make_weight_map(&tmW1, W1, HID, K1, HID) ||
+      !make_weight_map(&tmW2, W2, cout, HID, cout, Cfg::kBKH))
+    return cudaErrorInvalidValue;
+  dim3 grid((unsigned)((op.M + kBM - 1) / kBM), (unsigned)B);
+  resblock_tc_kernel<HID><<<grid, kGemmThreads, Cfg::smem(op.stages), st>>>(tmA, tmW1, tmW2, op);
+  return cudaGetLastError();
+}
+
+inline cudaError_t launch_resblock(const void* X, const void* W1, const void* W2, int hid, const ResOp& op, int B, cudaStream_t st) {
+  switch (hid) {
+    case 32: return launch_resblock_t<32>(X, W1, W2, op, B, st);
+    case 64: return launch_resblock_t<64>(X, W1, W2, op, B, st);
+    default: return launch_resblock_t<128>(X, W1, W2, op, B, st);
+  }
+}
 
 // K chunk width: 64 channels (128-byte rows) when the channel count allows, else 32 (64-byte rows)
 inline int pick_bk(int Cin) { return Cin % 64 == 0 ? 64 : (Cin % 32 == 0 ? 32 : 0); }
