@@ -24,6 +24,7 @@
 
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 
 namespace tc {
 
@@ -817,6 +818,8 @@ inline cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, con
   TcOp o = op;
   const int nk = op.K / BK;
   o.stages = nk < Cfg::kMaxStages ? nk : Cfg::kMaxStages;
+  // short-K layers are bound by their epilogues: two stages leave room for a third resident CTA per SM
+  if (nk <= 4 && o.stages > 2) o.stages = 2;
   dim3 grid((unsigned)((op.M + kBM - 1) / kBM), (unsigned)(op.N / BN), (unsigned)B);
   igemm_tc_kernel<BN, BK><<<grid, kGemmThreads, Cfg::smem(o.stages), st>>>(tmA, tmW, o);
   return cudaGetLastError();
