@@ -402,9 +402,10 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": t_total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 math / bf16 weight storage", "data": "synthetic", "config": config,
         "e2e": {"value": e2e_value, "unit": "frames/s",
-                "h2d_bytes_per_step": int(cond_h.numel() * 4 + txt_h.numel() * 4 + noise_h.numel() * 4),
-                "d2h_bytes_per_step": int(toks_h.nbytes + n_h.nbytes)},
-        "gpu_launches": 2 * args.steps * 2,  # (kv_build + ar_persistent) per pass, resident + e2e legs
+                # whole job: every rank copies its own shard's inputs in and its token ids out
+                "h2d_bytes_per_step": int(cond_h.numel() * 4 + txt_h.numel() * 4 + noise_h.numel() * 4) * max(world, 1),
+                "d2h_bytes_per_step": int(toks_h.nbytes + n_h.nbytes) * max(world, 1)},
+        "gpu_launches": 2 * args.steps * 2 * max(world, 1),  # (kv_build + ar_persistent) per pass, resident + e2e legs, per rank
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "ar_persistent_kernel<bf16>", "ms_per_launch": t_kernel_ms,
                      "alg_bytes_per_launch": alg_bytes_launch, "peak_source": peak_src,
