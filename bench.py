@@ -393,10 +393,13 @@ def main():
     alg_bytes_launch = (w_step + B * S_UTT_BYTES) * STEPS_AR
     achieved = alg_bytes_launch / (t_kernel_ms / 1e3) / 1e9
     traffic = None
+    ncu_note = None
     tp = os.path.join(ROOT, "profiles", "ar_kernel_traffic.json")
     if os.path.exists(tp):
         with open(tp) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            tj = json.load(f)
+        traffic = tj.get("dram_bytes_per_launch")
+        ncu_note = tj.get("ncu")
     line = {
         "metric": "ar_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": max(world, 1), "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -410,7 +413,9 @@ def main():
                      "traffic": traffic, "kernel": "ar_persistent_kernel<bf16>", "ms_per_launch": t_kernel_ms,
                      "alg_bytes_per_launch": alg_bytes_launch, "peak_source": peak_src,
                      "note": "algorithmic bytes = (W_step + B*3280) per AR step x 401 steps (SURVEY.md §8d); W_step is L2-resident "
-                             "after the first step, so DRAM traffic is far below this"},
+                             "after the first step, so DRAM traffic is far below this",
+                     # last committed ncu --set full capture of this kernel (not measured in this run)
+                     "ncu_capture": ncu_note},
         "clocks": clocks.summary(),
         "extra": {"us_per_ar_step": t_kernel_ms / STEPS_AR * 1e3, "frames_per_pass_per_gpu": frames_per_pass},
     }
