@@ -686,7 +686,7 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.Bt = Bt;
   p.t_begin = t_begin;
   p.t_end = t_end;
-  const size_t need_act = std::max((size_t)Bt * e->F * 4, (size_t)2 * Bt * e->D * 4 + (size_t)kWarps * 8 * e->KcP * 4);
+  const size_t need_act = std::max((size_t)Bt * e->F * 4, (size_t)2 * Bt * e->D * 4 + (size_t)kWarps * kTapSlots * e->KcP * 4);
   const int att_lc = std::min(128, s->Lmax);
   const size_t need_att_long = ((size_t)s->Lmax + (size_t)kWarps * e->Dh + (size_t)kWarps * 8 * e->Dh) * 4;
   const size_t need_att_fast = ((size_t)e->Dh + att_lc + (size_t)16 * e->Dh + (size_t)2 * att_lc * e->Dh) * 4;

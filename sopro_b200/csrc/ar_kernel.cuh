@@ -37,6 +37,7 @@ constexpr int kMaxTopK = 64;
 constexpr int kCand = 128;  // candidate slots of the sampler's top-k
 constexpr int kMaxUttPerTeam = 32;
 constexpr int kMaxVocab = 8 * kThreads;
+constexpr int kTapSlots = 16;     // dwconv tap rows staged per warp in the GLU stage (channels per task x utterances)
 constexpr int kTimingSlots = 224;  // [0,160) stage stamps, [160,192) sampler phases, [192,224) attention phases
 constexpr int kMaxStages = 6 * kMaxLayers + 2;
 constexpr int kMaxTilesPerStep = 256;
@@ -1522,7 +1523,9 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
             // operands of the epilogue are requested before the K loop: their latency hides under it
             float res_v = 0.f;
             float* rb = nullptr;
-            const unsigned tap_w = scratch_s + (unsigned)warp * (unsigned)(8 * p.KcP * 4) + (unsigned)uu * (unsigned)(p.KcP * 4);
+            // one tap row per (channel of the task, utterance): kTapSlots = 16 rows per warp (RC <= 2 channels x TU <= 8)
+            const unsigned tap_w = scratch_s + (unsigned)warp * (unsigned)(kTapSlots * p.KcP * 4) +
+                                   (unsigned)((i % RC) * TU + uu) * (unsigned)(p.KcP * 4);
             if (glu) {
               // conv state row of (utterance, channel, phase): [KcP] floats, see DESIGN.md §2
               rb = state + (((size_t)b * D + (mine ? r : td->row0)) * dil + phase) * p.KcP;

@@ -48,6 +48,28 @@ def test_decode_tensor_core_mode(B, T):
     assert float(err.pow(2).mean().sqrt()) <= 1e-2 * float(want.pow(2).mean().sqrt())
 
 
+def test_full_size_decode_properties():
+    """BASELINE.json's standalone configuration (10k frames) through size-independent properties: the decoder is
+    causal, so the first 300 frames of the 10k-frame waveform equal a 300-frame decode bit for bit (same kernels, other
+    grid sizes); the tensor-core result stays within the stated tolerance of the fp32 mode at full size; a batch of 25
+    x 400 frames equals the same utterances decoded one by one."""
+    eng, _ = _engine("bf16_tc")
+    codes = torch.randint(0, 2048, (1, 32, 10000), generator=torch.Generator().manual_seed(5))
+    big = eng.decode(codes)
+    assert big.shape == (1, 1, 10000 * 1920) and bool(torch.isfinite(big).all())
+    small = eng.decode(codes[:, :, :300])
+    assert torch.equal(big[..., : 300 * 1920], small)
+    eng.set_precision("fp32")
+    ref32 = eng.decode(codes[:, :, :2000])
+    eng.set_precision("bf16_tc")
+    err = (big[..., : 2000 * 1920] - ref32).abs().max()
+    assert float(err) <= 2e-2 * float(ref32.abs().max())
+    batch = codes.view(1, 32, 25, 400).permute(2, 1, 0, 3).reshape(25, 32, 400).contiguous()
+    wb = eng.decode(batch)
+    for i in (0, 11, 24):
+        assert torch.equal(wb[i: i + 1], eng.decode(batch[i: i + 1]))
+
+
 def _im2col(x, taps, dil, pad):
     B, R, Cin = x.shape
     cols = []
