@@ -158,6 +158,26 @@ def test_teams_of_eight_utterances_match_the_oracle(n_utts):
     assert not bad, f"utterances {bad} differ from the oracle"
 
 
+def test_teams_of_sixteen_utterances_barrier_mode():
+    """Non-default geometry (sopro_ar_session_set_team(16)): two 8-utterance groups per team, team barrier instead of
+    the LL exchange."""
+    spec = AR_CASES["peaked_fp32"]
+    cfg, sd, _ = ar_case_inputs(spec)
+    eng = _engine(cfg, sd, "fp32", _wkey(spec))
+    lens = [52, 7, 23, 33, 1, 12, 5, 40, 17, 9, 52, 3, 28, 44, 2, 36, 11, 6, 50]
+    n, steps = len(lens), 16
+    cond, txt, tapes = _batch_inputs(cfg, n, steps, lens)
+    samp = O.ArSampling(min_gen_frames=10 ** 9)
+    want = _oracle_batch(sd, cfg, cond, txt, tapes, lens, samp, steps)
+    ses = eng.session(n, steps, max(lens))
+    ses.set_team(16)
+    ses.begin(cond, txt, lens, tapes[:, :, :50].contiguous(), _sampling(samp, cfg))
+    ses.run()
+    toks, nn, done = ses.read()
+    bad = [i for i in range(n) if toks[i, : nn[i]].tolist() != want[i]]
+    assert not bad, f"utterances {bad} differ from the oracle"
+
+
 @pytest.mark.parametrize("team", [0, 1, 2, 3])
 def test_batch_equals_each_utterance_alone(team):
     """Utterance i of a ragged batch == the oracle run alone on utterance i,
