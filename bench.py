@@ -424,7 +424,10 @@ def main():
             line["extra"].update(extras(cfg, dev))
         except Exception as ex:  # the headline number must survive a failure in the side measurements
             line["extra"]["extras_error"] = repr(ex)
-    if not args.no_cpu_baseline:
+    if world > 1:  # the CPU baseline is measured at N=1 only (it does not depend on N)
+        line["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": None, "kind": "port",
+                                "sample": "measured on rank 0 at N=1 only"}
+    elif not args.no_cpu_baseline:
         threads, avail = pick_threads(cfg, sd)
         v, dt = cpu_reference_sample(cfg, sd, 16, threads)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": threads, "cores_available": avail, "kind": "port",
