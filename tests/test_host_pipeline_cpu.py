@@ -182,3 +182,33 @@ def test_stream_decoder_is_prefix_exact_through_the_codec_interface(tts):
         parts.append(w)
     np.testing.assert_allclose(torch.cat(parts, dim=1).numpy(), full.reshape(1, -1).numpy(), rtol=0, atol=1e-6)
     assert state.frames_seen == 9 and state.samples_emitted == 9 * 1920
+
+
+def test_stream_nar_windows_follow_the_reference(tts, monkeypatch):
+    """reference streaming.py:80-104: every chunk_frames tokens the NAR refiner sees the new frames plus
+    nar_context_frames of left context, and only the new frames' codes go to the Mimi stream decoder."""
+    seen = []
+    real = tts.model.nar_refine
+
+    def spy(cond, rvq1):
+        seen.append((int(cond.shape[1]), rvq1[0].tolist()))
+        return real(cond, rvq1)
+
+    monkeypatch.setattr(tts.model, "nar_refine", spy)
+    prep = tts.model.prepare_conditioning(tts.encode_text(TEXTS[1]), tts.ref, max_frames=KW["max_frames"],
+                                          style_strength=tts.cfg.style_strength)
+    toks = []
+    for _t, tok, is_eos in tts.model.ar_stream(prep, seed=2, **KW):
+        if is_eos:
+            break
+        toks.append(tok)
+    chunks = list(tts.stream(TEXTS[1], ref=tts.ref, seed=2, chunk_frames=4, nar_context_frames=3, **KW))
+    T, cf, ctx = len(toks), 4, 3
+    ends = list(range(cf, T + 1, cf)) + ([T] if T % cf else [])
+    want, emitted = [], 0
+    for e in ends:
+        lo = max(0, emitted - ctx)
+        want.append((e - lo, toks[lo:e]))
+        emitted = e
+    assert seen == want
+    assert sum(c.shape[1] for c in chunks) == T * 1920
