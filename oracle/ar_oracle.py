@@ -17,8 +17,7 @@ re-checks anywhere (see DESIGN.md "Oracle").
 """
 from __future__ import annotations
 
-import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
 import torch

@@ -13,9 +13,8 @@ additionally accepts ``seed=`` / ``generator=`` (an extension) to leave the glob
 from __future__ import annotations
 
 import os
-from typing import Dict, Iterator, List, Optional, Sequence, Tuple, Union
+from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
-import numpy as np
 import torch
 
 from . import prefill as P

@@ -6,7 +6,7 @@ rebuilds identical bytes."""
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Tuple
+from typing import Dict, List
 
 import numpy as np
 import torch

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import ar_oracle as O
-from tests.cases import AR_CASES, _unit, ar_case_inputs, ar_weights
+from tests.cases import AR_CASES, _unit, ar_case_inputs
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")

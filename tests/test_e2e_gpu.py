@@ -1,7 +1,6 @@
 """GPU: the public API end to end (prefill -> persistent AR kernel -> NAR -> CUDA Mimi) against the oracles."""
 import io
 
-import numpy as np
 import pytest
 import torch
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from tests.cases import E2E_CASE, e2e_inputs
+from tests.cases import e2e_inputs
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")

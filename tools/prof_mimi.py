@@ -1,5 +1,5 @@
 """Tiny driver for ncu / timing: Mimi decode of T random code frames.  usage: prof_mimi.py T [precision] [B] [reps]"""
-import os, sys, time
+import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
