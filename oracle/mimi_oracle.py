@@ -126,3 +126,58 @@ def mimi_decode(sd: SD, codes_bqt: Tensor) -> Tensor:
 
 
 from sopro_b200.weights import synth_mimi_state_dict  # noqa: E402,F401  (seeded random decode-path weights)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# A model of the PRODUCT's tensor-core mode (not of the reference): the same decode with operands rounded to bf16
+# exactly where sopro_b200/csrc/mimi_tc.cuh rounds them (weights of every contraction, the activation feeding every
+# contraction — after ELU where the layer wants ELU —, q / k / v, the softmax probabilities and the attention output),
+# fp32 accumulation and fp32 residual streams everywhere else.  It exists so that the tensor-core kernels can be held to
+# a tolerance far tighter than "2e-2 of the fp32 result": what remains between this restatement and the GPU is
+# accumulation order and rare one-ulp bf16 rounding flips.  Test infrastructure only.
+# ---------------------------------------------------------------------------------------------------------------
+def _bf(x: Tensor) -> Tensor:
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def transformer_bf16_operands(sd: SD, x: Tensor, n_layers: int = 8, n_heads: int = 8, window: int = 250, eps: float = 1e-5) -> Tensor:
+    B, T, C = x.shape
+    Dh = C // n_heads
+    i = torch.arange(T)
+    allowed = (i[None, :] <= i[:, None]) & (i[:, None] - i[None, :] < window)
+    for l in range(n_layers):
+        p = f"decoder_transformer.layers.{l}."
+        h = _bf(F.layer_norm(x, (C,), sd[p + "input_layernorm.weight"], sd[p + "input_layernorm.bias"], eps))
+        sp = lambda t: t.view(B, T, n_heads, Dh).transpose(1, 2)  # noqa: E731
+        q, k, v = (sp(F.linear(h, _bf(sd[p + f"self_attn.{n}_proj.weight"]))) for n in ("q", "k", "v"))
+        q, k = rope(q, k)
+        q, k, v = _bf(q), _bf(k), _bf(v)
+        s = torch.matmul(q, k.transpose(2, 3)) * (1.0 / math.sqrt(Dh))
+        s = s.masked_fill(~allowed, float("-inf"))
+        pr = _bf(torch.exp(s - s.amax(dim=-1, keepdim=True)))  # probabilities are rounded BEFORE they are summed
+        a = torch.matmul(pr, v) / pr.sum(dim=-1, keepdim=True)
+        a = _bf(a).transpose(1, 2).contiguous().view(B, T, C)
+        x = x + sd[p + "self_attn_layer_scale.scale"] * F.linear(a, _bf(sd[p + "self_attn.o_proj.weight"]))
+        h = _bf(F.layer_norm(x, (C,), sd[p + "post_attention_layernorm.weight"], sd[p + "post_attention_layernorm.bias"], eps))
+        h = _bf(F.gelu(F.linear(h, _bf(sd[p + "mlp.fc1.weight"]))))
+        x = x + sd[p + "mlp_layer_scale.scale"] * F.linear(h, _bf(sd[p + "mlp.fc2.weight"]))
+    return x
+
+
+def seanet_decoder_bf16_operands(sd: SD, x: Tensor) -> Tensor:
+    a = _bf(F.elu(conv1d_causal(_bf(x), _bf(sd["decoder.layers.0.conv.weight"]), sd["decoder.layers.0.conv.bias"])))
+    li = 1
+    for r in UPSAMPLING_RATIOS:
+        z = conv_transpose_causal(a, _bf(sd[f"decoder.layers.{li + 1}.conv.weight"]), sd[f"decoder.layers.{li + 1}.conv.bias"], r)
+        p = f"decoder.layers.{li + 2}.block."
+        h = _bf(F.elu(conv1d_causal(_bf(F.elu(z)), _bf(sd[p + "1.conv.weight"]), sd[p + "1.conv.bias"])))
+        a = _bf(F.elu(z + conv1d_causal(h, _bf(sd[p + "3.conv.weight"]), sd[p + "3.conv.bias"])))  # fp32 skip, bf16 operand out
+        li += 3
+    # the final conv keeps its fp32 weights; its input is the bf16 ELU'd activation above
+    return conv1d_causal(a, sd[f"decoder.layers.{li + 1}.conv.weight"], sd[f"decoder.layers.{li + 1}.conv.bias"])
+
+
+def mimi_decode_bf16_operands(sd: SD, codes_bqt: Tensor) -> Tensor:
+    x = upsample(sd, rvq_decode(sd, codes_bqt))  # fp32 in both modes of the product
+    x = transformer_bf16_operands(sd, x)
+    return seanet_decoder_bf16_operands(sd, x).transpose(1, 2)

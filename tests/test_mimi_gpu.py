@@ -46,6 +46,13 @@ def test_decode_tensor_core_mode(B, T):
     err = got - want
     assert float(err.abs().max()) <= 2e-2 * peak, (float(err.abs().max()), peak)
     assert float(err.pow(2).mean().sqrt()) <= 1e-2 * float(want.pow(2).mean().sqrt())
+    # against the bf16-operand model of this mode (oracle/mimi_oracle.py) the distance should be far smaller (accumulation
+    # order + rare bf16 rounding flips); reported here, to be tightened into the bound once it has GPU history
+    emu = M.mimi_decode_bf16_operands(sd, codes)
+    d = float((got - emu).abs().max())
+    print(f"tensor-core mode B={B} T={T}: max err vs fp32 oracle {float(err.abs().max()) / peak:.2e} of peak, "
+          f"vs bf16-operand model {d / peak:.2e} of peak")
+    assert d <= 2.6e-2 * peak
 
 
 def test_full_size_decode_properties():
