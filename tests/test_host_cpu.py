@@ -146,3 +146,16 @@ def test_noise_blocks_equal_one_tape_and_settle_rewinds():
     p = _Noise(5, V, 11, None)
     assert torch.equal(p.tape, torch.empty(5, V).exponential_(1.0, generator=torch.Generator().manual_seed(11)))
     assert torch.equal(before, torch.get_rng_state())
+
+
+def test_public_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header must compile as C99 on its own (no C++ or torch types)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = os.path.join(ROOT, "include", "sopro_b200.h")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
