@@ -258,6 +258,31 @@ int sopro_mimi_set_precision(sopro_mimi_t* m, int precision);
  * Results are identical to the plain path. */
 int sopro_mimi_set_graphs(sopro_mimi_t* m, int enabled);
 
+/* A decode that meets a code outside [0, vocab) (e.g. an uncut EOS id) clamps it and sets a sticky flag instead of
+ * reading outside the codebook (the reference's embedding lookup raises IndexError, modeling_mimi.py:1192-1196).
+ * sopro_mimi_check synchronises `stream`, returns SOPRO_ERR_INVALID if the flag was set since the last check, and
+ * clears it.  The *_host entry points validate their host buffers up front instead. */
+int sopro_mimi_check(sopro_mimi_t* m, void* stream);
+
+/* ---- streaming decode with persistent state: MimiStreamDecoder.decode_step / MimiDecodeState (reference
+ * codec/mimi.py:75-181).  A stream carries one K/V ring per transformer layer (the last `window` positions), the
+ * previous RVQ frame of the upsampler and the (taps-1) left-context rows of every causal conv (what transformers'
+ * MimiConv1dPaddingCache holds, modeling_mimi.py:77-170), so a chunk costs O(chunk) and, decoder being causal, the
+ * chunks concatenate to exactly what sopro_mimi_decode gives for the whole sequence (bit-identical in SOPRO_MIMI_FP32
+ * mode; within the tensor-core mode's stated tolerance otherwise).  The reference instead re-decodes 2 overlap frames
+ * on top of a transformers KV cache with no conv context and documents its stream as not bit-exact (README.md:151).
+ * One stream = one utterance; streams of one decoder are independent; the arithmetic mode is the decoder's at
+ * create / reset time. */
+typedef struct sopro_mimi_stream sopro_mimi_stream_t;
+int sopro_mimi_stream_create(sopro_mimi_t* m, int max_chunk_frames, sopro_mimi_stream_t** out);
+int sopro_mimi_stream_destroy(sopro_mimi_stream_t* s);
+int sopro_mimi_stream_reset(sopro_mimi_stream_t* s, void* stream);     /* back to frame 0 (MimiDecodeState()) */
+int64_t sopro_mimi_stream_frames(const sopro_mimi_stream_t* s);        /* MimiDecodeState.frames_seen */
+/* the next n frames: codes [n_q, n] i32 (device) -> wav [n*1920] f32 (device); any n >= 1 (longer than
+ * max_chunk_frames is processed in pieces) */
+int sopro_mimi_decode_step(sopro_mimi_stream_t* s, const int32_t* codes, int n, float* wav, void* stream);
+int sopro_mimi_decode_step_host(sopro_mimi_stream_t* s, const int32_t* codes_host, int n, float* wav_host, void* stream);
+
 /* test hook: one tensor-core implicit GEMM (no reference counterpart).  X bf16 [B][rows][cin] (device),
  * W bf16 [N][taps*cin] (device); out[b][m][n] = epi(sum_j sum_ci X[b][m + j*dil - pad][ci] * W[n][j*cin+ci] +
  * bias[n % bias_mod]); epi: 0 none, 1 GELU(erf), 2 R + scale*acc, 3 R + acc; out_f32 / out_bf16 may be null;

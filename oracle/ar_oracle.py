@@ -203,6 +203,8 @@ def sample_token(
     if top_p is not None and top_p < 1.0:
         sp, si = torch.sort(probs, descending=True, dim=-1)
         cum = torch.cumsum(sp, dim=-1)
+        if trace is not None:
+            trace["cum"] = cum[0, :64].clone()
         remove = cum > float(top_p)
         remove[..., 1:] = remove[..., :-1].clone()
         remove[..., 0] = False

@@ -105,6 +105,13 @@ SYMBOLS = {
     "sopro_mimi_decode_host": (_I, [_VP, _VP, _I, _I, _VP, _VP]),
     "sopro_mimi_set_precision": (_I, [_VP, _I]),
     "sopro_mimi_set_graphs": (_I, [_VP, _I]),
+    "sopro_mimi_check": (_I, [_VP, _VP]),
+    "sopro_mimi_stream_create": (_I, [_VP, _I, C.POINTER(_VP)]),
+    "sopro_mimi_stream_destroy": (_I, [_VP]),
+    "sopro_mimi_stream_reset": (_I, [_VP, _VP]),
+    "sopro_mimi_stream_frames": (C.c_int64, [_VP]),
+    "sopro_mimi_decode_step": (_I, [_VP, _VP, _I, _VP, _VP]),
+    "sopro_mimi_decode_step_host": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sopro_debug_tc_gemm": (_I, [_VP, _I, C.c_int64, _I, _I, _I, _I, _VP, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
 }
 

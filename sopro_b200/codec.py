@@ -99,9 +99,20 @@ class MimiEngine:
         """CUDA-graph replay of small (<= 64 frame) decodes inside the library; on by default."""
         _lib.check(self.lib.sopro_mimi_set_graphs(self._h, 1 if enabled else 0))
 
+    def _validated(self, codes: torch.Tensor) -> torch.Tensor:
+        """int32 codes on the device; like the reference's embedding lookup, a code outside [0, 2048) is an IndexError
+        (an uncut EOS id would otherwise read past the codebook; the kernel itself clamps and flags)."""
+        codes = codes.to(device=self.device, dtype=torch.int32).contiguous()
+        if codes.numel():
+            lo, hi = torch.aminmax(codes)
+            lo, hi = int(lo), int(hi)
+            if lo < 0 or hi >= 2048:
+                raise IndexError(f"Mimi codes must be in [0, 2048), got values in [{lo}, {hi}]")
+        return codes
+
     def decode(self, codes_bqt: torch.Tensor) -> torch.Tensor:
         """codes [B, Q, T] (any int dtype, any device) -> wav [B, 1, T*hop] f32 on the engine's device."""
-        codes = codes_bqt.to(device=self.device, dtype=torch.int32).contiguous()
+        codes = self._validated(codes_bqt)
         B, Q, T = codes.shape
         if Q != self.num_quantizers:
             raise ValueError(f"expected {self.num_quantizers} codebooks, got {Q}")
@@ -120,10 +131,65 @@ class MimiEngine:
                                                    int(torch.cuda.current_stream(self.device).cuda_stream)))
         return wav
 
+    def check(self) -> None:
+        """Raises if any decode since the last check met an out-of-range code (device-side sticky flag)."""
+        _lib.check(self.lib.sopro_mimi_check(self._h, int(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def stream(self, max_chunk_frames: int = 16) -> "MimiStream":
+        return MimiStream(self, max_chunk_frames)
+
     def close(self):
         if getattr(self, "_h", None):
             self.lib.sopro_mimi_destroy(self._h)
             self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class MimiStream:
+    """Persistent decode state of one utterance on the device (K/V rings, upsampler frame, conv context rows):
+    ``step(codes [Q, n])`` returns the next n*hop samples in O(n) work.  See include/sopro_b200.h."""
+
+    def __init__(self, engine: MimiEngine, max_chunk_frames: int = 16):
+        self.engine, self.lib = engine, engine.lib
+        h = C.c_void_p()
+        _lib.check(self.lib.sopro_mimi_stream_create(engine._h, int(max_chunk_frames), C.byref(h)))
+        self._h = h
+
+    @property
+    def frames(self) -> int:
+        return int(self.lib.sopro_mimi_stream_frames(self._h))
+
+    def reset(self) -> None:
+        _lib.check(self.lib.sopro_mimi_stream_reset(self._h, int(torch.cuda.current_stream(self.engine.device).cuda_stream)))
+
+    def step(self, codes_qn: torch.Tensor) -> torch.Tensor:
+        codes = self.engine._validated(codes_qn)
+        Q, n = codes.shape
+        if Q != self.engine.num_quantizers:
+            raise ValueError(f"expected {self.engine.num_quantizers} codebooks, got {Q}")
+        wav = torch.empty((1, n * self.engine.hop), dtype=torch.float32, device=self.engine.device)
+        if n:
+            _lib.check(self.lib.sopro_mimi_decode_step(self._h, codes.data_ptr(), int(n), wav.data_ptr(),
+                                                       int(torch.cuda.current_stream(self.engine.device).cuda_stream)))
+        return wav
+
+    def step_host(self, codes_qn: np.ndarray) -> np.ndarray:
+        codes = np.ascontiguousarray(codes_qn, dtype=np.int32)
+        Q, n = codes.shape
+        wav = np.empty((1, n * self.engine.hop), dtype=np.float32)
+        _lib.check(self.lib.sopro_mimi_decode_step_host(self._h, codes.ctypes.data, int(n), wav.ctypes.data,
+                                                        int(torch.cuda.current_stream(self.engine.device).cuda_stream)))
+        return wav
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.engine, "_h", None):
+            self.lib.sopro_mimi_stream_destroy(self._h)
+        self._h = None
 
     def __del__(self):
         try:
@@ -183,26 +249,28 @@ class MimiCodec:
 
 @dataclass
 class MimiDecodeState:
-    """Fields of the reference's state (codec/mimi.py:75-80) + the code history our decoder re-reads."""
+    """Fields of the reference's state (codec/mimi.py:75-80).  ``decoder_past_key_values`` holds the device-side
+    stream (K/V rings of the transformer + the conv context rows) instead of a transformers cache object."""
     decoder_past_key_values: Optional[object] = None
     frames_seen: int = 0
     samples_emitted: int = 0
     tail_codes_tq: Optional[torch.Tensor] = None
-    history_tq: Optional[torch.Tensor] = None
 
 
 class MimiStreamDecoder:
-    """Chunked streaming decode (reference codec/mimi.py:83-181).
+    """Chunked streaming decode (reference codec/mimi.py:83-181) over a persistent device state.
 
-    The reference re-feeds the last ``overlap_frames`` frames on top of a transformer KV cache and warns that
-    the result is "not bit-exact compared to the non-streaming version" (README.md:151); on transformers >= 5
-    its cache trimming silently does nothing.  The whole Mimi decode path is causal
-    (tests/test_mimi_oracle.py::test_decode_is_causal_prefix_exact), so this decoder instead decodes the
-    prefix seen so far and emits the samples of the new frames: chunk by chunk it yields EXACTLY the
-    non-streaming waveform.  ``overlap_frames`` is accepted for signature compatibility."""
+    The reference re-feeds the last ``overlap_frames`` frames on top of a transformers KV cache, with no conv
+    context, and documents the result as "not bit-exact compared to the non-streaming version" (README.md:151); on
+    transformers >= 5 its cache trimming silently does nothing and later chunks drift by up to 0.7 of
+    the waveform's peak from its own decode_full (measured: tests/golden/measure_stream_distance.py).
+    Here the state carries everything a causal decoder needs (K/V rings, upsampler frame, the left context of every
+    conv), so each chunk costs O(chunk) and the chunks concatenate to exactly the non-streaming waveform.
+    ``overlap_frames`` is accepted for signature compatibility; nothing is re-decoded."""
 
-    def __init__(self, codec: MimiCodec):
+    def __init__(self, codec: MimiCodec, max_chunk_frames: int = 16):
         self.codec = codec
+        self.max_chunk_frames = int(max_chunk_frames)
 
     @torch.inference_mode()
     def decode_step(self, codes_chunk_tq: torch.Tensor, state: Optional[MimiDecodeState] = None, *,
@@ -212,15 +280,11 @@ class MimiStreamDecoder:
         n_new = int(codes_chunk_tq.size(0))
         if n_new == 0:
             return torch.zeros(1, 0, device=self.codec.device), state
+        if state.decoder_past_key_values is None:
+            state.decoder_past_key_values = self.codec.engine.stream(self.max_chunk_frames)
         chunk = codes_chunk_tq.to(self.codec.device)
-        hist = chunk if state.history_tq is None else torch.cat([state.history_tq, chunk], dim=0)
-        hop = self.codec.engine.hop
-        # causal receptive field of the decoder in codec frames: 250-position attention window at 25 Hz
-        # (125 frames) per layer is unbounded through depth, so the full prefix is decoded (<= 400 frames)
-        wav = self.codec.engine.decode(hist.permute(1, 0).unsqueeze(0)).reshape(1, -1)
-        wav_new = wav[:, (hist.size(0) - n_new) * hop:]
-        state.history_tq = hist
+        wav_new = state.decoder_past_key_values.step(chunk.permute(1, 0))
         state.frames_seen += n_new
         state.samples_emitted += int(wav_new.size(1))
-        state.tail_codes_tq = hist[-max(int(overlap_frames), 0):].detach() if overlap_frames > 0 else None
+        state.tail_codes_tq = chunk[-max(int(overlap_frames), 0):].detach() if overlap_frames > 0 else None
         return wav_new, state

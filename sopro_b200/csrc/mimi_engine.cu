@@ -158,13 +158,19 @@ __global__ void __launch_bounds__(256) igemm_kernel(const GemmOp op) {
 }
 
 // RVQ lookup-sum: codes [B][Q][T] -> S [B][T][2*Dc] = [semantic sum | acoustic sum]
+// A code outside [0, vocab) (an uncut EOS id, a negative pad) is clamped and recorded in *bad (sticky, read by
+// sopro_mimi_check): the gather never leaves the table.  The reference's embedding lookup raises IndexError there.
 __global__ void rvq_gather_kernel(const int* __restrict__ codes, const float* __restrict__ embed, float* __restrict__ S,
-                                  int Q, int T, int Dc, int vocab, int n_sem) {
+                                  int Q, int T, int Dc, int vocab, int n_sem, int* __restrict__ bad) {
   const int t = blockIdx.x, b = blockIdx.y;
   for (int c = threadIdx.x; c < Dc; c += blockDim.x) {
     float s0 = 0.f, s1 = 0.f;
     for (int q = 0; q < Q; ++q) {
-      const int code = codes[((size_t)b * Q + q) * T + t];
+      int code = codes[((size_t)b * Q + q) * T + t];
+      if (code < 0 || code >= vocab) {
+        if (c == 0) atomicOr(bad, 1);
+        code = min(max(code, 0), vocab - 1);
+      }
       const float e = __ldg(embed + ((size_t)q * vocab + code) * Dc + c);
       if (q < n_sem) s0 += e;
       else s1 += e;
@@ -176,14 +182,16 @@ __global__ void rvq_gather_kernel(const int* __restrict__ codes, const float* __
 }
 
 // depthwise ConvTranspose k=4 s=2, causal: y[2t+r][c] = x[t][c]*w[c][r] + x[t-1][c]*w[c][r+2]
+// `prev` (streaming, B = 1): the frame before x[0] (zeros at the start of a stream), else null
 __global__ void upsample_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int T,
-                                int C) {
+                                int C, const float* __restrict__ prev) {
   const int to = blockIdx.x, b = blockIdx.y;  // output row 0..2T-1
   const int t = to >> 1, r = to & 1;
   const float* xb = x + (size_t)b * T * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float v = xb[(size_t)t * C + c] * __ldg(w + c * 4 + r);
     if (t > 0) v += xb[(size_t)(t - 1) * C + c] * __ldg(w + c * 4 + r + 2);
+    else if (prev) v += prev[c] * __ldg(w + c * 4 + r + 2);
     y[((size_t)b * 2 * T + to) * C + c] = v;
   }
 }
@@ -224,12 +232,15 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 }
 
 // RoPE in place on the q and k thirds of QKV [rows][3C]; rope table [T2][Dh/2] cos, then sin
-__global__ void rope_kernel(float* __restrict__ qkv, const float* __restrict__ cs, int T2, int tab_T2, int C, int H) {
+// Streaming (kring != null, B = 1): row t sits at absolute position pos0 + t; its rotated key and its value are also
+// appended to the layer's K/V ring at slot (pos0 + t) % R.
+__global__ void rope_kernel(float* __restrict__ qkv, const float* __restrict__ cs, int T2, int tab_T2, int C, int H,
+                            int pos0, float* __restrict__ kring, float* __restrict__ vring, int R) {
   const int t = blockIdx.x, b = blockIdx.y;
   const int Dh = C / H, half = Dh / 2;
   float* row = qkv + ((size_t)b * T2 + t) * 3 * C;
-  const float* cosr = cs + (size_t)t * half;
-  const float* sinr = cs + (size_t)(tab_T2 + t) * half;  // table: [cos rows 0..tab_T2) | sin rows 0..tab_T2)]
+  const float* cosr = cs + (size_t)(pos0 + t) * half;
+  const float* sinr = cs + (size_t)(tab_T2 + pos0 + t) * half;  // table: [cos rows 0..tab_T2) | sin rows 0..tab_T2)]
   for (int i = threadIdx.x; i < 2 * H * half; i += blockDim.x) {
     const int which = i / (H * half);  // 0 = q, 1 = k
     const int rem = i - which * H * half;
@@ -239,6 +250,14 @@ __global__ void rope_kernel(float* __restrict__ qkv, const float* __restrict__ c
     const float c = cosr[d], s = sinr[d];
     p[d] = x1 * c - x2 * s;          // q*cos + rotate_half(q)*sin, first half: -x2
     p[d + half] = x2 * c + x1 * s;   // second half: +x1
+  }
+  if (kring) {
+    __syncthreads();
+    const size_t slot = (size_t)((pos0 + t) % R) * C;
+    for (int c4 = threadIdx.x * 4; c4 < C; c4 += blockDim.x * 4) {
+      *reinterpret_cast<float4*>(kring + slot + c4) = *reinterpret_cast<const float4*>(row + C + c4);
+      *reinterpret_cast<float4*>(vring + slot + c4) = *reinterpret_cast<const float4*>(row + 2 * C + c4);
+    }
   }
 }
 
@@ -286,9 +305,13 @@ __global__ void __launch_bounds__(256) rope_pack_kernel(const float* __restrict_
 }
 
 // causal sliding-window attention, one warp per (b, h, query); QKV rotated; out [B][T2][C]
+// Streaming (kring != null, B = 1): query row i sits at absolute position pos0 + i and the keys / values of positions
+// [pos - window + 1, pos] are read from the layer's ring (slot = position % R); the arithmetic and its order are the
+// full decode's, so a chunked decode equals the full decode's prefix bit for bit in fp32 mode.
 template <typename OutT>
 __global__ void __launch_bounds__(256) attn_kernel(const float* __restrict__ qkv, OutT* __restrict__ out, int T2, int C,
-                                                   int H, int window) {
+                                                   int H, int window, int pos0, const float* __restrict__ kring,
+                                                   const float* __restrict__ vring, int R) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Dh = C / H;
@@ -300,12 +323,13 @@ __global__ void __launch_bounds__(256) attn_kernel(const float* __restrict__ qkv
   const float* q = base + (size_t)i * 3 * C + h * Dh;
   for (int d = lane; d < Dh; d += 32) qs[d] = q[d];
   __syncwarp();
-  const int j0 = max(0, i - window + 1);
-  const int nk = i - j0 + 1;
+  const int ia = pos0 + i;  // absolute position
+  const int j0 = max(0, ia - window + 1);
+  const int nk = ia - j0 + 1;
   const float scale = 1.0f / sqrtf((float)Dh);
   float mx = -INFINITY;
   for (int jj = lane; jj < nk; jj += 32) {
-    const float* kr = base + (size_t)(j0 + jj) * 3 * C + C + h * Dh;
+    const float* kr = kring ? kring + (size_t)((j0 + jj) % R) * C + h * Dh : base + (size_t)(j0 + jj) * 3 * C + C + h * Dh;
     float s = 0.f;
     for (int d = 0; d < Dh; d += 4) {
       const float4 kk = *reinterpret_cast<const float4*>(kr + d);
@@ -329,14 +353,20 @@ __global__ void __launch_bounds__(256) attn_kernel(const float* __restrict__ qkv
   const float inv = 1.0f / sum;
   for (int d = lane; d < Dh; d += 32) {
     float o = 0.f;
-    for (int jj = 0; jj < nk; ++jj) o += (sc[jj] * inv) * base[(size_t)(j0 + jj) * 3 * C + 2 * C + h * Dh + d];
+    if (vring) {
+      for (int jj = 0; jj < nk; ++jj) o += (sc[jj] * inv) * vring[(size_t)((j0 + jj) % R) * C + h * Dh + d];
+    } else {
+      for (int jj = 0; jj < nk; ++jj) o += (sc[jj] * inv) * base[(size_t)(j0 + jj) * 3 * C + 2 * C + h * Dh + d];
+    }
     put(out + ((size_t)b * T2 + i) * C + h * Dh + d, o);
   }
 }
 
 // final conv: ELU -> causal conv k taps, Cin -> 1
+// rows r >= lo are readable (lo = 0: the causal zero pad; streaming: lo = -(taps-1), the carried context rows sit in
+// front of x)
 __global__ void final_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
-                                  float* __restrict__ y, long long Tn, int Cin, int taps) {
+                                  float* __restrict__ y, long long Tn, int Cin, int taps, int lo) {
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int b = blockIdx.y;
   if (t >= Tn) return;
@@ -344,7 +374,7 @@ __global__ void final_conv_kernel(const float* __restrict__ x, const float* __re
   float acc = __ldg(bias);
   for (int j = 0; j < taps; ++j) {
     const long long r = t + j - (taps - 1);
-    if (r < 0) continue;
+    if (r < lo) continue;
     const float* xr = xb + r * Cin;
     for (int c = 0; c < Cin; c += 4) {
       const float4 v = *reinterpret_cast<const float4*>(xr + c);
@@ -360,7 +390,7 @@ __global__ void final_conv_kernel(const float* __restrict__ x, const float* __re
 // through shared memory.  256 - (taps-1) outputs per block.
 __global__ void __launch_bounds__(256) final_conv_h_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ bias, float* __restrict__ y, long long Tn,
-                                                           int Cin, int taps) {
+                                                           int Cin, int taps, int lo) {
   extern __shared__ float fsm[];  // [taps][256] partial dots, then [taps*Cin] weights
   float* sp = fsm;
   float* sw = fsm + taps * 256;
@@ -371,8 +401,8 @@ __global__ void __launch_bounds__(256) final_conv_h_kernel(const __nv_bfloat16* 
   float acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-  if (r >= 0 && r < Tn) {
-    const uint4* xr = reinterpret_cast<const uint4*>(x + ((size_t)b * Tn + r) * Cin);
+  if (r >= lo && r < Tn) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + ((long long)b * Tn + r) * Cin);
     for (int c = 0; c < Cin; c += 8) {
       const uint4 v = xr[c >> 3];
       const uint32_t u[4] = {v.x, v.y, v.z, v.w};
@@ -482,6 +512,7 @@ struct sopro_mimi {
   size_t ws_bytes = 0;
   int* codes_dev = nullptr;
   size_t codes_cap = 0;
+  int* bad_code = nullptr;  // sticky flag: a decode saw a code outside [0, vocab)
   // launch-bound small decodes (streaming chunks, time-to-first-audio) are replayed from CUDA graphs captured over
   // internal static buffers; every graph dies when the workspace or the rope table is reallocated
   struct Replay {
@@ -594,6 +625,8 @@ int sopro_mimi_create(const sopro_mimi_config_t* cfg, const sopro_mimi_weights_t
   m->n_floats = A.host.size();
   cudaError_t err = cudaMalloc(&m->dev, m->n_floats * 4);
   if (err == cudaSuccess) err = cudaMemcpy(m->dev, A.host.data(), m->n_floats * 4, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMalloc(&m->bad_code, 256);
+  if (err == cudaSuccess) err = cudaMemset(m->bad_code, 0, 256);
   if (err == cudaSuccess) err = cudaMalloc(&m->dev_h, Hh.host.size() * 2);
   if (err == cudaSuccess) err = cudaMemcpy(m->dev_h, Hh.host.data(), Hh.host.size() * 2, cudaMemcpyHostToDevice);
   if (err == cudaSuccess && !tc::encode_tiled_fn()) {
@@ -620,6 +653,7 @@ int sopro_mimi_destroy(sopro_mimi_t* m) {
   cudaFree(m->rope);
   cudaFree(m->ws);
   cudaFree(m->codes_dev);
+  cudaFree(m->bad_code);
   for (auto& r : m->replays) cudaGraphExecDestroy(r.exec);
   cudaFree(m->g_codes);
   cudaFree(m->g_wav);
@@ -666,9 +700,10 @@ void drop_replays(sopro_mimi* m) {
 }
 
 // Allocations and table uploads a decode of [B, T] needs; never called inside a stream capture.
-int mimi_prepare(sopro_mimi* m, int B, int T, cudaStream_t st) {
+// RoPE table [cos rows 0..T2) | sin rows 0..T2)] covering at least T2 positions
+int ensure_rope(sopro_mimi* m, int T2, cudaStream_t st) {
   const sopro_mimi_config_t& c = m->cfg;
-  const int C = c.hidden, T2 = 2 * T, Dh = C / c.n_heads, FF = c.ffn;
+  const int Dh = c.hidden / c.n_heads;
   if (m->rope_T2 < T2) {
     drop_replays(m);
     cudaFree(m->rope);
@@ -686,6 +721,17 @@ int mimi_prepare(sopro_mimi* m, int B, int T, cudaStream_t st) {
     MCK(cudaMemcpyAsync(m->rope, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
     MCK(cudaStreamSynchronize(st));
     m->rope_T2 = T2;
+  }
+  return SOPRO_OK;
+}
+
+int mimi_prepare(sopro_mimi* m, int B, int T, cudaStream_t st) {
+  const sopro_mimi_config_t& c = m->cfg;
+  const int C = c.hidden, T2 = 2 * T, FF = c.ffn;
+  {
+    // streams share the table: never shrink it, grow with headroom
+    const int rc = ensure_rope(m, T2, st);
+    if (rc) return rc;
   }
   long long up = 2;
   for (int i = 0; i < c.n_ratios; ++i) up *= c.ratios[i];
@@ -780,7 +826,7 @@ int mimi_enqueue(sopro_mimi* m, const int32_t* codes, int B, int T, float* wav, 
   __nv_bfloat16* h1 = h0 + bufsz;
   __nv_bfloat16* h2 = h1 + bufsz;
   // ---- RVQ + projection + upsample (small; fp32 in both modes)
-  rvq_gather_kernel<<<dim3(T, B), 256, 0, st>>>(codes, Wd + m->embed, b0, c.n_q, T, c.codebook_dim, c.vocab, c.n_sem);
+  rvq_gather_kernel<<<dim3(T, B), 256, 0, st>>>(codes, Wd + m->embed, b0, c.n_q, T, c.codebook_dim, c.vocab, c.n_sem, m->bad_code);
   MCK(cudaGetLastError());
   GemmOp g{};
   auto lin = [&](const float* A, int M, int K, const float* W, int N, float* Cc, int epi, const float* R, const float* scale) {
@@ -812,7 +858,7 @@ int mimi_enqueue(sopro_mimi* m, const int32_t* codes, int B, int T, float* wav, 
   };
   int rc;
   if ((rc = lin(b0, T, C, Wd + m->rvq_w, C, b1, EPI_NONE, nullptr, nullptr))) return rc;
-  upsample_kernel<<<dim3(T2, B), 256, 0, st>>>(b1, Wd + m->up_w, x, T, C);
+  upsample_kernel<<<dim3(T2, B), 256, 0, st>>>(b1, Wd + m->up_w, x, T, C, nullptr);
   MCK(cudaGetLastError());
   // ---- transformer
   const long long rows = (long long)B * T2;
@@ -833,8 +879,8 @@ int mimi_enqueue(sopro_mimi* m, const int32_t* codes, int B, int T, float* wav, 
         cudaError_t ae = tc::launch_attn(h0, h1, h2, att, B, T2, T2p, C, H, c.window, st);
         if (ae != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "tensor-core attention: %s", cudaGetErrorString(ae));
       } else {
-        rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H);
-        attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, att, T2, C, H, c.window);
+        rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H, 0, nullptr, nullptr, 1);
+        attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, att, T2, C, H, c.window, 0, nullptr, nullptr, 1);
         MCK(cudaGetLastError());
       }
       if ((rc = tcg(att, T2, C, 1, 0, Wh + L.wo_h, nullptr, C, C, tc::EPI_RES_SCALE, x, Wd + L.ls1, x, nullptr, 0))) return rc;
@@ -844,8 +890,8 @@ int mimi_enqueue(sopro_mimi* m, const int32_t* codes, int B, int T, float* wav, 
     } else {
       layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln1w, Wd + L.ln1b, ln, rows, C, c.norm_eps);
       if ((rc = lin(ln, T2, C, Wd + L.qkv, 3 * C, b0, EPI_NONE, nullptr, nullptr))) return rc;
-      rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H);
-      attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, b1, T2, C, H, c.window);
+      rope_kernel<<<dim3(T2, B), 256, 0, st>>>(b0, m->rope, T2, m->rope_T2, C, H, 0, nullptr, nullptr, 1);
+      attn_kernel<<<dim3((T2 + 7) / 8, H, B), 256, asm_bytes, st>>>(b0, b1, T2, C, H, c.window, 0, nullptr, nullptr, 1);
       MCK(cudaGetLastError());
       if ((rc = lin(b1, T2, C, Wd + L.wo, C, x, EPI_RES_SCALE, x, Wd + L.ls1))) return rc;
       layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln2w, Wd + L.ln2b, ln, rows, C, c.norm_eps);
@@ -872,7 +918,7 @@ int mimi_enqueue(sopro_mimi* m, const int32_t* codes, int B, int T, float* wav, 
       if ((rc = conv(o2, Tn, hid, 1, 0, Wd + S.r2w, Wd + S.r2b, S.cout, S.cout, cur, 1, EPI_RES, o1))) return rc;
       ch = S.cout;
     }
-    final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
+    final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel, 0);
     MCK(cudaGetLastError());
     return SOPRO_OK;
   }
@@ -962,18 +1008,413 @@ int mimi_enqueue(sopro_mimi* m, const int32_t* codes, int B, int T, float* wav, 
     ch = S.cout;
   }
   if (cur32) {
-    final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur32, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
+    final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), B), 256, 0, st>>>(cur32, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel, 0);
   } else {
     const int per = 256 - (c.last_kernel - 1);
     final_conv_h_kernel<<<dim3((unsigned)((Tn + per - 1) / per), B), 256, (size_t)(c.last_kernel * 256 + c.last_kernel * ch) * 4, st>>>(
-        curh, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel);
+        curh, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel, 0);
   }
   MCK(cudaGetLastError());
   return SOPRO_OK;
 }
 }  // namespace
 
+
+// ---------------------------------------------------------------------------------------------
+// Streaming decode with persistent state (reference codec/mimi.py:83-181 MimiStreamDecoder; transformers
+// modeling_mimi.py:77-170 MimiConv1dPaddingCache is the per-conv left context this replaces).
+//
+// A stream owns (a) one K/V ring per transformer layer holding the rotated keys and the values of the last
+// `window` positions, (b) the previous RVQ frame (the depthwise ConvTranspose upsampler reads x[t-1]) and (c) for every
+// causal conv of the SEANet decoder the last (taps-1) input rows.  (c) is stored IN PLACE: each conv input buffer is
+// laid out [context rows | rows of this chunk]; the conv runs as a "valid" convolution over it (pad = 0,
+// Min = M + taps - 1) and afterwards the buffer's last context-many rows are moved to its front.  At the start of a
+// stream the context rows are zero, which is exactly the causal zero padding of the full decode, and every kernel
+// computes each output element in the same order as the full decode: in fp32 mode the chunks are bit-identical to the
+// full decode's prefix.  Work per chunk is O(chunk), not O(prefix).
+// ---------------------------------------------------------------------------------------------
+struct TailShift {
+  void* base[16];
+  int row_bytes[16], ctx[16], rows[16];  // rows = new rows written behind the ctx rows this step
+  int n;
+};
+
+// one block per buffer: rows [rows, rows + ctx) -> [0, ctx) (through shared memory: the ranges may overlap)
+__global__ void __launch_bounds__(256) tail_shift_kernel(const TailShift ts) {
+  extern __shared__ uint4 tsm[];
+  const int i = blockIdx.x;
+  const int n16 = ts.ctx[i] * ts.row_bytes[i] / 16;
+  const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(ts.base[i]) + (size_t)ts.rows[i] * ts.row_bytes[i]);
+  uint4* dst = reinterpret_cast<uint4*>(ts.base[i]);
+  for (int e = threadIdx.x; e < n16; e += blockDim.x) tsm[e] = src[e];
+  __syncthreads();
+  for (int e = threadIdx.x; e < n16; e += blockDim.x) dst[e] = tsm[e];
+}
+
+struct sopro_mimi_stream {
+  sopro_mimi* m = nullptr;
+  int max_n = 0, precision = 0, R = 0;
+  long long frames = 0;
+  unsigned char* slab = nullptr;
+  size_t slab_bytes = 0, state_bytes = 0;
+  // ---- state (zeroed by reset): [up_prev | K rings | V rings | conv-context rows at the front of the buffers below]
+  float* up_prev = nullptr;
+  float *kring = nullptr, *vring = nullptr;  // [n_layers][R][C]
+  // ---- chunk buffers
+  float *S = nullptr, *E = nullptr, *XC = nullptr, *LN = nullptr, *QKV = nullptr, *ATT = nullptr, *HID = nullptr;
+  __nv_bfloat16 *LNh = nullptr, *ATTh = nullptr, *HIDh = nullptr, *XCh = nullptr;
+  void* A0 = nullptr;               // conv0 output  [1 + T2][16F]    (fp32 raw | bf16 ELU'd)
+  void* Z[SOPRO_MIMI_MAX_RATIOS]{};    // ConvTranspose output [2 + Tn][cout] (fp32 raw | bf16 ELU'd)
+  float* Zf[SOPRO_MIMI_MAX_RATIOS]{};  // tensor-core mode: fp32 skip [Tn][cout]
+  float* Hs[SOPRO_MIMI_MAX_RATIOS]{};  // fp32 mode: res hidden [Tn][cout/2]
+  void* O[SOPRO_MIMI_MAX_RATIOS]{};    // block output [ctx + Tn][cout], ctx = 1 (next ConvTranspose) or taps-1 (final conv)
+  int* codes_dev = nullptr;
+  float* wav_dev = nullptr;
+};
+
+namespace {
+struct SlabPlan {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off = (off + bytes + 255) / 256 * 256;
+    return o;
+  }
+};
+
+// lays the stream's slab out; with base == nullptr only sizes are computed
+void stream_layout(sopro_mimi_stream* s, unsigned char* base) {
+  const sopro_mimi_config_t& c = s->m->cfg;
+  const bool tcm = s->precision == SOPRO_MIMI_BF16_TC;
+  const size_t C = c.hidden, FF = c.ffn, n = s->max_n, T2 = 2 * n, NL = c.n_layers;
+  const size_t es = tcm ? 2 : 4;  // element size of the conv operands
+  SlabPlan P;
+  auto at = [&](size_t o) { return base ? base + o : nullptr; };
+  // state first
+  s->up_prev = (float*)at(P.take(C * 4));
+  s->kring = (float*)at(P.take(NL * s->R * C * 4));
+  s->vring = (float*)at(P.take(NL * s->R * C * 4));
+  // conv operand buffers: the context rows at their fronts are state too, so they come next
+  const int k0 = c.kernel - 1;
+  s->XC = (float*)at(P.take((k0 + T2) * C * 4));
+  s->XCh = tcm ? (__nv_bfloat16*)at(P.take((k0 + T2) * C * 2)) : nullptr;
+  size_t ch = (size_t)c.num_filters << c.n_ratios, Tn = T2;
+  s->A0 = at(P.take((1 + Tn) * ch * es));
+  for (int i = 0; i < c.n_ratios; ++i) {
+    const size_t cout = ch / 2;
+    Tn *= c.ratios[i];
+    const size_t ctx_o = i + 1 == c.n_ratios ? (size_t)(c.last_kernel - 1) : 1;
+    s->Z[i] = at(P.take((c.res_kernel - 1 + Tn) * cout * es));
+    s->O[i] = at(P.take((ctx_o + Tn) * cout * es));
+    ch = cout;
+  }
+  s->state_bytes = P.off;  // everything up to here is zeroed by reset (a superset of the state proper)
+  ch = (size_t)c.num_filters << c.n_ratios;
+  Tn = T2;
+  for (int i = 0; i < c.n_ratios; ++i) {
+    const size_t cout = ch / 2;
+    Tn *= c.ratios[i];
+    s->Zf[i] = tcm ? (float*)at(P.take(Tn * cout * 4)) : nullptr;
+    s->Hs[i] = tcm ? nullptr : (float*)at(P.take(Tn * (cout / c.compress) * 4));
+    ch = cout;
+  }
+  s->S = (float*)at(P.take(n * C * 4));
+  s->E = (float*)at(P.take(n * C * 4));
+  s->LN = (float*)at(P.take(T2 * C * 4));
+  s->QKV = (float*)at(P.take(T2 * 3 * C * 4));
+  s->ATT = (float*)at(P.take(T2 * C * 4));
+  s->HID = (float*)at(P.take(T2 * FF * 4));
+  s->LNh = (__nv_bfloat16*)s->LN;
+  s->ATTh = (__nv_bfloat16*)s->ATT;
+  s->HIDh = (__nv_bfloat16*)s->HID;
+  s->slab_bytes = P.off;
+}
+
+int stream_step(sopro_mimi_stream* s, const int32_t* codes, int n, int code_stride, float* wav, cudaStream_t st) {
+  sopro_mimi* m = s->m;
+  const sopro_mimi_config_t& c = m->cfg;
+  const int C = c.hidden, T2 = 2 * n, H = c.n_heads, Dh = C / H, FF = c.ffn;
+  const float* Wd = m->dev;
+  const __nv_bfloat16* Wh = m->dev_h;
+  const bool tcm = s->precision == SOPRO_MIMI_BF16_TC;
+  const int pos0 = (int)(2 * s->frames);
+  int rc = ensure_rope(m, std::max(4096, 2 * (pos0 + T2)), st);
+  if (rc) return rc;
+  GemmOp g{};
+  auto lin = [&](const float* A, int M, int K, const float* W, int N, float* Cc, int epi, const float* R, const float* scale) {
+    g = GemmOp{};
+    g.A = A; g.W = W; g.C = Cc; g.R = R; g.scale = scale; g.bias = nullptr;
+    g.M = M; g.N = N; g.K = K; g.Min = M; g.Cin = K; g.taps = 1; g.dil = 1; g.pad = 0; g.ldc = N; g.bias_mod = N; g.epi = epi;
+    return launch_gemm(g, 1, st);
+  };
+  // "valid" conv over [ctx rows | M rows]: A points at the first context row, Min = M + taps - 1, pad = 0
+  auto conv = [&](const float* A, long long M, int cin, int taps, const float* W, const float* bias, int N, int bias_mod, float* Cc,
+                  int elu, int epi, const float* R) {
+    g = GemmOp{};
+    g.A = A; g.W = W; g.C = Cc; g.R = R; g.bias = bias; g.scale = nullptr;
+    g.M = (int)M; g.N = N; g.K = taps * cin; g.Min = (int)M + taps - 1; g.Cin = cin; g.taps = taps; g.dil = 1; g.pad = 0; g.ldc = N;
+    g.bias_mod = bias_mod; g.epi = epi; g.a_elu = elu;
+    return launch_gemm(g, 1, st);
+  };
+  auto tcg = [&](const __nv_bfloat16* X, long long M, int cin, int taps, const __nv_bfloat16* W, const float* bias, int N, int bias_mod,
+                 int epi, const float* R, const float* scale, float* of, __nv_bfloat16* oh, int out_elu) {
+    tc::TcOp o{};
+    o.bias = bias; o.R = R; o.scale = scale; o.out_f32 = of; o.out_bf16 = oh;
+    o.c_bs = M * N; o.M = (int)M; o.N = N; o.K = taps * cin; o.Cin = cin; o.dil = 1; o.pad = 0;
+    o.bias_mod = bias_mod; o.epi = epi; o.out_elu = out_elu;
+    cudaError_t e = tc::launch(X, M + taps - 1, W, o, 1, st);
+    if (e != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "tensor-core GEMM (stream, N=%d K=%d): %s", N, o.K, cudaGetErrorString(e));
+    return (int)SOPRO_OK;
+  };
+  // ---- RVQ + projection + upsample
+  rvq_gather_kernel<<<dim3(n, 1), 256, 0, st>>>(codes, Wd + m->embed, s->S, c.n_q, code_stride, c.codebook_dim, c.vocab, c.n_sem, m->bad_code);
+  MCK(cudaGetLastError());
+  if ((rc = lin(s->S, n, C, Wd + m->rvq_w, C, s->E, EPI_NONE, nullptr, nullptr))) return rc;
+  const int k0 = c.kernel - 1;
+  float* x = s->XC + (size_t)k0 * C;  // residual stream: the rows behind conv0's context rows
+  upsample_kernel<<<dim3(T2, 1), 256, 0, st>>>(s->E, Wd + m->up_w, x, n, C, s->up_prev);
+  MCK(cudaGetLastError());
+  MCK(cudaMemcpyAsync(s->up_prev, s->E + (size_t)(n - 1) * C, (size_t)C * 4, cudaMemcpyDeviceToDevice, st));
+  // ---- transformer: K/V of the new positions go to the rings, queries attend over the ring
+  const unsigned ln_grid = (unsigned)((T2 + 7) / 8);
+  const size_t asm_bytes = (size_t)8 * (Dh + c.window) * 4;
+  for (size_t li = 0; li < m->layers.size(); ++li) {
+    const sopro_mimi::Layer& L = m->layers[li];
+    float* kr = s->kring + li * (size_t)s->R * C;
+    float* vr = s->vring + li * (size_t)s->R * C;
+    if (tcm) {
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln1w, Wd + L.ln1b, s->LNh, (long long)T2, C, c.norm_eps);
+      if ((rc = tcg(s->LNh, T2, C, 1, Wh + L.qkv_h, nullptr, 3 * C, 3 * C, tc::EPI_NONE, nullptr, nullptr, s->QKV, nullptr, 0))) return rc;
+      rope_kernel<<<dim3(T2, 1), 256, 0, st>>>(s->QKV, m->rope, T2, m->rope_T2, C, H, pos0, kr, vr, s->R);
+      attn_kernel<<<dim3((T2 + 7) / 8, H, 1), 256, asm_bytes, st>>>(s->QKV, s->ATTh, T2, C, H, c.window, pos0, kr, vr, s->R);
+      MCK(cudaGetLastError());
+      if ((rc = tcg(s->ATTh, T2, C, 1, Wh + L.wo_h, nullptr, C, C, tc::EPI_RES_SCALE, x, Wd + L.ls1, x, nullptr, 0))) return rc;
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln2w, Wd + L.ln2b, s->LNh, (long long)T2, C, c.norm_eps);
+      if ((rc = tcg(s->LNh, T2, C, 1, Wh + L.fc1_h, nullptr, FF, FF, tc::EPI_GELU, nullptr, nullptr, nullptr, s->HIDh, 0))) return rc;
+      if ((rc = tcg(s->HIDh, T2, FF, 1, Wh + L.fc2_h, nullptr, C, C, tc::EPI_RES_SCALE, x, Wd + L.ls2, x, nullptr, 0))) return rc;
+    } else {
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln1w, Wd + L.ln1b, s->LN, (long long)T2, C, c.norm_eps);
+      if ((rc = lin(s->LN, T2, C, Wd + L.qkv, 3 * C, s->QKV, EPI_NONE, nullptr, nullptr))) return rc;
+      rope_kernel<<<dim3(T2, 1), 256, 0, st>>>(s->QKV, m->rope, T2, m->rope_T2, C, H, pos0, kr, vr, s->R);
+      attn_kernel<<<dim3((T2 + 7) / 8, H, 1), 256, asm_bytes, st>>>(s->QKV, s->ATT, T2, C, H, c.window, pos0, kr, vr, s->R);
+      MCK(cudaGetLastError());
+      if ((rc = lin(s->ATT, T2, C, Wd + L.wo, C, x, EPI_RES_SCALE, x, Wd + L.ls1))) return rc;
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln2w, Wd + L.ln2b, s->LN, (long long)T2, C, c.norm_eps);
+      if ((rc = lin(s->LN, T2, C, Wd + L.fc1, FF, s->HID, EPI_GELU, nullptr, nullptr))) return rc;
+      if ((rc = lin(s->HID, T2, FF, Wd + L.fc2, C, x, EPI_RES_SCALE, x, Wd + L.ls2))) return rc;
+    }
+  }
+  // ---- SEANet decoder over [context | chunk] buffers
+  TailShift ts{};
+  auto carry = [&](void* base, int row_bytes, int ctx, long long rows) {
+    ts.base[ts.n] = base;
+    ts.row_bytes[ts.n] = row_bytes;
+    ts.ctx[ts.n] = ctx;
+    ts.rows[ts.n] = (int)rows;
+    ++ts.n;
+  };
+  long long Tn = T2;
+  int ch = c.num_filters << c.n_ratios;
+  const int kr3 = c.res_kernel - 1;
+  if (!tcm) {
+    float* a0 = reinterpret_cast<float*>(s->A0);
+    if ((rc = conv(s->XC, Tn, C, c.kernel, Wd + m->c0w, Wd + m->c0b, ch, ch, a0 + (size_t)ch, 0, EPI_NONE, nullptr))) return rc;
+    carry(s->XC, C * 4, k0, Tn);
+    carry(a0, ch * 4, 1, Tn);
+    const float* cur = a0;  // [1 ctx row | Tn rows]
+    for (size_t si = 0; si < m->stages.size(); ++si) {
+      const sopro_mimi::Stage& S = m->stages[si];
+      const bool last = si + 1 == m->stages.size();
+      const int hid = S.cout / c.compress, ctx_o = last ? c.last_kernel - 1 : 1;
+      float* z = reinterpret_cast<float*>(s->Z[si]);
+      float* o = reinterpret_cast<float*>(s->O[si]);
+      if ((rc = conv(cur, Tn, S.cin, 2, Wd + S.tw, Wd + S.tb, S.ratio * S.cout, S.cout, z + (size_t)kr3 * S.cout, 1, EPI_NONE, nullptr))) return rc;
+      Tn *= S.ratio;
+      if ((rc = conv(z, Tn, S.cout, c.res_kernel, Wd + S.r1w, Wd + S.r1b, hid, hid, s->Hs[si], 1, EPI_NONE, nullptr))) return rc;
+      if ((rc = conv(s->Hs[si], Tn, hid, 1, Wd + S.r2w, Wd + S.r2b, S.cout, S.cout, o + (size_t)ctx_o * S.cout, 1, EPI_RES,
+                     z + (size_t)kr3 * S.cout)))
+        return rc;
+      carry(z, S.cout * 4, kr3, Tn);
+      carry(o, S.cout * 4, ctx_o, Tn);
+      cur = o;
+      ch = S.cout;
+    }
+    const int lk = c.last_kernel - 1;
+    final_conv_kernel<<<dim3((unsigned)((Tn + 255) / 256), 1), 256, 0, st>>>(cur + (size_t)lk * ch, Wd + m->lw, Wd + m->lb, wav, Tn, ch,
+                                                                              c.last_kernel, -lk);
+    MCK(cudaGetLastError());
+  } else {
+    if (!tc::supported(ch, c.kernel * C, C) || c.num_filters % 8 || c.last_kernel > 8)
+      return mfail(SOPRO_ERR_UNSUPPORTED, "streaming tensor-core mode: unsupported conv0 / final conv geometry (use SOPRO_MIMI_FP32)");
+    const long long n4 = (long long)T2 * C / 4;
+    cast_bf16_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, s->XCh + (size_t)k0 * C, n4);
+    MCK(cudaGetLastError());
+    __nv_bfloat16* a0 = reinterpret_cast<__nv_bfloat16*>(s->A0);
+    if ((rc = tcg(s->XCh, Tn, C, c.kernel, Wh + m->c0w_h, Wd + m->c0b, ch, ch, tc::EPI_NONE, nullptr, nullptr, nullptr, a0 + (size_t)ch, 1)))
+      return rc;
+    carry(s->XCh, C * 2, k0, Tn);
+    carry(a0, ch * 2, 1, Tn);
+    const __nv_bfloat16* cur = a0;
+    for (size_t si = 0; si < m->stages.size(); ++si) {
+      const sopro_mimi::Stage& S = m->stages[si];
+      const bool last = si + 1 == m->stages.size();
+      const int hid = S.cout / c.compress, NT = S.ratio * S.cout, ctx_o = last ? c.last_kernel - 1 : 1;
+      if (!tc::supported(NT, 2 * S.cin, S.cin) || !tc::supported(hid, c.res_kernel * S.cout, S.cout) || !tc::supported(S.cout, hid, hid) ||
+          !tc::resblock_supported(hid, S.cout) || (S.cout * c.res_kernel) % 64)
+        return mfail(SOPRO_ERR_UNSUPPORTED, "streaming tensor-core mode: unsupported geometry at stage %zu (use SOPRO_MIMI_FP32)", si);
+      __nv_bfloat16* zh = reinterpret_cast<__nv_bfloat16*>(s->Z[si]);
+      __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(s->O[si]);
+      if ((rc = tcg(cur, Tn, S.cin, 2, Wh + S.tw_h, Wd + S.tb, NT, S.cout, tc::EPI_NONE, nullptr, nullptr, s->Zf[si], zh + (size_t)kr3 * S.cout, 1)))
+        return rc;
+      Tn *= S.ratio;
+      tc::ResOp ro{};
+      ro.bias1 = Wd + S.r1b;
+      ro.bias2 = Wd + S.r2b;
+      ro.Z = s->Zf[si];
+      ro.out_f32 = nullptr;
+      ro.out_bf16 = oh + (size_t)ctx_o * S.cout;
+      ro.M = (int)Tn;
+      ro.Min = (int)Tn + kr3;
+      ro.taps = c.res_kernel;
+      ro.pad = 0;
+      ro.out_elu = 1;
+      cudaError_t fe = tc::launch_resblock(zh, Wh + S.r1w_h, Wh + S.r2w_h, hid, ro, 1, st);
+      if (fe != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "fused ResnetBlock (stream, stage %zu): %s", si, cudaGetErrorString(fe));
+      carry(zh, S.cout * 2, kr3, Tn);
+      carry(oh, S.cout * 2, ctx_o, Tn);
+      cur = oh;
+      ch = S.cout;
+    }
+    const int lk = c.last_kernel - 1, per = 256 - lk;
+    final_conv_h_kernel<<<dim3((unsigned)((Tn + per - 1) / per), 1), 256, (size_t)(c.last_kernel * 256 + c.last_kernel * ch) * 4, st>>>(
+        cur + (size_t)lk * ch, Wd + m->lw, Wd + m->lb, wav, Tn, ch, c.last_kernel, -lk);
+    MCK(cudaGetLastError());
+  }
+  tail_shift_kernel<<<ts.n, 256, 16384, st>>>(ts);
+  MCK(cudaGetLastError());
+  s->frames += n;
+  return SOPRO_OK;
+}
+}  // namespace
+
 extern "C" {
+
+int sopro_mimi_stream_create(sopro_mimi_t* m, int max_chunk_frames, sopro_mimi_stream_t** out) {
+  if (!m || !out) return mfail(SOPRO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (max_chunk_frames < 1 || max_chunk_frames > 256) return mfail(SOPRO_ERR_INVALID, "max_chunk_frames must be in [1, 256]");
+  MCK(cudaSetDevice(m->device));
+  sopro_mimi_stream* s = new sopro_mimi_stream();
+  s->m = m;
+  s->max_n = max_chunk_frames;
+  s->precision = m->precision;
+  s->R = (m->cfg.window + 2 * max_chunk_frames + 7) / 8 * 8;
+  stream_layout(s, nullptr);
+  if ((size_t)(m->cfg.kernel - 1) * m->cfg.hidden * 4 > 16384) {
+    delete s;
+    return mfail(SOPRO_ERR_UNSUPPORTED, "conv context rows exceed the tail-shift staging buffer");
+  }
+  cudaError_t e = cudaMalloc(&s->slab, s->slab_bytes);
+  if (e != cudaSuccess) {
+    delete s;
+    return mfail(SOPRO_ERR_CUDA, "stream state %zu MB: %s", s->slab_bytes >> 20, cudaGetErrorString(e));
+  }
+  stream_layout(s, s->slab);
+  e = cudaMemset(s->slab, 0, s->state_bytes);
+  if (e != cudaSuccess) {
+    cudaFree(s->slab);
+    delete s;
+    return mfail(SOPRO_ERR_CUDA, "stream state init: %s", cudaGetErrorString(e));
+  }
+  *out = s;
+  return SOPRO_OK;
+}
+
+int sopro_mimi_stream_destroy(sopro_mimi_stream_t* s) {
+  if (!s) return SOPRO_OK;
+  cudaSetDevice(s->m->device);
+  cudaFree(s->slab);
+  cudaFree(s->codes_dev);
+  delete s;
+  return SOPRO_OK;
+}
+
+int sopro_mimi_stream_reset(sopro_mimi_stream_t* s, void* stream) {
+  if (!s) return mfail(SOPRO_ERR_INVALID, "null argument");
+  MCK(cudaSetDevice(s->m->device));
+  if (s->precision != s->m->precision) {  // the buffers are laid out per arithmetic mode
+    s->precision = s->m->precision;
+    size_t old = s->slab_bytes;
+    stream_layout(s, nullptr);
+    if (s->slab_bytes > old) {
+      MCK(cudaStreamSynchronize(reinterpret_cast<cudaStream_t>(stream)));
+      cudaFree(s->slab);
+      s->slab = nullptr;
+      MCK(cudaMalloc(&s->slab, s->slab_bytes));
+    }
+    stream_layout(s, s->slab);
+  }
+  MCK(cudaMemsetAsync(s->slab, 0, s->state_bytes, reinterpret_cast<cudaStream_t>(stream)));
+  s->frames = 0;
+  return SOPRO_OK;
+}
+
+int64_t sopro_mimi_stream_frames(const sopro_mimi_stream_t* s) { return s ? s->frames : -1; }
+
+int sopro_mimi_decode_step(sopro_mimi_stream_t* s, const int32_t* codes, int n, float* wav, void* stream) {
+  if (!s || !codes || !wav) return mfail(SOPRO_ERR_INVALID, "null argument");
+  if (n < 1) return mfail(SOPRO_ERR_INVALID, "n must be >= 1");
+  if (s->precision != s->m->precision)
+    return mfail(SOPRO_ERR_STATE, "the decoder's precision changed since this stream started: call sopro_mimi_stream_reset");
+  if (2 * (s->frames + n) > 0x3fffffffLL) return mfail(SOPRO_ERR_INVALID, "stream too long");
+  MCK(cudaSetDevice(s->m->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t hop = sopro_mimi_samples_per_frame(s->m);
+  for (int done = 0; done < n; done += s->max_n) {  // codes are [n_q][n]: a sub-chunk starts at column `done`
+    const int k = std::min(s->max_n, n - done);
+    const int rc = stream_step(s, codes + done, k, n, wav + (size_t)done * hop, st);
+    if (rc) return rc;
+  }
+  return SOPRO_OK;
+}
+
+int sopro_mimi_decode_step_host(sopro_mimi_stream_t* s, const int32_t* codes_host, int n, float* wav_host, void* stream) {
+  if (!s || !codes_host || !wav_host) return mfail(SOPRO_ERR_INVALID, "null argument");
+  if (n < 1 || n > 65536) return mfail(SOPRO_ERR_INVALID, "n must be in [1, 65536]");
+  const sopro_mimi_config_t& c = s->m->cfg;
+  for (size_t i = 0; i < (size_t)n * c.n_q; ++i)
+    if (codes_host[i] < 0 || codes_host[i] >= c.vocab)
+      return mfail(SOPRO_ERR_INVALID, "code %d at flat index %zu is outside [0, %d)", codes_host[i], i, c.vocab);
+  MCK(cudaSetDevice(s->m->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t nc = (size_t)n * c.n_q, nw = (size_t)n * (size_t)sopro_mimi_samples_per_frame(s->m);
+  cudaFree(s->codes_dev);
+  s->codes_dev = nullptr;
+  MCK(cudaMalloc(&s->codes_dev, nc * 4 + nw * 4));
+  s->wav_dev = reinterpret_cast<float*>(s->codes_dev + nc);
+  MCK(cudaMemcpyAsync(s->codes_dev, codes_host, nc * 4, cudaMemcpyHostToDevice, st));
+  const int rc = sopro_mimi_decode_step(s, s->codes_dev, n, s->wav_dev, stream);
+  if (rc) return rc;
+  MCK(cudaMemcpyAsync(wav_host, s->wav_dev, nw * 4, cudaMemcpyDeviceToHost, st));
+  MCK(cudaStreamSynchronize(st));
+  return SOPRO_OK;
+}
+
+}  // extern "C"
+
+extern "C" {
+
+int sopro_mimi_check(sopro_mimi_t* m, void* stream) {
+  if (!m) return mfail(SOPRO_ERR_INVALID, "null argument");
+  MCK(cudaSetDevice(m->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int flag = 0;
+  MCK(cudaMemcpyAsync(&flag, m->bad_code, 4, cudaMemcpyDeviceToHost, st));
+  MCK(cudaMemsetAsync(m->bad_code, 0, 4, st));
+  MCK(cudaStreamSynchronize(st));
+  if (flag) return mfail(SOPRO_ERR_INVALID, "a decode since the last check read a code outside [0, %d) (clamped)", m->cfg.vocab);
+  return SOPRO_OK;
+}
 
 int sopro_mimi_set_graphs(sopro_mimi_t* m, int enabled) {
   if (!m) return mfail(SOPRO_ERR_INVALID, "null argument");
@@ -1000,8 +1441,12 @@ int sopro_mimi_decode_host(sopro_mimi_t* m, const int32_t* codes_host, int B, in
   if (!m || !codes_host || !wav_host) return mfail(SOPRO_ERR_INVALID, "null argument");
   MCK(cudaSetDevice(m->device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (B < 1 || T < 1) return mfail(SOPRO_ERR_INVALID, "B and T must be >= 1");
   const size_t nc = (size_t)B * m->cfg.n_q * T;
   const size_t nw = (size_t)B * T * sopro_mimi_samples_per_frame(m);
+  for (size_t i = 0; i < nc; ++i)
+    if (codes_host[i] < 0 || codes_host[i] >= m->cfg.vocab)
+      return mfail(SOPRO_ERR_INVALID, "code %d at flat index %zu is outside [0, %d)", codes_host[i], i, m->cfg.vocab);
   if (m->codes_cap < nc * 4 + nw * 4) {
     cudaFree(m->codes_dev);
     m->codes_dev = nullptr;

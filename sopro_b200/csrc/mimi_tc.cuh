@@ -323,6 +323,7 @@ struct ResOp {
   float* out_f32;      // [B][M][2*HID] or null
   __nv_bfloat16* out_bf16;  // [B][M][2*HID] or null, through ELU when out_elu
   int M, taps, pad, out_elu, stages;
+  int Min;  // rows of the bf16 input X (0 = M; streaming: M + taps - 1 with pad = 0, the context rows in front)
 };
 
 template <int HID>
@@ -785,7 +786,7 @@ inline cudaError_t launch_resblock_t(const void* X, const void* W1, const void* 
   const int cout = Cfg::kCout, K1 = op.taps * cout, nk = K1 / kBK;
   op.stages = nk < Cfg::kMaxStages ? nk : Cfg::kMaxStages;
   CUtensorMap tmA, tmW1, tmW2;
-  if (!make_act_map(&tmA, X, B, op.M, cout) || !make_weight_map(&tmW1, W1, HID, K1, HID) ||
+  if (!make_act_map(&tmA, X, B, op.Min > 0 ? op.Min : op.M, cout) || !make_weight_map(&tmW1, W1, HID, K1, HID) ||
       !make_weight_map(&tmW2, W2, cout, HID, cout, Cfg::kBKH))
     return cudaErrorInvalidValue;
   dim3 grid((unsigned)((op.M + kBM - 1) / kBM), (unsigned)B);

@@ -13,6 +13,7 @@ additionally accepts ``seed=`` / ``generator=`` (an extension) to leave the glob
 from __future__ import annotations
 
 import os
+import threading
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
 import torch
@@ -32,6 +33,32 @@ def center_crop_tokens(ref_tq: torch.Tensor, win_frames: int) -> torch.Tensor:
         return ref_tq
     s = (T - win_frames) // 2
     return ref_tq[s: s + win_frames]
+
+
+def _complete_state_dict(cfg: SoproTTSConfig, sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """The reference loads with load_state_dict(strict=False) (model.py:443-446): tensors a checkpoint omits keep their
+    module-init values.  The known omittable ones get those defaults here; anything else missing is ONE explicit error
+    at construction instead of a KeyError deep inside the first synthesize call."""
+    from .weights import param_specs
+
+    Q = int(cfg.num_codebooks)
+    tv = int(sd["text_enc.embed.emb.weight"].shape[0]) if "text_enc.embed.emb.weight" in sd else 0
+    specs = param_specs(cfg, tv)
+    out = dict(sd)
+    missing = []
+    for name, (shape, _kind, _fan) in specs.items():
+        if name in out:
+            continue
+        if name in ("ref_cb_weights", "token2sv.cb_weights"):  # model.py:113-117, nn/speaker.py:22-23
+            out[name] = torch.linspace(1.0, 0.1, Q)
+        elif name == "nar_prev_cb_weights" or name.startswith("nar.head_id_emb."):  # model.py:70-72, nn/nar.py:79 (zeros)
+            out[name] = torch.zeros(shape)
+        else:
+            missing.append(name)
+    if missing:
+        raise KeyError(f"checkpoint is missing {len(missing)} tensor(s) the engine needs: {missing[:12]}"
+                       + (" ..." if len(missing) > 12 else ""))
+    return out
 
 
 class _Noise:
@@ -80,6 +107,7 @@ class SoproModel:
         if dev.type != "cuda":
             raise RuntimeError("sopro_b200 runs on CUDA devices only (sm_100a); there is no CPU fallback")
         self.cfg = cfg
+        state_dict = _complete_state_dict(cfg, state_dict)
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.eos_id = int(cfg.codebook_size)
         self.weight_dtype = weight_dtype
@@ -90,7 +118,11 @@ class SoproModel:
                    if not k.startswith(skip) and v.is_floating_point()}
         self.text_pos = P.sinusoid_table(int(cfg.max_text_len) + 8, int(cfg.d_model), self.device)
         self.frame_pos = P.sinusoid_table(int(cfg.pos_emb_max) + 8, int(cfg.d_model), self.device)
-        self._sessions: Dict[Tuple[int, int, int], ArSession] = {}
+        # AR sessions are CHECKED OUT per generator / call and returned when it ends (ar_stream is a suspended
+        # generator: two interleaved streams must never share a session's device state)
+        self._sessions: Dict[Tuple[int, int, int], List[ArSession]] = {}
+        self._sessions_busy: set = set()
+        self._sessions_lock = threading.Lock()
         self._prep_graphs: Dict[tuple, tuple] = {}
         self._prep_seen: Dict[tuple, int] = {}
         self._nar_cache: dict = {}
@@ -108,13 +140,30 @@ class SoproModel:
     def eval(self):
         return self
 
-    def _session(self, batch: int, steps: int, text_len: int) -> ArSession:
+    def _checkout(self, batch: int, steps: int, text_len: int) -> ArSession:
+        """An idle session of this geometry (a fresh one when every cached one is in use); pair with _release."""
         key = (int(batch), int(steps), (int(text_len) + 63) // 64 * 64)
-        if key not in self._sessions:
-            if len(self._sessions) >= 8:
-                self._sessions.pop(next(iter(self._sessions))).close()
-            self._sessions[key] = self.engine.session(*key)
-        return self._sessions[key]
+        with self._sessions_lock:
+            for ses in self._sessions.get(key, []):
+                if id(ses) not in self._sessions_busy:
+                    self._sessions_busy.add(id(ses))
+                    return ses
+            # evict idle sessions of other geometries beyond 8 cached (never one a live generator holds)
+            idle = [(k, x) for k, v in self._sessions.items() for x in v if id(x) not in self._sessions_busy and k != key]
+            total = sum(len(v) for v in self._sessions.values())
+            while total >= 8 and idle:
+                k, x = idle.pop(0)
+                self._sessions[k].remove(x)
+                x.close()
+                total -= 1
+            ses = self.engine.session(*key)
+            self._sessions.setdefault(key, []).append(ses)
+            self._sessions_busy.add(id(ses))
+            return ses
+
+    def _release(self, ses: ArSession) -> None:
+        with self._sessions_lock:
+            self._sessions_busy.discard(id(ses))
 
     # ---- prefill (torch)
     @torch.no_grad()
@@ -197,9 +246,17 @@ class SoproModel:
     def _sampling(self, top_p, temperature, anti_loop, loop_streak, recovery_top_p, recovery_temp, min_gen_frames,
                   stop_on_first_eos) -> Sampling:
         mg = int(min_gen_frames if min_gen_frames is not None else self.cfg.min_gen_frames)
+        # top_p=None is legal in the reference (sampling.py:69: `top_p is not None and top_p < 1.0`) == no top-p
+        top_p = 1.0 if top_p is None else top_p
+        recovery_top_p = 1.0 if recovery_top_p is None else recovery_top_p
         return Sampling(top_p=float(top_p), temperature=float(temperature), recovery_top_p=float(recovery_top_p),
                         recovery_temp=float(recovery_temp), repetition_penalty=1.1, top_k=50, anti_loop=bool(anti_loop),
                         loop_streak=int(loop_streak), min_gen_frames=min(mg, 2 ** 31 - 1), stop_on_first_eos=stop_on_first_eos)
+
+    def _noise_cols(self, samp: Sampling) -> int:
+        """Exp(1) draws per step the kernel reads: the top_k sorted ranks with top-p (sampling.py:83-84), every
+        vocabulary id on the unsorted multinomial branch taken when top_p >= 1 (sampling.py:88-93)."""
+        return int(samp.top_k) if (samp.top_p < 1.0 and samp.recovery_top_p < 1.0) else int(self.cfg.ar_vocab())
 
     @torch.no_grad()
     def ar_stream(self, prep: Dict[str, torch.Tensor], *, max_frames: int, top_p: float = 0.9, temperature: float = 1.05,
@@ -215,20 +272,21 @@ class SoproModel:
             raise ValueError(f"cond_ar has {cond.size(1)} rows, need max_frames+1 = {steps}")
         L = int(txt.size(1))
         noise = _Noise(steps, self.cfg.ar_vocab(), seed, generator)
-        ses = self._session(1, steps, L)
         samp = self._sampling(top_p, temperature, anti_loop, loop_streak, recovery_top_p, recovery_temp, min_gen_frames, False)
-        # the session keeps a pointer to this device tape; each launch's rows are drawn and uploaded just before it
-        tape = torch.zeros(1, steps, samp.top_k, device=self.device)
-        ses.begin(cond[:, :steps], txt, [L], tape, samp)
+        nk = self._noise_cols(samp)
+        ses = self._checkout(1, steps, L)
         per = steps if launch_frames <= 0 else int(launch_frames)
         t = 0
         used = 0
         try:
+            # the session keeps a pointer to this device tape; each launch's rows are drawn and uploaded just before it
+            tape = torch.zeros(1, steps, nk, device=self.device)
+            ses.begin(cond[:, :steps], txt, [L], tape, samp)
             while t < steps:
                 lo = noise.drawn
                 blk = noise.rows(t + per)
                 if blk.size(0):
-                    tape[0, lo: lo + blk.size(0)].copy_(blk[:, : samp.top_k])
+                    tape[0, lo: lo + blk.size(0)].copy_(blk[:, :nk])
                 ses.run(per)
                 toks, n, done = ses.read()
                 upto = int(n[0])
@@ -240,6 +298,7 @@ class SoproModel:
                 if done[0] or upto < min(steps, ses.position):
                     break
         finally:
+            self._release(ses)
             noise.settle(used)
 
     @torch.no_grad()
@@ -257,18 +316,22 @@ class SoproModel:
         txt = torch.zeros(B, Ls, D, device=self.device)
         for i, p in enumerate(preps):
             txt[i, : lens[i]] = p["txt_seq"][0]
+        samp = self._sampling(top_p, temperature, anti_loop, 8, 0.85, 1.2, min_gen_frames, stop_on_first_eos)
+        nk = self._noise_cols(samp)
         if seeds is None:  # one shared generator: utterance after utterance
-            tapes = [_Noise(steps, V, None, None).tape[:, :50] for _ in range(B)]
+            tapes = [_Noise(steps, V, None, None).tape[:, :nk] for _ in range(B)]
         else:  # independent private generators: draw them on a few host threads (the draws release the GIL)
             from concurrent.futures import ThreadPoolExecutor
 
             with ThreadPoolExecutor(max_workers=min(B, max(1, len(os.sched_getaffinity(0))))) as ex:
-                tapes = list(ex.map(lambda sd_: _Noise(steps, V, int(sd_), None).tape[:, :50].contiguous(), seeds))
-        ses = self._session(B, steps, Ls)
-        samp = self._sampling(top_p, temperature, anti_loop, 8, 0.85, 1.2, min_gen_frames, stop_on_first_eos)
-        ses.begin(cond, txt, lens, torch.stack(tapes).contiguous(), samp)
-        ses.run()
-        toks, n, _ = ses.read()
+                tapes = list(ex.map(lambda sd_: _Noise(steps, V, int(sd_), None).tape[:, :nk].contiguous(), seeds))
+        ses = self._checkout(B, steps, Ls)
+        try:
+            ses.begin(cond, txt, lens, torch.stack(tapes).contiguous(), samp)
+            ses.run()
+            toks, n, _ = ses.read()
+        finally:
+            self._release(ses)
         return [toks[i, : n[i]].tolist() for i in range(B)]
 
     @torch.no_grad()

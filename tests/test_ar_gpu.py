@@ -199,14 +199,35 @@ def test_batch_equals_each_utterance_alone(team):
         assert toks[i, : nn[i]].tolist() == want[i], f"utterance {i} (L={lens[i]})"
 
 
+def _near_tie_margin(sd, cfg, cond_i, txt_i, samp, tape, want, t):
+    """Relative distance to the nearest decision boundary of the oracle's sampler at step `t` (oracle history):
+    the two best ratios p_sorted[j] / q[j] of the draw, and the top-p cut (cum[j] vs top_p)."""
+    logits, rec = [], []
+    gen = O.ar_stream(sd, cfg, cond_i, txt_i, torch.ones(1, txt_i.size(1), dtype=torch.bool), max_frames=t, sampling=samp,
+                      noise_tv=tape, logits_out=logits, recovery_out=rec)
+    for _ in gen:
+        pass
+    top_p, temp = (samp.recovery_top_p, samp.recovery_temp) if t in rec else (samp.top_p, samp.temperature)
+    tr = {}
+    O.sample_token(logits[t].view(1, 1, -1), want[:t], top_p=top_p, top_k=samp.top_k, temperature=temp,
+                   repetition_penalty=samp.repetition_penalty, noise_v=tape[t], trace=tr)
+    sp = tr["sorted_probs"][:50].double()
+    r = (sp / tape[t][:50].double()).sort(descending=True).values
+    draw = float((r[0] - r[1]) / r[0])
+    cut = float((tr["cum"][:50].double() - top_p).abs().min())
+    return min(draw, cut)
+
+
 def test_full_size_batch64_properties():
-    """BASELINE.json's batch-64 configuration at full size (64 utterances x 401 steps, L=52, bf16 weight storage).
-    25,664 sampled frames cannot all sit clear of fp32 near-ties (the sampler is discontinuous in the logits and every
-    summation order, the reference's own MKL threading included, moves them by ~1e-6), so the full-size statement is:
+    """BASELINE.json's batch-64 configuration at full size (64 utterances x 401 steps, L=52, bf16 weight storage),
+    EVERY utterance against the CPU oracle:
     (1) the launch is deterministic and every utterance runs its full length;
-    (2) with the CPU oracle's tokens teacher-forced, the token the kernel samples at every one of the 401 steps is the
-        oracle's, for utterances taken from four different teams (at most one near-tie flip per utterance tolerated);
-    (3) free-running, those utterances follow the oracle from the first frame (a flip, if any, is reported)."""
+    (2) with the oracle's tokens teacher-forced, the token the kernel samples at each of the 64 x 401 steps is the
+        oracle's.  The sampler is discontinuous in the logits, so a flip is tolerated only when the oracle itself sits
+        within 1e-5 (relative) of a decision boundary at that step (two candidates' p/q ratios, or the top-p cut), and
+        at most 2 such flips in the whole batch;
+    (3) free-running, every utterance equals the oracle for all 401 frames unless its first divergence is one of the
+        near-tie steps of (2)."""
     spec = AR_CASES["default_bf16"]
     cfg, sd, _ = ar_case_inputs(spec)
     eng = _engine(cfg, sd, "bf16", _wkey(spec))
@@ -214,7 +235,8 @@ def test_full_size_batch64_properties():
     D = int(cfg.d_model)
     cond = torch.stack([_unit(steps * D, 7000 + i).view(steps, D) for i in range(n)])
     txt = torch.stack([_unit(L * D, 7500 + i).view(L, D) for i in range(n)])
-    tapes = torch.stack([O.noise_tape(300 + i, steps, cfg.ar_vocab())[:, :50] for i in range(n)]).contiguous()
+    full_tapes = [O.noise_tape(300 + i, steps, cfg.ar_vocab()) for i in range(n)]
+    tapes = torch.stack([t[:, :50] for t in full_tapes]).contiguous()
     samp = O.ArSampling(min_gen_frames=10 ** 9)
     ses = eng.session(n, steps, L)
     out = []
@@ -226,30 +248,22 @@ def test_full_size_batch64_properties():
         assert (nn == steps).all()
     assert np.array_equal(out[0], out[1])
     assert len({tuple(r) for r in out[0].tolist()}) == n  # 64 different utterances
-    picked = (0, 9, 37, 63)
-    want = {}
-    for i in picked:
-        want[i] = O.ar_generate(sd, cfg, cond[i:i + 1], txt[i:i + 1], torch.ones(1, L, dtype=torch.bool), max_frames=steps - 1,
-                                sampling=samp, noise_tv=O.noise_tape(300 + i, steps, cfg.ar_vocab()))
-    forced = torch.from_numpy(out[0].astype(np.int32)).clone()
-    for i in picked:
-        forced[i] = torch.tensor(want[i], dtype=torch.int32)
+    want = [O.ar_generate(sd, cfg, cond[i:i + 1], txt[i:i + 1], torch.ones(1, L, dtype=torch.bool), max_frames=steps - 1,
+                          sampling=samp, noise_tv=full_tapes[i]) for i in range(n)]
+    forced = torch.tensor(want, dtype=torch.int32)
     ses.set_forced(forced)
     ses.begin(cond, txt, [L] * n, tapes, _sampling(samp, cfg))
     ses.run()
     sampled = ses.sampled().cpu().numpy()
     ses.set_forced(None)
-    report = []
-    for i in picked:
-        flips = [t for t in range(steps) if int(sampled[i, t]) != want[i][t]]
+    flips = [(i, t) for i in range(n) for t in range(steps) if int(sampled[i, t]) != want[i][t]]
+    margins = {(i, t): _near_tie_margin(sd, cfg, cond[i:i + 1], txt[i:i + 1], samp, full_tapes[i], want[i], t) for i, t in flips}
+    print("full-size report: teacher-forced flips (utterance, step) -> oracle boundary margin:", margins)
+    assert len(flips) <= 2, margins
+    assert all(m < 1e-5 for m in margins.values()), margins
+    for i in range(n):
         first = next((t for t in range(steps) if int(out[0][i, t]) != want[i][t]), None)
-        report.append((i, flips, first))
-        assert len(flips) <= 1, f"utterance {i}: teacher-forced mismatches at steps {flips}"
-    others = [i for i in range(n) if i not in picked]
-    assert np.array_equal(sampled[others], out[0][others])  # forcing a run with its own tokens changes nothing
-    free_equal = sum(1 for _i, _f, first in report if first is None)
-    print("full-size report (utterance, teacher-forced flips, first free-running divergence):", report)
-    assert free_equal >= 2, report
+        assert first is None or (i, first) in margins, f"utterance {i} diverges free-running at step {first} without a near-tie"
 
 
 def test_long_text_takes_the_streaming_attention_path():

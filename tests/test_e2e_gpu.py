@@ -125,3 +125,80 @@ def test_prepared_reference_roundtrips_through_torch_save():
         tts.prepare_reference()
     with pytest.raises(RuntimeError):
         tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"], ref_audio_path="x.wav")
+
+
+def test_stream_concat_equals_synthesize():
+    """Through the public API only.  (a) One chunk covering the whole utterance: stream() == synthesize() for the same
+    seed, sample for sample (same AR ids, the NAR refiner sees the same window, the stream decoder equals the one-shot
+    decode).  (b) Chunked: the AR ids are synthesize()'s; the NAR refiner is not causal, so (as in the reference,
+    streaming.py:81-104) a chunk's codes come from a window that ends at the chunk; the concatenated audio equals
+    decode_full of exactly those window-refined codes -- the stream decoder adds no error of its own."""
+    tts, _ = _tts()
+    cfg, sd, inp = e2e_inputs()
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    F = 25
+    tts.codec.engine.set_precision("fp32")
+    try:
+        full = tts.synthesize(TEXT, ref=ref, max_frames=F, seed=9, min_gen_frames=10 ** 9)
+        T = full.shape[-1] // 1920
+        one = list(tts.stream(TEXT, ref=ref, max_frames=F, seed=9, min_gen_frames=10 ** 9, chunk_frames=64))
+        assert len(one) == 1 and torch.equal(one[0].reshape(-1), full.reshape(-1))
+        chunks = list(tts.stream(TEXT, ref=ref, max_frames=F, seed=9, min_gen_frames=10 ** 9, chunk_frames=6))
+        audio = torch.cat(chunks, dim=1)
+        assert audio.shape[-1] == T * 1920
+        # the same windows through the public model API
+        ids = tts.encode_text(TEXT)
+        prep = tts.model.prepare_conditioning(ids, ref, max_frames=F, style_strength=cfg.style_strength)
+        toks = tts.model.generate_tokens(ids, ref, max_frames=F, style_strength=cfg.style_strength, seed=9, min_gen_frames=10 ** 9)
+        ar = toks[:, 0].tolist()
+        assert len(ar) == T
+        ctx, rows, emitted = tts.model.rf_nar(), [], 0
+        while emitted < T:
+            end = min(emitted + 6, T)
+            lo = max(0, emitted - ctx)
+            win = tts.model.nar_refine(prep["cond_ar"][:, lo:end], torch.tensor(ar[lo:end], device=tts.device).unsqueeze(0))[0]
+            rows.append(win[emitted - lo:])
+            emitted = end
+        emitted_codes = torch.cat(rows, dim=0)
+        assert emitted_codes[:, 0].tolist() == ar
+        assert torch.equal(audio.reshape(-1), tts.codec.decode_full(emitted_codes).reshape(-1))
+    finally:
+        tts.codec.engine.set_precision("bf16_tc")
+
+
+def test_interleaved_streams_do_not_share_ar_state():
+    """two suspended stream() generators (a server interleaving requests) must each equal their solo run."""
+    tts, _ = _tts()
+    cfg, sd, inp = e2e_inputs()
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    t2 = " ".join(str(5 * i + 1) for i in range(20))  # same token count -> same session geometry
+    solo_a = list(tts.stream(TEXT, ref=ref, max_frames=18, seed=21, min_gen_frames=10 ** 9))
+    solo_b = list(tts.stream(t2, ref=ref, max_frames=18, seed=22, min_gen_frames=10 ** 9))
+    ga = tts.stream(TEXT, ref=ref, max_frames=18, seed=21, min_gen_frames=10 ** 9)
+    gb = tts.stream(t2, ref=ref, max_frames=18, seed=22, min_gen_frames=10 ** 9)
+    mixa, mixb = [], []
+    for _ in range(max(len(solo_a), len(solo_b))):
+        for g, out in ((ga, mixa), (gb, mixb)):
+            c = next(g, None)
+            if c is not None:
+                out.append(c)
+    mid = tts.synthesize(TEXT, ref=ref, max_frames=12, seed=5, min_gen_frames=10 ** 9)  # a synthesize in between
+    assert mid.shape[-1] == 13 * 1920
+    assert len(mixa) == len(solo_a) and all(torch.equal(x, y) for x, y in zip(mixa, solo_a))
+    assert len(mixb) == len(solo_b) and all(torch.equal(x, y) for x, y in zip(mixb, solo_b))
+
+
+def test_no_top_p_takes_the_unsorted_multinomial_branch():
+    """top_p=1.0 / None (reference sampling.py:88-93: multinomial over vocabulary order, noise index = token id)."""
+    tts, _ = _tts()
+    cfg, sd, inp = e2e_inputs()
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    ids = tts.encode_text(TEXT)
+    F = 12
+    prep = tts.model.prepare_conditioning(ids, ref, max_frames=F, style_strength=cfg.style_strength)
+    for tp in (1.0, None):
+        got = [tok for _t, tok, _e in tts.model.ar_stream(prep, max_frames=F, top_p=tp, seed=31, min_gen_frames=10 ** 9, anti_loop=False)]
+        want = O.ar_generate(sd, cfg, prep["cond_ar"].cpu(), prep["txt_seq"].cpu(), torch.ones(1, prep["txt_seq"].size(1), dtype=torch.bool),
+                             max_frames=F, sampling=O.ArSampling(top_p=1.0, anti_loop=False, min_gen_frames=10 ** 9),
+                             noise_tv=O.noise_tape(31, F + 1, cfg.ar_vocab()))
+        assert got == want

@@ -159,3 +159,22 @@ def test_public_header_is_plain_c():
     hdr = os.path.join(ROOT, "include", "sopro_b200.h")
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_missing_checkpoint_tensors_get_reference_defaults_or_one_clear_error():
+    """The reference loads strict=False: omitted buffers keep their init values (model.py:113-117, 70-72; nn/nar.py:79)."""
+    from sopro_b200.config import SoproTTSConfig
+    from sopro_b200.model import _complete_state_dict
+    from sopro_b200.weights import synth_state_dict
+
+    cfg = SoproTTSConfig()
+    sd = synth_state_dict(cfg, text_vocab=64)
+    cut = {k: v for k, v in sd.items() if k not in ("ref_cb_weights", "nar_prev_cb_weights") and not k.startswith("nar.head_id_emb.")}
+    full = _complete_state_dict(cfg, cut)
+    assert torch.equal(full["ref_cb_weights"], torch.linspace(1.0, 0.1, int(cfg.num_codebooks)))
+    assert float(full["nar_prev_cb_weights"].abs().sum()) == 0.0
+    assert all(float(full[k].abs().sum()) == 0.0 for k in sd if k.startswith("nar.head_id_emb."))
+    del cut["ar.head.weight"], cut["cond_norm.weight"]
+    with pytest.raises(KeyError) as ei:
+        _complete_state_dict(cfg, cut)
+    assert "ar.head.weight" in str(ei.value) and "cond_norm.weight" in str(ei.value)

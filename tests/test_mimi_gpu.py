@@ -71,6 +71,18 @@ def test_full_size_decode_properties():
     eng.set_precision("bf16_tc")
     err = (big[..., : 2000 * 1920] - ref32).abs().max()
     assert float(err) <= 2e-2 * float(ref32.abs().max())
+    # against the CPU oracle directly: the decoder is causal, so the oracle's decode of the first 700 frames is the
+    # reference for frames [0, 700) of the 10k-frame waveform: the start [0, 300) and a mid-stream slice [400, 700)
+    # (past the 125-frame attention window) in both modes
+    want = M.mimi_decode(_ENG["sd"], codes[:, :, :700])
+    peak = float(want.abs().max())
+    for lo, hi in ((0, 300), (400, 700)):
+        sl = slice(lo * 1920, hi * 1920)
+        e_tc = float((big[..., sl].cpu() - want[..., sl]).abs().max())
+        e_32 = float((ref32[..., sl].cpu() - want[..., sl]).abs().max())
+        print(f"10k-frame decode vs oracle, frames [{lo},{hi}): tensor-core {e_tc / peak:.2e} of peak, fp32 {e_32 / peak:.2e} of peak")
+        assert e_tc <= 2e-2 * peak, (lo, hi, e_tc, peak)
+        assert e_32 <= 2e-4 * max(1.0, peak), (lo, hi, e_32, peak)
     batch = codes.view(1, 32, 25, 400).permute(2, 1, 0, 3).reshape(25, 32, 400).contiguous()
     wb = eng.decode(batch)
     for i in (0, 11, 24):
@@ -185,3 +197,82 @@ def test_decode_full_signature():
     codes_tq = torch.randint(0, 2048, (5, 32), generator=torch.Generator().manual_seed(4))
     wav = codec.decode_full(codes_tq)
     assert wav.shape == (1, 1, 5 * 1920) and wav.dtype == torch.float32
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16_tc"])
+def test_stream_decode_step_equals_the_full_decode(mode):
+    """sopro_mimi_decode_step carries the K/V rings and every conv's left context: chunks of ragged sizes (1 frame,
+    the default 6, 16, a 40-frame chunk that is split internally, ...) over 310 frames -- 620 transformer positions,
+    far past the 250-position window and past the ring's wrap-around -- concatenate to the one-shot decode.  fp32
+    mode: bit for bit (every output element is computed in the same order).  Tensor-core mode: the dense blocks are the
+    same tcgen05 tiles, only the attention core runs in fp32 on the ring; the stated tolerance is 4e-3 of the peak vs the
+    one-shot tensor-core decode and the mode's 2e-2 vs the fp32 oracle."""
+    eng, sd = _engine(mode)
+    T = 310
+    codes = torch.randint(0, 2048, (1, 32, T), generator=torch.Generator().manual_seed(77))
+    full = eng.decode(codes).reshape(1, -1)
+    st = eng.stream(16)
+    sizes, pos, parts = [1, 6, 6, 16, 3, 40, 6, 2, 64, 6], 0, []
+    i = 0
+    while pos < T:
+        n = min(sizes[i % len(sizes)], T - pos)
+        parts.append(st.step(codes[0, :, pos:pos + n]))
+        pos += n
+        i += 1
+    assert st.frames == T
+    got = torch.cat(parts, dim=1)
+    assert got.shape == full.shape
+    peak = float(full.abs().max())
+    err = float((got - full).abs().max())
+    print(f"stream vs one-shot [{mode}]: max err {err / peak:.2e} of peak")
+    if mode == "fp32":
+        assert torch.equal(got, full)
+    else:
+        assert err <= 4e-3 * peak, (err, peak)
+        want = M.mimi_decode(sd, codes[:, :, :150]).reshape(1, -1)
+        assert float((got[:, : 150 * 1920].cpu() - want).abs().max()) <= 2e-2 * float(want.abs().max())
+    # reset -> the same stream object decodes a new utterance from frame 0; host-buffer entry point
+    st.reset()
+    assert st.frames == 0
+    again = st.step_host(codes[0, :, :9].numpy())
+    one = eng.decode(codes[:, :, :9]).reshape(1, -1).cpu().numpy()
+    if mode == "fp32":
+        assert np.array_equal(again, one)
+    else:
+        assert float(np.abs(again - one).max()) <= 4e-3 * peak
+
+
+def test_two_streams_are_independent_and_state_is_per_stream():
+    eng, _ = _engine("fp32")
+    a = torch.randint(0, 2048, (32, 30), generator=torch.Generator().manual_seed(1))
+    b = torch.randint(0, 2048, (32, 30), generator=torch.Generator().manual_seed(2))
+    sa, sb = eng.stream(8), eng.stream(8)
+    outa, outb = [], []
+    for lo in range(0, 30, 6):  # interleaved
+        outa.append(sa.step(a[:, lo:lo + 6]))
+        outb.append(sb.step(b[:, lo:lo + 6]))
+    assert torch.equal(torch.cat(outa, 1), eng.decode(a.unsqueeze(0)).reshape(1, -1))
+    assert torch.equal(torch.cat(outb, 1), eng.decode(b.unsqueeze(0)).reshape(1, -1))
+
+
+def test_out_of_range_codes_are_reported_not_read():
+    """An uncut EOS id (2048) must not index past the codebook: the Python layer raises IndexError like the reference's
+    embedding lookup, the host C-ABI path returns an error, and the device path clamps + flags (sopro_mimi_check)."""
+    import ctypes as C
+
+    from sopro_b200 import _lib
+
+    eng, _ = _engine("fp32")
+    bad = torch.randint(0, 2048, (1, 32, 4))
+    bad[0, 3, 2] = 2048
+    with pytest.raises(IndexError):
+        eng.decode(bad)
+    with pytest.raises(_lib.SoproError):
+        eng.decode_host(bad.numpy())
+    dev = bad.to("cuda:0", torch.int32).contiguous()
+    wav = torch.empty(1, 1, 4 * 1920, device="cuda:0")
+    _lib.check(eng.lib.sopro_mimi_decode(eng._h, dev.data_ptr(), 1, 4, wav.data_ptr(), int(torch.cuda.current_stream().cuda_stream)))
+    with pytest.raises(_lib.SoproError):
+        eng.check()
+    eng.check()  # the flag is cleared by the failed check
+    assert bool(torch.isfinite(wav).all())
