@@ -283,6 +283,124 @@ int64_t sopro_mimi_stream_frames(const sopro_mimi_stream_t* s);        /* MimiDe
 int sopro_mimi_decode_step(sopro_mimi_stream_t* s, const int32_t* codes, int n, float* wav, void* stream);
 int sopro_mimi_decode_step_host(sopro_mimi_stream_t* s, const int32_t* codes_host, int n, float* wav_host, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * NAR refiner: SoproTTSModel.nar_refine (reference model.py:307-347) over NARSinglePass.forward_stage
+ * (nn/nar.py:89-116), NARStageAdapter (nn/nar.py:13-32), SSMLiteBlock.forward (nn/blocks.py:143-148) and
+ * CodebookEmbedding.sum_embed_subset (nn/embeddings.py:77-112).  Given the AR tokens (codebook 0) and the
+ * conditioning rows it fills codebooks 1..Q-1 stage by stage (argmax).  fp32 throughout: the ids equal the
+ * reference's.  HOST fp32 pointers in state_dict layouts; the engine uploads its own copy.
+ * ------------------------------------------------------------------------------------------------ */
+#define SOPRO_MAX_SSM_LAYERS 16
+#define SOPRO_NAR_MAX_STAGES 8
+#define SOPRO_NAR_MAX_CODEBOOKS 64
+
+typedef struct sopro_ssm_block_weights { /* SSMLiteBlock (nn/blocks.py:113-133) */
+  const float* norm_w;              /* norm.weight [D] */
+  const float *glu_w, *glu_b;       /* glu.pro [2D, D], [2D] */
+  const float *dw_w, *dw_b;         /* dw.dw [D, 1, k], [D] */
+  const float* ffn_norm_w;          /* ff.0.weight [D] */
+  const float *ffn_w1, *ffn_b1;     /* ff.1 [4D, D], [4D] */
+  const float *ffn_w2, *ffn_b2;     /* ff.3 [D, 4D], [D] */
+} sopro_ssm_block_weights_t;
+
+typedef struct sopro_nar_config {
+  int32_t d_model;        /* 384 */
+  int32_t n_layers;       /* cfg.n_layers_nar (6) */
+  int32_t kernel;         /* cfg.nar_kernel_size (11) */
+  int32_t dilation[SOPRO_MAX_SSM_LAYERS]; /* nn/nar.py:47-52 */
+  int32_t n_codebooks;    /* Q = 32 */
+  int32_t codebook_size;  /* V = 2048 */
+  int32_t head_dim;       /* cfg.nar_head_dim (256) */
+  int32_t adapter_hidden; /* 256 (nn/nar.py:14) */
+  int32_t n_stages;       /* non-empty stages of B, C, D, E (nn/nar.py:41-44) */
+  int32_t stage_first[SOPRO_NAR_MAX_STAGES]; /* first codebook of the stage; stages cover 1..Q-1 consecutively */
+  int32_t stage_count[SOPRO_NAR_MAX_STAGES];
+} sopro_nar_config_t;
+
+typedef struct sopro_nar_weights {
+  sopro_ssm_block_weights_t block[SOPRO_MAX_SSM_LAYERS];  /* nar.blocks.{i} */
+  const float* norm_w;                     /* nar.norm.weight [D] */
+  const float *pre_w, *pre_b;              /* nar.pre [Hn, D], [Hn] */
+  const float* stage_emb;                  /* nar.stage_emb.weight [n_stages, D] */
+  const float* adapter_norm_w;             /* nar.adapter.norm.weight [D] */
+  const float *adapter_w0, *adapter_b0;    /* nar.adapter.mlp.0 [256, D], [256] */
+  const float *adapter_w2, *adapter_b2;    /* nar.adapter.mlp.2 [2D, 256], [2D] */
+  const float* head_w[SOPRO_NAR_MAX_CODEBOOKS]; /* nar.heads.{stage}.{j}.weight [V, Hn], indexed by CODEBOOK (1..Q-1) */
+  const float* head_b[SOPRO_NAR_MAX_CODEBOOKS];
+  const float* head_id_emb[SOPRO_NAR_MAX_STAGES]; /* nar.head_id_emb.{stage}.weight [count, Hn] */
+  const float* mix[SOPRO_NAR_MAX_STAGES];         /* nar.mix.{stage} [2] (softmaxed, model.py:335-337) */
+  const float* prev_cb_weights;            /* nar_prev_cb_weights [Q] (model.py:70-72) */
+  const float* cb_embed;                   /* cb_embed.emb.weight [Q*V + 1, D] */
+} sopro_nar_weights_t;
+
+typedef struct sopro_nar sopro_nar_t;
+int sopro_nar_create(const sopro_nar_config_t* cfg, const sopro_nar_weights_t* host_weights, int device, sopro_nar_t** out);
+int sopro_nar_destroy(sopro_nar_t* n);
+/* cond: rows [b][t][d_model] f32 (device), utterance b starting at cond + b*cond_batch_stride (floats) -- cond_ar[:, :T]
+ * of the prefill; rvq1 [B, Tmax] i32 (device): the AR tokens; lens [B] i32 (device) or NULL: valid frames per
+ * utterance (the refiner is not causal: rows >= lens[b] are padding and act as the zero padding of the convs);
+ * codes [B, Tmax, Q] i32 (device) out: codebook 0 = rvq1, 1..Q-1 refined (rows >= lens[b] are undefined). */
+int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_stride, const int32_t* rvq1, const int32_t* lens,
+                     int B, int Tmax, int32_t* codes, void* stream);
+/* test hook (teacher forcing): when non-NULL, every stage conditions on the previous codebooks of forced_codes
+ * [B, Tmax, Q] i32 (device) instead of on its own argmax results, so one near-tie flip cannot cascade. */
+int sopro_nar_set_forced(sopro_nar_t* n, const int32_t* forced_codes);
+
+/* ------------------------------------------------------------------------------------------------
+ * Prefill: SoproTTSModel.prepare_conditioning (reference model.py:172-216) for B texts that share one prepared
+ * reference voice: TextEncoder (nn/text.py:16-44) -> txt_seq, txt_pool; base = txt_pool + frame sinusoid;
+ * SpeakerFiLM (nn/speaker.py:64-85); RefXAttnStack with cached K/V (nn/ref.py:57-108, 111-160); cond_norm -> cond_ar.
+ * fp32 (cond_ar / txt_seq feed the id-exact AR kernel).  HOST fp32 weight pointers, state_dict layouts.
+ * prepare_reference (once per voice: Token2SV, reference encoder, K/V projections) stays with the caller.
+ * ------------------------------------------------------------------------------------------------ */
+#define SOPRO_PREFILL_MAX_REF_LAYERS 8
+
+typedef struct sopro_prefill_config {
+  int32_t d_model;        /* 384 */
+  int32_t n_layers_text;  /* cfg.n_layers_text (2) */
+  int32_t text_kernel;    /* 7 (nn/text.py:24) */
+  int32_t text_vocab;     /* rows of text_enc.embed.emb.weight */
+  int32_t sv_dim;         /* cfg.sv_student_dim (192) */
+  int32_t ref_layers;     /* cfg.ref_xattn_layers (3) */
+  int32_t ref_heads;      /* cfg.ref_xattn_heads (2) */
+  float ref_gmax;         /* cfg.ref_xattn_gmax */
+  int32_t max_text_len;   /* rows of text_pos */
+  int32_t max_frames_pos; /* rows of frame_pos */
+} sopro_prefill_config_t;
+
+typedef struct sopro_prefill_ref_layer {
+  const float* nq_w;      /* ref_xattn.blocks.{i}.nq.weight [D] */
+  const float* q_w;       /* ...q_proj.weight [D, D] */
+  const float* o_w;       /* ...out_proj.weight [D, D] */
+  float gate;             /* ...gate (scalar; gmax * tanh(gate) is applied, nn/ref.py:105) */
+} sopro_prefill_ref_layer_t;
+
+typedef struct sopro_prefill_weights {
+  const float* text_emb;   /* text_enc.embed.emb.weight [vocab, D] */
+  const float* text_pos;   /* sinusoid table [max_text_len, D] (nn/embeddings.py:11-25; a non-persistent buffer) */
+  const float* frame_pos;  /* sinusoid table [max_frames_pos, D] */
+  sopro_ssm_block_weights_t text_block[SOPRO_MAX_SSM_LAYERS]; /* text_enc.layers.{i} */
+  const float* text_norm_w;             /* text_enc.norm.weight */
+  const float *film_w0, *film_b0;       /* spk_film.mlp.0 [D, sv], [D] */
+  const float *film_w2, *film_b2;       /* spk_film.mlp.2 [2D, D], [2D] */
+  const float *film_norm_w, *film_norm_b; /* spk_film.norm (LayerNorm) */
+  sopro_prefill_ref_layer_t ref_layer[SOPRO_PREFILL_MAX_REF_LAYERS];
+  const float* cond_norm_w;             /* cond_norm.weight */
+} sopro_prefill_weights_t;
+
+typedef struct sopro_prefill sopro_prefill_t;
+int sopro_prefill_create(const sopro_prefill_config_t* cfg, const sopro_prefill_weights_t* host_weights, int device,
+                         sopro_prefill_t** out);
+int sopro_prefill_destroy(sopro_prefill_t* p);
+/* All pointers below are DEVICE pointers.  text_ids [B, Lmax] i32 (padded), text_len [B] i32; sv [B or 1, sv_dim]
+ * (sv_shared != 0: one speaker vector for the batch); ref_k / ref_v: HOST arrays of ref_layers device pointers to the
+ * prepared reference's cached K / V [H, Tr, D/H] (PreparedReference.ref_kv_caches, model.py:45-50);
+ * n_frames = max_frames + 1.  Outputs: txt_seq [B, Lmax, D] (rows >= text_len[b] undefined), txt_pool [B, D],
+ * cond_ar [B, n_frames, D] -- the `prep` dict of model.py:210-216. */
+int sopro_prefill_run(sopro_prefill_t* p, const int32_t* text_ids, const int32_t* text_len, int B, int Lmax, const float* sv,
+                      int sv_shared, const float* const* ref_k, const float* const* ref_v, int Tr, float style_strength,
+                      int n_frames, float* txt_seq, float* txt_pool, float* cond_ar, void* stream);
+
 /* test hook: one tensor-core implicit GEMM (no reference counterpart).  X bf16 [B][rows][cin] (device),
  * W bf16 [N][taps*cin] (device); out[b][m][n] = epi(sum_j sum_ci X[b][m + j*dil - pad][ci] * W[n][j*cin+ci] +
  * bias[n % bias_mod]); epi: 0 none, 1 GELU(erf), 2 R + scale*acc, 3 R + acc; out_f32 / out_bf16 may be null;

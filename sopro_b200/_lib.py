@@ -75,6 +75,43 @@ class MimiWeights(C.Structure):
                 ("stage", MimiStageWeights * MIMI_MAX_RATIOS), ("last_w", _FP), ("last_b", _FP)]
 
 
+class SsmBlockWeights(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_float)) for n in
+                ("norm_w", "glu_w", "glu_b", "dw_w", "dw_b", "ffn_norm_w", "ffn_w1", "ffn_b1", "ffn_w2", "ffn_b2")]
+
+
+class NarConfig(C.Structure):
+    _fields_ = [("d_model", C.c_int32), ("n_layers", C.c_int32), ("kernel", C.c_int32), ("dilation", C.c_int32 * 16),
+                ("n_codebooks", C.c_int32), ("codebook_size", C.c_int32), ("head_dim", C.c_int32),
+                ("adapter_hidden", C.c_int32), ("n_stages", C.c_int32), ("stage_first", C.c_int32 * 8),
+                ("stage_count", C.c_int32 * 8)]
+
+
+class NarWeights(C.Structure):
+    _fields_ = [("block", SsmBlockWeights * 16)] + [(n, C.POINTER(C.c_float)) for n in
+                ("norm_w", "pre_w", "pre_b", "stage_emb", "adapter_norm_w", "adapter_w0", "adapter_b0", "adapter_w2", "adapter_b2")] + [
+        ("head_w", C.POINTER(C.c_float) * 64), ("head_b", C.POINTER(C.c_float) * 64), ("head_id_emb", C.POINTER(C.c_float) * 8),
+        ("mix", C.POINTER(C.c_float) * 8), ("prev_cb_weights", C.POINTER(C.c_float)), ("cb_embed", C.POINTER(C.c_float))]
+
+
+class PrefillConfig(C.Structure):
+    _fields_ = [("d_model", C.c_int32), ("n_layers_text", C.c_int32), ("text_kernel", C.c_int32), ("text_vocab", C.c_int32),
+                ("sv_dim", C.c_int32), ("ref_layers", C.c_int32), ("ref_heads", C.c_int32), ("ref_gmax", C.c_float),
+                ("max_text_len", C.c_int32), ("max_frames_pos", C.c_int32)]
+
+
+class PrefillRefLayer(C.Structure):
+    _fields_ = [("nq_w", C.POINTER(C.c_float)), ("q_w", C.POINTER(C.c_float)), ("o_w", C.POINTER(C.c_float)), ("gate", C.c_float)]
+
+
+class PrefillWeights(C.Structure):
+    _fields_ = [("text_emb", C.POINTER(C.c_float)), ("text_pos", C.POINTER(C.c_float)), ("frame_pos", C.POINTER(C.c_float)),
+                ("text_block", SsmBlockWeights * 16), ("text_norm_w", C.POINTER(C.c_float)),
+                ("film_w0", C.POINTER(C.c_float)), ("film_b0", C.POINTER(C.c_float)), ("film_w2", C.POINTER(C.c_float)),
+                ("film_b2", C.POINTER(C.c_float)), ("film_norm_w", C.POINTER(C.c_float)), ("film_norm_b", C.POINTER(C.c_float)),
+                ("ref_layer", PrefillRefLayer * 8), ("cond_norm_w", C.POINTER(C.c_float))]
+
+
 # every symbol include/sopro_b200.h declares: name -> (restype, argtypes)
 _VP, _I, _I32P = C.c_void_p, C.c_int, C.POINTER(C.c_int32)
 SYMBOLS = {
@@ -112,6 +149,13 @@ SYMBOLS = {
     "sopro_mimi_stream_frames": (C.c_int64, [_VP]),
     "sopro_mimi_decode_step": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sopro_mimi_decode_step_host": (_I, [_VP, _VP, _I, _VP, _VP]),
+    "sopro_nar_create": (_I, [_VP, _VP, _I, C.POINTER(_VP)]),
+    "sopro_nar_destroy": (_I, [_VP]),
+    "sopro_nar_set_forced": (_I, [_VP, _VP]),
+    "sopro_nar_refine": (_I, [_VP, _VP, C.c_int64, _VP, _VP, _I, _I, _VP, _VP]),
+    "sopro_prefill_create": (_I, [_VP, _VP, _I, C.POINTER(_VP)]),
+    "sopro_prefill_destroy": (_I, [_VP]),
+    "sopro_prefill_run": (_I, [_VP, _VP, _VP, _I, _I, _VP, _I, _VP, _VP, _I, C.c_float, _I, _VP, _VP, _VP, _VP]),
     "sopro_debug_tc_gemm": (_I, [_VP, _I, C.c_int64, _I, _I, _I, _I, _VP, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
 }
 

@@ -271,6 +271,21 @@ class MimiStreamDecoder:
     def __init__(self, codec: MimiCodec, max_chunk_frames: int = 16):
         self.codec = codec
         self.max_chunk_frames = int(max_chunk_frames)
+        self._idle: list = []  # device streams of finished utterances, reused after a reset (no allocation per stream())
+
+    def new_state(self) -> MimiDecodeState:
+        """A fresh state; reuses the device buffers of a released one when available."""
+        st = MimiDecodeState()
+        if self._idle:
+            st.decoder_past_key_values = self._idle.pop()
+            st.decoder_past_key_values.reset()
+        return st
+
+    def release(self, state: Optional[MimiDecodeState]) -> None:
+        """Hand a finished utterance's device buffers back for reuse."""
+        if state is not None and state.decoder_past_key_values is not None and len(self._idle) < 4:
+            self._idle.append(state.decoder_past_key_values)
+            state.decoder_past_key_values = None
 
     @torch.inference_mode()
     def decode_step(self, codes_chunk_tq: torch.Tensor, state: Optional[MimiDecodeState] = None, *,

@@ -1092,72 +1092,71 @@ __device__ __noinline__ void sample_utterance(const ArParams& p, int b, int t, f
   }
   se = block_sum(se, sm);
   SMARK();  // 4: exp + block sum
-  float lmax = -1.f;
-  int limax = 0x7fffffff;
+  float lmax = 0.f;
 #pragma unroll 1
   for (int v = tid; v < V; v += kThreads) {
     float q = sp[v] / se;
     if (!isfinite(q)) q = 0.f;
     sp[v] = q;
-    if (q > lmax) {
-      lmax = q;
-      limax = v;
-    }
+    lmax = fmaxf(lmax, q);
   }
-  // 3. top-k.  (a) a lower bound T_lb of the kk-th largest probability: every warp extracts the
-  //    r = ceil(kk/16) largest of its lanes' maxima; those 16*r <= 64 values are real elements, so the
-  //    kk-th largest of them is <= the true threshold.  (b) elements >= T_lb are the only candidates
-  //    (~1.5*kk of them on typical data): if they fit the 64 slots, one warp sort both selects and
-  //    orders them; otherwise the exact radix select (cold) runs.  Order everywhere: value desc,
-  //    index asc (topk/sort keep the first of a tie).
   const int kk = min(min(spar.top_k, V), kMaxTopK);
   SMARK();  // 5: probabilities
+  // 3. top-k.  (a) a threshold from a histogram of the probabilities' float bits: 64 bins per octave, 1024 bins below the
+  //    largest probability (16 octaves); the bin in which the running count (from the top) reaches kk gives the candidate
+  //    set {p : bin(p) <= b} -- a superset of the kk largest, a few elements more on typical data.  (b) if the
+  //    candidates fit the kCand slots, block-parallel rank ordering both selects and orders them; otherwise (extremely
+  //    peaked rows whose kk-th value sits more than 16 octaves below the maximum, or massive ties) the exact radix
+  //    select (cold) runs.  Order everywhere: value desc, index asc (topk/sort keep the first of a tie).
+  constexpr int kBins = 1024;
+  float bm;
   {
-    const int rr = (kk + kWarps - 1) / kWarps;  // <= 4
-    float cv = lmax;
-    int ci = limax;
+    for (int i = tid; i < kBins; i += kThreads) sm.hist[i] = 0;
+    bm = block_max(lmax, sm);  // also the barrier between clearing and counting
+    const int top_key = (int)(__float_as_uint(bm) >> 17);  // sign 0 | 8 exponent bits | 6 mantissa bits
 #pragma unroll 1
-    for (int r = 0; r < rr; ++r) {
-      float bv = cv;
-      int bi = ci;
-      warp_argmax(bv, bi);
-      if (lane == 0) {
-        sm.topv[warp * rr + r] = bv;
-        sm.topi[warp * rr + r] = bi;
-      }
-      if (ci == bi) cv = -1.f, ci = 0x7fffffff;  // the winner lane retires its maximum
+    for (int v = tid; v < V; v += kThreads) {
+      const int rel = min(top_key - (int)(__float_as_uint(sp[v]) >> 17), kBins - 1);
+      atomicAdd(&sm.hist[rel], 1u);
     }
+    __syncthreads();
+    // inclusive scan over the bins (2 per thread), find the bin where the count reaches kk
+    const unsigned c0 = sm.hist[2 * tid], c1 = sm.hist[2 * tid + 1];
+    unsigned x = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) sm.wtot[warp] = x;
+    __syncthreads();
+    unsigned before = 0;
+    for (int w = 0; w < warp; ++w) before += sm.wtot[w];
+    const unsigned incl = before + x, excl = incl - (c0 + c1);
+    if (excl < (unsigned)kk && (unsigned)kk <= incl) {  // exactly one thread
+      const bool first = excl + c0 >= (unsigned)kk;
+      sm.sel_digit = (unsigned)(2 * tid + (first ? 0 : 1));
+      sm.sel_need = first ? excl + c0 : incl;  // candidates down to and including that bin
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  rank_order(sm);
-  SMARK();  // 6: lower bound (lane maxima ranked)
-  const float t_lb = sm.sortv[kk - 1];
-  __syncthreads();  // topv is rewritten below
-  if (tid < kCand) {
-    sm.topv[tid] = -1.f;
-    sm.topi[tid] = 0x7fffffff;
-  }
-  __syncthreads();
+  const int b_sel = (int)sm.sel_digit;
+  const bool fits = b_sel < kBins - 1 && sm.sel_need <= (unsigned)kCand;
+  SMARK();  // 6: threshold bin
+  if (fits) {
+    const int top_key = (int)(__float_as_uint(bm) >> 17);
 #pragma unroll 1
-  for (int v = tid; v < V; v += kThreads) {
-    const float q = sp[v];
-    if (q >= t_lb) {
-      const unsigned slot = atomicAdd(&sm.n_cand, 1u);
-      if (slot < (unsigned)kCand) {
+    for (int v = tid; v < V; v += kThreads) {
+      const float q = sp[v];
+      if (top_key - (int)(__float_as_uint(q) >> 17) <= b_sel) {
+        const unsigned slot = atomicAdd(&sm.n_cand, 1u);
         sm.topv[slot] = q;
         sm.topi[slot] = v;
       }
     }
-  }
-  __syncthreads();
-  if (sm.n_cand > (unsigned)kCand) {
     __syncthreads();
-    if (tid < kCand) {
-      sm.topv[tid] = -1.f;
-      sm.topi[tid] = 0x7fffffff;
-    }
-    __syncthreads();
-    topk_radix_cold(sp, V, kk, t_lb, sm);
+  } else {
+    topk_radix_cold(sp, V, kk, 0.0f, sm);
   }
   rank_order(sm);
   SMARK();  // 7: candidates compacted

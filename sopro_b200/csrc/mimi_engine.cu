@@ -1115,7 +1115,7 @@ void stream_layout(sopro_mimi_stream* s, unsigned char* base) {
     const size_t cout = ch / 2;
     Tn *= c.ratios[i];
     s->Zf[i] = tcm ? (float*)at(P.take(Tn * cout * 4)) : nullptr;
-    s->Hs[i] = tcm ? nullptr : (float*)at(P.take(Tn * (cout / c.compress) * 4));
+    s->Hs[i] = (float*)at(P.take(Tn * (cout / c.compress) * 4));  // fp32 mode: fp32; tensor-core mode: bf16 view (unfused blocks)
     ch = cout;
   }
   s->S = (float*)at(P.take(n * C * 4));
@@ -1259,27 +1259,35 @@ int stream_step(sopro_mimi_stream* s, const int32_t* codes, int n, int code_stri
       const sopro_mimi::Stage& S = m->stages[si];
       const bool last = si + 1 == m->stages.size();
       const int hid = S.cout / c.compress, NT = S.ratio * S.cout, ctx_o = last ? c.last_kernel - 1 : 1;
-      if (!tc::supported(NT, 2 * S.cin, S.cin) || !tc::supported(hid, c.res_kernel * S.cout, S.cout) || !tc::supported(S.cout, hid, hid) ||
-          !tc::resblock_supported(hid, S.cout) || (S.cout * c.res_kernel) % 64)
+      if (!tc::supported(NT, 2 * S.cin, S.cin) || !tc::supported(hid, c.res_kernel * S.cout, S.cout) || !tc::supported(S.cout, hid, hid))
         return mfail(SOPRO_ERR_UNSUPPORTED, "streaming tensor-core mode: unsupported geometry at stage %zu (use SOPRO_MIMI_FP32)", si);
+      const bool fused = tc::resblock_supported(hid, S.cout) && (S.cout * c.res_kernel) % 64 == 0;
       __nv_bfloat16* zh = reinterpret_cast<__nv_bfloat16*>(s->Z[si]);
       __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(s->O[si]);
       if ((rc = tcg(cur, Tn, S.cin, 2, Wh + S.tw_h, Wd + S.tb, NT, S.cout, tc::EPI_NONE, nullptr, nullptr, s->Zf[si], zh + (size_t)kr3 * S.cout, 1)))
         return rc;
       Tn *= S.ratio;
-      tc::ResOp ro{};
-      ro.bias1 = Wd + S.r1b;
-      ro.bias2 = Wd + S.r2b;
-      ro.Z = s->Zf[si];
-      ro.out_f32 = nullptr;
-      ro.out_bf16 = oh + (size_t)ctx_o * S.cout;
-      ro.M = (int)Tn;
-      ro.Min = (int)Tn + kr3;
-      ro.taps = c.res_kernel;
-      ro.pad = 0;
-      ro.out_elu = 1;
-      cudaError_t fe = tc::launch_resblock(zh, Wh + S.r1w_h, Wh + S.r2w_h, hid, ro, 1, st);
-      if (fe != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "fused ResnetBlock (stream, stage %zu): %s", si, cudaGetErrorString(fe));
+      if (fused) {
+        tc::ResOp ro{};
+        ro.bias1 = Wd + S.r1b;
+        ro.bias2 = Wd + S.r2b;
+        ro.Z = s->Zf[si];
+        ro.out_f32 = nullptr;
+        ro.out_bf16 = oh + (size_t)ctx_o * S.cout;
+        ro.M = (int)Tn;
+        ro.Min = (int)Tn + kr3;
+        ro.taps = c.res_kernel;
+        ro.pad = 0;
+        ro.out_elu = 1;
+        cudaError_t fe = tc::launch_resblock(zh, Wh + S.r1w_h, Wh + S.r2w_h, hid, ro, 1, st);
+        if (fe != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "fused ResnetBlock (stream, stage %zu): %s", si, cudaGetErrorString(fe));
+      } else {  // conv k=3 -> ELU(h) bf16, then the 1x1 conv + fp32 skip (same two launches as the one-shot decode)
+        __nv_bfloat16* hh = reinterpret_cast<__nv_bfloat16*>(s->Hs[si]);
+        if ((rc = tcg(zh, Tn, S.cout, c.res_kernel, Wh + S.r1w_h, Wd + S.r1b, hid, hid, tc::EPI_NONE, nullptr, nullptr, nullptr, hh, 1))) return rc;
+        if ((rc = tcg(hh, Tn, hid, 1, Wh + S.r2w_h, Wd + S.r2b, S.cout, S.cout, tc::EPI_RES, s->Zf[si], nullptr, nullptr,
+                      oh + (size_t)ctx_o * S.cout, 1)))
+          return rc;
+      }
       carry(zh, S.cout * 2, kr3, Tn);
       carry(oh, S.cout * 2, ctx_o, Tn);
       cur = oh;

@@ -1,0 +1,697 @@
+// NAR refiner (reference nn/nar.py:13-116, model.py:307-347) on the device as a handful of fused fp32 kernels:
+// per stage  embed-mix + stage adapter (1 launch)  ->  6 x SSMLiteBlock (RMSNorm+GLU GEMM | dwconv+residual |
+// RMSNorm+FFN1+GELU GEMM | FFN2+residual GEMM)  ->  RMSNorm+pre GEMM  ->  all heads of the stage in ONE grouped GEMM launch
+// with an argmax epilogue (the logits never reach memory)  ->  argmax finish.  28 launches per stage instead of ~150
+// ATen ops.  The ids must equal the reference's, so every contraction is fp32 (dense_f32.cuh).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sopro_b200.h"
+#include "dense_f32.cuh"
+
+namespace mimi {
+void set_error(const char* msg);  // ar_engine.cu: the string behind sopro_last_error()
+}
+
+namespace pstage {
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  mimi::set_error(buf);
+  return code;
+}
+#define PCK(call)                                                                                                       \
+  do {                                                                                                                  \
+    cudaError_t e__ = (call);                                                                                           \
+    if (e__ != cudaSuccess)                                                                                             \
+      return pstage::fail(SOPRO_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct FArena {
+  std::vector<float> host;
+  size_t add(const float* p, size_t n) {
+    const size_t off = (host.size() + 63) / 64 * 64;
+    host.resize(off + n);
+    if (p) memcpy(host.data() + off, p, n * 4);
+    return off;
+  }
+};
+
+struct BlockOff {
+  size_t norm_w, glu_w, glu_b, dw_w, dw_b, ffn_norm_w, w1, b1, w2, b2;
+};
+
+void add_block(FArena& A, const sopro_ssm_block_weights_t& L, int D, int k, BlockOff* o) {
+  o->norm_w = A.add(L.norm_w, D);
+  o->glu_w = A.add(L.glu_w, (size_t)2 * D * D);
+  o->glu_b = A.add(L.glu_b, 2 * D);
+  o->dw_w = A.add(L.dw_w, (size_t)D * k);
+  o->dw_b = A.add(L.dw_b, D);
+  o->ffn_norm_w = A.add(L.ffn_norm_w, D);
+  o->w1 = A.add(L.ffn_w1, (size_t)4 * D * D);
+  o->b1 = A.add(L.ffn_b1, 4 * D);
+  o->w2 = A.add(L.ffn_w2, (size_t)4 * D * D);
+  o->b2 = A.add(L.ffn_b2, D);
+}
+
+bool block_ok(const sopro_ssm_block_weights_t& L) {
+  return L.norm_w && L.glu_w && L.glu_b && L.dw_w && L.dw_b && L.ffn_norm_w && L.ffn_w1 && L.ffn_b1 && L.ffn_w2 && L.ffn_b2;
+}
+
+// C = epi(prologue(A) . W^T): picks the skinny kernel for M <= 16 rows, the 128x128 tile kernel otherwise.
+// groups > 1 (argmax heads): blockIdx.z = group.
+int launch_dense(dense::DenseOp op, int groups, cudaStream_t st) {
+  if (op.K % 16 || op.M < 1 || op.N < 1) return fail(SOPRO_ERR_INVALID, "dense: bad shape M=%d N=%d K=%d", op.M, op.N, op.K);
+  if (op.M <= dense::kSkinnyRows) {
+    const int ncol = op.epi == dense::EPI_GLU ? op.N / 2 : op.N;
+    // about two waves of CTAs over the GPU, at least one column per warp
+    int cols = std::max(8, (ncol * groups + 295) / 296);
+    cols = (cols + 7) / 8 * 8;
+    const int parts = (ncol + cols - 1) / cols;
+    if (op.epi == dense::EPI_ARGMAX) op.parts = parts;
+    const size_t smem = (size_t)dense::kSkinnyRows * op.K * 4;
+    static bool attr = false;
+    if (!attr) {
+      PCK(cudaFuncSetAttribute(dense::dense_skinny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2048 * 4));
+      attr = true;
+    }
+    if (smem > (size_t)16 * 2048 * 4) return fail(SOPRO_ERR_INVALID, "dense: K=%d too large for the skinny kernel", op.K);
+    dense::dense_skinny_kernel<<<dim3(parts, 1, groups), dense::kSkinnyThreads, smem, st>>>(op, cols);
+  } else {
+    const int gy = (op.N + dense::kBN - 1) / dense::kBN;
+    if (op.epi == dense::EPI_ARGMAX) op.parts = gy;
+    dense::dense_tile_kernel<<<dim3((op.M + dense::kBM - 1) / dense::kBM, gy, groups), dense::kTileThreads, 0, st>>>(op);
+  }
+  PCK(cudaGetLastError());
+  return SOPRO_OK;
+}
+
+// argmax partial slots per row the launch above will write (must match launch_dense)
+int argmax_parts(int M, int N, int groups) {
+  if (M <= dense::kSkinnyRows) {
+    int cols = std::max(8, (N * groups + 295) / 296);
+    cols = (cols + 7) / 8 * 8;
+    return (N + cols - 1) / cols;
+  }
+  return (N + dense::kBN - 1) / dense::kBN;
+}
+
+// one SSMLiteBlock (nn/blocks.py:143-148) over rows [B][Tmax][D], in place on x; h [M][D] and hid [M][4D] are scratch
+int ssm_block(const float* W, const BlockOff& o, float* x, float* h, float* hid, const int* lens, int B, int Tmax, int D, int k, int dil,
+              bool causal, cudaStream_t st) {
+  const int M = B * Tmax;
+  dense::DenseOp g{};
+  g.A = x; g.W = W + o.glu_w; g.bias = W + o.glu_b; g.norm_w = W + o.norm_w; g.C = h; g.M = M; g.N = 2 * D; g.K = D; g.ldc = D;
+  g.epi = dense::EPI_GLU;
+  int rc = launch_dense(g, 1, st);
+  if (rc) return rc;
+  const int total = (k - 1) * dil, left = causal ? total : total / 2;
+  dense::dwconv_res_kernel<<<dim3(Tmax, B), 128, 0, st>>>(h, x, W + o.dw_w, W + o.dw_b, x, lens, Tmax, D, k, dil, left);
+  PCK(cudaGetLastError());
+  g = dense::DenseOp{};
+  g.A = x; g.W = W + o.w1; g.bias = W + o.b1; g.norm_w = W + o.ffn_norm_w; g.C = hid; g.M = M; g.N = 4 * D; g.K = D; g.ldc = 4 * D;
+  g.epi = dense::EPI_GELU;
+  if ((rc = launch_dense(g, 1, st))) return rc;
+  g = dense::DenseOp{};
+  g.A = hid; g.W = W + o.w2; g.bias = W + o.b2; g.R = x; g.C = x; g.M = M; g.N = D; g.K = 4 * D; g.ldc = D; g.epi = dense::EPI_RES;
+  return launch_dense(g, 1, st);
+}
+
+// ---- NAR stage input (model.py:318-341 + nn/embeddings.py:77-112 + nn/nar.py:28-32), one warp per (b, t) row:
+//   prev = sum_j w[j] * cb_embed[cb[j]*V + tok[j]]      (the codebooks decided so far, softmax weights)
+//   x    = mix0 * cond + mix1 * prev
+//   out  = RMSNorm(x) * (1 + tanh(g)) + tanh(b)         (stage adapter; g, b depend on the stage only)
+struct EmbedMix {
+  const float* cond;      // [B][cond_bs] rows of D
+  long long cond_bs;
+  const int* codes;       // [B][Tmax][Q] (codebooks < n_prev already decided)
+  const float* emb;       // [Q*V + 1][D]
+  const float* w_prev;    // [n_prev]
+  const float* norm_w;    // adapter RMSNorm
+  const float* mul;       // [D] 1 + tanh(g)
+  const float* add;       // [D] tanh(b)
+  float* out;             // [B][Tmax][D]
+  float mix0, mix1;
+  int Tmax, D, Q, V, n_prev;
+};
+
+__global__ void __launch_bounds__(256) nar_embed_mix_kernel(const EmbedMix p, long long rows) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long b = row / p.Tmax, t = row - b * p.Tmax;
+  const float* c = p.cond + b * p.cond_bs + t * p.D;
+  const int* tk = p.codes + row * p.Q;
+  constexpr int kMaxPer = 16;  // D <= 512
+  float x[kMaxPer];
+  float ss = 0.f;
+  int n = 0;
+  for (int k = lane; k < p.D; k += 32, ++n) {
+    float prev = 0.f;
+    for (int j = 0; j < p.n_prev; ++j) {
+      const int tok = min(max(tk[j], 0), p.V - 1);
+      prev += __ldg(p.w_prev + j) * __ldg(p.emb + ((size_t)j * p.V + tok) * p.D + k);
+    }
+    const float v = p.mix0 * c[k] + p.mix1 * prev;
+    x[n] = v;
+    ss += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = 1.0f / sqrtf(ss / (float)p.D + 1e-6f);
+  n = 0;
+  for (int k = lane; k < p.D; k += 32, ++n)
+    p.out[row * p.D + k] = ((x[n] * inv) * __ldg(p.norm_w + k)) * __ldg(p.mul + k) + __ldg(p.add + k);
+}
+
+// codes[b][t][0] = rvq1[b][t]
+__global__ void set_first_codebook_kernel(const int* __restrict__ rvq1, int* __restrict__ codes, long long rows, int Q) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows) codes[i * Q] = rvq1[i];
+}
+
+}  // namespace pstage
+
+using namespace pstage;
+
+struct sopro_nar {
+  int device = 0;
+  sopro_nar_config_t cfg{};
+  float* dev = nullptr;
+  size_t n_floats = 0;
+  BlockOff blk[SOPRO_MAX_SSM_LAYERS]{};
+  size_t norm_w = 0, pre_w = 0, pre_b = 0, adapter_norm_w = 0, emb = 0;
+  struct Stage {
+    int first, count, n_prev;
+    size_t w_prev, mul, add, head_w, head_b, head_id;
+    float mix0, mix1;
+  };
+  std::vector<Stage> stages;
+  // workspace
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  const int32_t* forced = nullptr;  // test hook: the previous codebooks every stage conditions on
+};
+
+extern "C" {
+
+int sopro_nar_create(const sopro_nar_config_t* cfg, const sopro_nar_weights_t* w, int device, sopro_nar_t** out) {
+  if (!cfg || !w || !out) return fail(SOPRO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) return fail(SOPRO_ERR_UNSUPPORTED, "no CUDA device; the NAR refiner has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SOPRO_ERR_INVALID, "device %d out of range", device);
+  cudaDeviceProp prop;
+  PCK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(SOPRO_ERR_UNSUPPORTED, "device is sm_%d%d; this build targets sm_100a only", prop.major, prop.minor);
+  const int D = cfg->d_model, NL = cfg->n_layers, k = cfg->kernel, Q = cfg->n_codebooks, V = cfg->codebook_size, Hn = cfg->head_dim,
+            AH = cfg->adapter_hidden, NS = cfg->n_stages;
+  if (D < 32 || D > 512 || D % 16 || Hn % 16 || NL < 1 || NL > SOPRO_MAX_SSM_LAYERS || k < 1 || k > 64 || Q < 2 || Q > SOPRO_NAR_MAX_CODEBOOKS ||
+      NS < 1 || NS > SOPRO_NAR_MAX_STAGES || V < 2 || AH < 1)
+    return fail(SOPRO_ERR_INVALID, "unsupported NAR geometry (d_model=%d head_dim=%d layers=%d codebooks=%d stages=%d)", D, Hn, NL, Q, NS);
+  for (int i = 0; i < NL; ++i)
+    if (!block_ok(w->block[i]) || cfg->dilation[i] < 1) return fail(SOPRO_ERR_INVALID, "NAR block %d: null weight or bad dilation", i);
+  if (!w->norm_w || !w->pre_w || !w->pre_b || !w->stage_emb || !w->adapter_norm_w || !w->adapter_w0 || !w->adapter_b0 || !w->adapter_w2 ||
+      !w->adapter_b2 || !w->prev_cb_weights || !w->cb_embed)
+    return fail(SOPRO_ERR_INVALID, "NAR: null weight pointer");
+  int covered = 1;
+  for (int s = 0; s < NS; ++s) {
+    if (cfg->stage_first[s] != covered || cfg->stage_count[s] < 1 || !w->head_id_emb[s] || !w->mix[s])
+      return fail(SOPRO_ERR_INVALID, "NAR stage %d: codebooks must be consecutive from 1 (first=%d count=%d)", s, cfg->stage_first[s],
+                  cfg->stage_count[s]);
+    for (int j = 0; j < cfg->stage_count[s]; ++j)
+      if (covered + j >= Q || !w->head_w[covered + j] || !w->head_b[covered + j])
+        return fail(SOPRO_ERR_INVALID, "NAR stage %d head %d: null weight or codebook out of range", s, j);
+    covered += cfg->stage_count[s];
+  }
+  PCK(cudaSetDevice(device));
+  sopro_nar* n = new sopro_nar();
+  n->device = device;
+  n->cfg = *cfg;
+  FArena A;
+  for (int i = 0; i < NL; ++i) add_block(A, w->block[i], D, k, &n->blk[i]);
+  n->norm_w = A.add(w->norm_w, D);
+  n->pre_w = A.add(w->pre_w, (size_t)Hn * D);
+  n->pre_b = A.add(w->pre_b, Hn);
+  n->adapter_norm_w = A.add(w->adapter_norm_w, D);
+  n->emb = A.add(w->cb_embed, ((size_t)Q * V + 1) * D);
+  for (int s = 0; s < NS; ++s) {
+    sopro_nar::Stage S{};
+    S.first = cfg->stage_first[s];
+    S.count = cfg->stage_count[s];
+    S.n_prev = S.first;  // codebooks 0 .. first-1 are decided when the stage runs
+    // softmax over the previous codebooks' weights (model.py:332, nn/embeddings.py:94-108), in double
+    {
+      std::vector<double> e(S.n_prev);
+      double mx = -1e300, sum = 0;
+      for (int j = 0; j < S.n_prev; ++j) mx = std::max(mx, (double)w->prev_cb_weights[j]);
+      for (int j = 0; j < S.n_prev; ++j) sum += (e[j] = exp((double)w->prev_cb_weights[j] - mx));
+      std::vector<float> wp(S.n_prev);
+      for (int j = 0; j < S.n_prev; ++j) wp[j] = (float)(e[j] / sum);
+      S.w_prev = A.add(wp.data(), wp.size());
+    }
+    {
+      const double a = w->mix[s][0], b = w->mix[s][1], mx = std::max(a, b);
+      const double ea = exp(a - mx), eb = exp(b - mx);
+      S.mix0 = (float)(ea / (ea + eb));
+      S.mix1 = (float)(eb / (ea + eb));
+    }
+    // stage adapter MLP on the stage embedding (nn/nar.py:20-31): g, b = Linear(GELU(Linear(e))).chunk(2); constants
+    {
+      std::vector<double> hmid(AH);
+      const float* e = w->stage_emb + (size_t)s * D;
+      for (int i = 0; i < AH; ++i) {
+        double acc = w->adapter_b0[i];
+        for (int c = 0; c < D; ++c) acc += (double)w->adapter_w0[(size_t)i * D + c] * e[c];
+        const double x = acc;
+        hmid[i] = 0.5 * x * (1.0 + erf(x * 0.70710678118654752440));
+      }
+      std::vector<float> mul(D), add(D);
+      for (int c = 0; c < 2 * D; ++c) {
+        double acc = w->adapter_b2[c];
+        for (int i = 0; i < AH; ++i) acc += (double)w->adapter_w2[(size_t)c * AH + i] * hmid[i];
+        if (c < D) mul[c] = (float)(1.0 + tanh(acc));
+        else add[c - D] = (float)tanh(acc);
+      }
+      S.mul = A.add(mul.data(), D);
+      S.add = A.add(add.data(), D);
+    }
+    // the stage's heads, contiguous: W [count][V][Hn], bias [count][V], id embedding [count][Hn]
+    S.head_w = A.add(nullptr, (size_t)S.count * V * Hn);
+    S.head_b = A.add(nullptr, (size_t)S.count * V);
+    for (int j = 0; j < S.count; ++j) {
+      memcpy(A.host.data() + S.head_w + (size_t)j * V * Hn, w->head_w[S.first + j], (size_t)V * Hn * 4);
+      memcpy(A.host.data() + S.head_b + (size_t)j * V, w->head_b[S.first + j], (size_t)V * 4);
+    }
+    S.head_id = A.add(w->head_id_emb[s], (size_t)S.count * Hn);
+    n->stages.push_back(S);
+  }
+  n->n_floats = A.host.size();
+  cudaError_t err = cudaMalloc(&n->dev, n->n_floats * 4);
+  if (err == cudaSuccess) err = cudaMemcpy(n->dev, A.host.data(), n->n_floats * 4, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    if (n->dev) cudaFree(n->dev);
+    delete n;
+    return fail(SOPRO_ERR_CUDA, "NAR weight upload (%zu MB) failed: %s", (A.host.size() * 4) >> 20, cudaGetErrorString(err));
+  }
+  *out = n;
+  return SOPRO_OK;
+}
+
+int sopro_nar_destroy(sopro_nar_t* n) {
+  if (!n) return SOPRO_OK;
+  cudaSetDevice(n->device);
+  cudaFree(n->dev);
+  cudaFree(n->ws);
+  delete n;
+  return SOPRO_OK;
+}
+
+int sopro_nar_set_forced(sopro_nar_t* n, const int32_t* forced_codes) {
+  if (!n) return fail(SOPRO_ERR_INVALID, "null argument");
+  n->forced = forced_codes;
+  return SOPRO_OK;
+}
+
+int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_stride, const int32_t* rvq1, const int32_t* lens, int B,
+                     int Tmax, int32_t* codes, void* stream) {
+  if (!n || !cond || !rvq1 || !codes) return fail(SOPRO_ERR_INVALID, "null argument");
+  if (B < 1 || Tmax < 1 || (long long)B * Tmax > 0x3fffffffLL) return fail(SOPRO_ERR_INVALID, "bad B=%d Tmax=%d", B, Tmax);
+  const sopro_nar_config_t& c = n->cfg;
+  const int D = c.d_model, Q = c.n_codebooks, V = c.codebook_size, Hn = c.head_dim;
+  if (cond_batch_stride < (int64_t)Tmax * D) return fail(SOPRO_ERR_INVALID, "cond_batch_stride smaller than Tmax*d_model");
+  PCK(cudaSetDevice(n->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long M = (long long)B * Tmax;
+  int max_heads = 1;
+  for (const auto& S : n->stages) max_heads = std::max(max_heads, S.count);
+  const size_t parts_max = (size_t)std::max(argmax_parts((int)M, V, 1), argmax_parts((int)M, V, max_heads));
+  const size_t fx = (size_t)M * D, fh = (size_t)M * D, fhid = (size_t)M * 4 * D, fz = (size_t)M * Hn,
+               famax = (size_t)max_heads * M * parts_max;
+  auto al = [](size_t x) { return (x + 63) / 64 * 64; };
+  const size_t need = (al(fx) + al(fh) + al(fhid) + al(fz) + 2 * al(famax)) * 4;
+  if (n->ws_bytes < need) {
+    PCK(cudaStreamSynchronize(st));
+    cudaFree(n->ws);
+    n->ws = nullptr;
+    n->ws_bytes = 0;
+    cudaError_t e = cudaMalloc(&n->ws, need);
+    if (e != cudaSuccess) return fail(SOPRO_ERR_CUDA, "NAR workspace %zu MB: %s", need >> 20, cudaGetErrorString(e));
+    n->ws_bytes = need;
+  }
+  float* x = n->ws;
+  float* h = x + al(fx);
+  float* hid = h + al(fh);
+  float* z = hid + al(fhid);
+  float* amax_v = z + al(fz);
+  int* amax_i = reinterpret_cast<int*>(amax_v + al(famax));
+  const float* W = n->dev;
+  set_first_codebook_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(rvq1, codes, M, Q);
+  PCK(cudaGetLastError());
+  for (const auto& S : n->stages) {
+    EmbedMix em{};
+    em.cond = cond; em.cond_bs = cond_batch_stride; em.codes = n->forced ? n->forced : codes; em.emb = W + n->emb; em.w_prev = W + S.w_prev;
+    em.norm_w = W + n->adapter_norm_w; em.mul = W + S.mul; em.add = W + S.add; em.out = x; em.mix0 = S.mix0; em.mix1 = S.mix1;
+    em.Tmax = Tmax; em.D = D; em.Q = Q; em.V = V; em.n_prev = S.n_prev;
+    nar_embed_mix_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(em, M);
+    PCK(cudaGetLastError());
+    int rc;
+    for (int i = 0; i < c.n_layers; ++i)
+      if ((rc = ssm_block(W, n->blk[i], x, h, hid, lens, B, Tmax, D, c.kernel, c.dilation[i], false, st))) return rc;
+    dense::DenseOp g{};
+    g.A = x; g.W = W + n->pre_w; g.bias = W + n->pre_b; g.norm_w = W + n->norm_w; g.C = z; g.M = (int)M; g.N = Hn; g.K = D; g.ldc = Hn;
+    g.epi = dense::EPI_BIAS;
+    if ((rc = launch_dense(g, 1, st))) return rc;
+    g = dense::DenseOp{};
+    g.A = z; g.W = W + S.head_w; g.bias = W + S.head_b; g.a_add = W + S.head_id; g.M = (int)M; g.N = V; g.K = Hn; g.epi = dense::EPI_ARGMAX;
+    g.amax_val = amax_v; g.amax_idx = amax_i; g.zW = (size_t)V * Hn; g.zBias = V; g.zAdd = Hn;
+    const int parts = argmax_parts((int)M, V, S.count);
+    if ((rc = launch_dense(g, S.count, st))) return rc;
+    dense::argmax_finish_kernel<<<dim3((unsigned)((M + 127) / 128), S.count), 128, 0, st>>>(amax_v, amax_i, (int)M, parts, codes + S.first, Q);
+    PCK(cudaGetLastError());
+  }
+  return SOPRO_OK;
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// Prefill: SoproTTSModel.prepare_conditioning (reference model.py:172-216) batched over utterances that share one
+// prepared reference voice:
+//   TextEncoder (nn/text.py:29-44): embedding + sinusoid -> mask -> n SSMLiteBlocks (non-causal) -> RMSNorm -> masked mean
+//   base[t] = txt_pool + frame_pos[t]                                 (model.py:200-202)
+//   SpeakerFiLM (nn/speaker.py:76-85): LayerNorm(base) * (1 + s*tanh(gamma)) + s*tanh(beta)
+//   3 x RefXAttnBlock with cached K/V (nn/ref.py:57-108): q = Wq RMSNorm(x); softmax(q K^T / sqrt(dh)) V; nan_to_num;
+//       a *= clamp(rms(x) / rms(a), 0, 10); x += gmax*tanh(gate) * Wo a
+//   cond_ar = RMSNorm(x)                                              (model.py:208)
+// cond_ar and txt_seq are INPUTS of the id-exact AR kernel, hence fp32 everywhere.
+// =================================================================================================
+namespace pstage {
+
+// x[b][l] = (emb[id] + pos[l]) * (l < len[b])      (nn/text.py:31-35)
+__global__ void __launch_bounds__(128) text_embed_kernel(const int* __restrict__ ids, const int* __restrict__ len,
+                                                         const float* __restrict__ emb, const float* __restrict__ pos,
+                                                         float* __restrict__ x, int Lmax, int D, int vocab) {
+  const int l = blockIdx.x, b = blockIdx.y;
+  const bool live = l < len[b];
+  const int id = min(max(ids[(size_t)b * Lmax + l], 0), vocab - 1);
+  for (int c = threadIdx.x; c < D; c += blockDim.x)
+    x[((size_t)b * Lmax + l) * D + c] = live ? __ldg(emb + (size_t)id * D + c) + __ldg(pos + (size_t)l * D + c) : 0.f;
+}
+
+// pool[b][c] = sum_{l < len} x[b][l][c] / (len + 1e-6)      (nn/text.py:41-43)
+__global__ void __launch_bounds__(128) mean_pool_kernel(const float* __restrict__ x, const int* __restrict__ len,
+                                                        float* __restrict__ pool, int Lmax, int D) {
+  const int b = blockIdx.x;
+  const int L = len[b];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float s = 0.f;
+    for (int l = 0; l < L; ++l) s += x[((size_t)b * Lmax + l) * D + c];
+    pool[(size_t)b * D + c] = s / ((float)L + 1e-6f);
+  }
+}
+
+// one warp per (b, t) row: base = pool[b] + frame_pos[t]; LayerNorm (eps 1e-5, biased variance) * w + bias;
+// y = ln * (1 + s*tanh(gamma[b])) + s*tanh(beta[b])         (film rows [Bf][2D], Bf = B or 1)
+__global__ void __launch_bounds__(256) film_rows_kernel(const float* __restrict__ pool, const float* __restrict__ fpos,
+                                                        const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                        const float* __restrict__ film, int film_shared, float strength,
+                                                        float* __restrict__ y, long long rows, int T, int D) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const long long b = row / T, t = row - b * T;
+  constexpr int kMaxPer = 16;
+  float v[kMaxPer];
+  float s = 0.f;
+  int n = 0;
+  for (int k = lane; k < D; k += 32, ++n) {
+    v[n] = pool[b * D + k] + __ldg(fpos + t * D + k);
+    s += v[n];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)D;
+  float var = 0.f;
+  n = 0;
+  for (int k = lane; k < D; k += 32, ++n) {
+    const float d = v[n] - mean;
+    var += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float inv = 1.0f / sqrtf(var / (float)D + 1e-5f);
+  const float* f = film + (film_shared ? 0 : b * 2 * D);
+  n = 0;
+  for (int k = lane; k < D; k += 32, ++n) {
+    const float ln = (v[n] - mean) * inv * __ldg(ln_w + k) + __ldg(ln_b + k);
+    y[row * D + k] = ln * (1.0f + strength * tanhf(f[k])) + strength * tanhf(f[D + k]);
+  }
+}
+
+// Cached reference cross-attention core + RMS matching, one warp per query row (nn/ref.py:84-101):
+//   per head: s_j = q.K_j / sqrt(dh); p = softmax(s); a = sum_j p_j V_j; nan_to_num
+//   a *= clamp(rms(x) / rms(a), 0, 10) over the full row (both heads)
+// K, V: [H][Tr][dh] (one shared reference voice).  Shared memory per warp: q [D] | p [Tr] | a [D].
+__global__ void __launch_bounds__(256) ref_attn_kernel(const float* __restrict__ q, const float* __restrict__ x,
+                                                       const float* __restrict__ Kc, const float* __restrict__ Vc,
+                                                       float* __restrict__ out, long long rows, int D, int H, int Tr) {
+  extern __shared__ float rsm[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int dh = D / H, Trp = (Tr + 3) & ~3;  // padded: the per-warp regions stay 16-byte aligned
+  float* qs = rsm + (size_t)warp * (2 * D + Trp);
+  float* ps = qs + D;
+  float* as = ps + Trp;
+  for (int k = lane; k < D; k += 32) qs[k] = q[row * D + k];
+  __syncwarp();
+  const float scale = 1.0f / sqrtf((float)dh);
+  float ssa = 0.f;
+  for (int h = 0; h < H; ++h) {
+    const float* Kh = Kc + (size_t)h * Tr * dh;
+    const float* Vh = Vc + (size_t)h * Tr * dh;
+    float mx = -INFINITY;
+    for (int j = lane; j < Tr; j += 32) {
+      const float* kr = Kh + (size_t)j * dh;
+      float s = 0.f;
+      for (int d = 0; d < dh; d += 4) {
+        const float4 kk = __ldg(reinterpret_cast<const float4*>(kr + d));
+        const float4 qq = *reinterpret_cast<const float4*>(qs + h * dh + d);
+        s += kk.x * qq.x + kk.y * qq.y + kk.z * qq.z + kk.w * qq.w;
+      }
+      s *= scale;
+      ps[j] = s;
+      mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < Tr; j += 32) {
+      const float e = expf(ps[j] - mx);
+      ps[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    for (int d = lane; d < dh; d += 32) {
+      float o = 0.f;
+      for (int j = 0; j < Tr; ++j) o += (ps[j] * inv) * __ldg(Vh + (size_t)j * dh + d);
+      if (!isfinite(o)) o = 0.f;
+      as[h * dh + d] = o;
+      ssa += o * o;
+    }
+    __syncwarp();
+  }
+  float ssx = 0.f;
+  for (int k = lane; k < D; k += 32) {
+    const float xv = x[row * D + k];
+    ssx += xv * xv;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ssa += __shfl_xor_sync(0xffffffffu, ssa, o);
+    ssx += __shfl_xor_sync(0xffffffffu, ssx, o);
+  }
+  const float rx = sqrtf(ssx / (float)D + 1e-6f), ra = sqrtf(ssa / (float)D + 1e-6f);
+  const float sc = fminf(fmaxf(rx / ra, 0.0f), 10.0f);
+  for (int k = lane; k < D; k += 32) out[row * D + k] = as[k] * sc;
+}
+
+}  // namespace pstage
+
+struct sopro_prefill {
+  int device = 0;
+  sopro_prefill_config_t cfg{};
+  float* dev = nullptr;
+  size_t n_floats = 0;
+  size_t text_emb = 0, text_pos = 0, frame_pos = 0, text_norm_w = 0, film_w0 = 0, film_b0 = 0, film_w2 = 0, film_b2 = 0, film_ln_w = 0,
+         film_ln_b = 0, cond_norm_w = 0;
+  BlockOff blk[SOPRO_MAX_SSM_LAYERS]{};
+  struct Ref {
+    size_t nq_w, q_w, o_w;
+    float gate_eff;
+  } ref[SOPRO_PREFILL_MAX_REF_LAYERS]{};
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+};
+
+extern "C" {
+
+int sopro_prefill_create(const sopro_prefill_config_t* cfg, const sopro_prefill_weights_t* w, int device, sopro_prefill_t** out) {
+  if (!cfg || !w || !out) return fail(SOPRO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) return fail(SOPRO_ERR_UNSUPPORTED, "no CUDA device; the prefill has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SOPRO_ERR_INVALID, "device %d out of range", device);
+  cudaDeviceProp prop;
+  PCK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(SOPRO_ERR_UNSUPPORTED, "device is sm_%d%d; this build targets sm_100a only", prop.major, prop.minor);
+  const int D = cfg->d_model, NL = cfg->n_layers_text, k = cfg->text_kernel, SV = cfg->sv_dim, RL = cfg->ref_layers, H = cfg->ref_heads;
+  if (D < 32 || D > 512 || D % 16 || NL < 0 || NL > SOPRO_MAX_SSM_LAYERS || k < 1 || k > 64 || SV < 16 || SV % 16 || RL < 0 ||
+      RL > SOPRO_PREFILL_MAX_REF_LAYERS || H < 1 || D % H || (D / H) % 4 || cfg->text_vocab < 1 || cfg->max_text_len < 1 || cfg->max_frames_pos < 1)
+    return fail(SOPRO_ERR_INVALID, "unsupported prefill geometry");
+  for (int i = 0; i < NL; ++i)
+    if (!block_ok(w->text_block[i])) return fail(SOPRO_ERR_INVALID, "text block %d: null weight", i);
+  if (!w->text_emb || !w->text_pos || !w->frame_pos || !w->text_norm_w || !w->film_w0 || !w->film_b0 || !w->film_w2 || !w->film_b2 ||
+      !w->film_norm_w || !w->film_norm_b || !w->cond_norm_w)
+    return fail(SOPRO_ERR_INVALID, "prefill: null weight pointer");
+  for (int i = 0; i < RL; ++i)
+    if (!w->ref_layer[i].nq_w || !w->ref_layer[i].q_w || !w->ref_layer[i].o_w) return fail(SOPRO_ERR_INVALID, "ref layer %d: null weight", i);
+  PCK(cudaSetDevice(device));
+  sopro_prefill* p = new sopro_prefill();
+  p->device = device;
+  p->cfg = *cfg;
+  FArena A;
+  p->text_emb = A.add(w->text_emb, (size_t)cfg->text_vocab * D);
+  p->text_pos = A.add(w->text_pos, (size_t)cfg->max_text_len * D);
+  p->frame_pos = A.add(w->frame_pos, (size_t)cfg->max_frames_pos * D);
+  for (int i = 0; i < NL; ++i) add_block(A, w->text_block[i], D, k, &p->blk[i]);
+  p->text_norm_w = A.add(w->text_norm_w, D);
+  p->film_w0 = A.add(w->film_w0, (size_t)D * SV);
+  p->film_b0 = A.add(w->film_b0, D);
+  p->film_w2 = A.add(w->film_w2, (size_t)2 * D * D);
+  p->film_b2 = A.add(w->film_b2, 2 * D);
+  p->film_ln_w = A.add(w->film_norm_w, D);
+  p->film_ln_b = A.add(w->film_norm_b, D);
+  for (int i = 0; i < RL; ++i) {
+    p->ref[i].nq_w = A.add(w->ref_layer[i].nq_w, D);
+    p->ref[i].q_w = A.add(w->ref_layer[i].q_w, (size_t)D * D);
+    p->ref[i].o_w = A.add(w->ref_layer[i].o_w, (size_t)D * D);
+    p->ref[i].gate_eff = cfg->ref_gmax * tanhf(w->ref_layer[i].gate);
+  }
+  p->cond_norm_w = A.add(w->cond_norm_w, D);
+  p->n_floats = A.host.size();
+  cudaError_t err = cudaMalloc(&p->dev, p->n_floats * 4);
+  if (err == cudaSuccess) err = cudaMemcpy(p->dev, A.host.data(), p->n_floats * 4, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    if (p->dev) cudaFree(p->dev);
+    delete p;
+    return fail(SOPRO_ERR_CUDA, "prefill weight upload failed: %s", cudaGetErrorString(err));
+  }
+  *out = p;
+  return SOPRO_OK;
+}
+
+int sopro_prefill_destroy(sopro_prefill_t* p) {
+  if (!p) return SOPRO_OK;
+  cudaSetDevice(p->device);
+  cudaFree(p->dev);
+  cudaFree(p->ws);
+  delete p;
+  return SOPRO_OK;
+}
+
+int sopro_prefill_run(sopro_prefill_t* p, const int32_t* text_ids, const int32_t* text_len, int B, int Lmax, const float* sv,
+                      int sv_shared, const float* const* ref_k, const float* const* ref_v, int Tr, float style_strength, int n_frames,
+                      float* txt_seq, float* txt_pool, float* cond_ar, void* stream) {
+  if (!p || !text_ids || !text_len || !sv || !txt_seq || !txt_pool || !cond_ar) return fail(SOPRO_ERR_INVALID, "null argument");
+  const sopro_prefill_config_t& c = p->cfg;
+  const int D = c.d_model, SV = c.sv_dim, H = c.ref_heads;
+  if (B < 1 || Lmax < 1 || Lmax > c.max_text_len || n_frames < 1 || n_frames > c.max_frames_pos || (long long)B * n_frames > 0x3fffffffLL)
+    return fail(SOPRO_ERR_INVALID, "bad B=%d Lmax=%d (max %d) n_frames=%d (max %d)", B, Lmax, c.max_text_len, n_frames, c.max_frames_pos);
+  if (c.ref_layers > 0 && (!ref_k || !ref_v || Tr < 1 || Tr > 4096)) return fail(SOPRO_ERR_INVALID, "reference K/V missing or Tr=%d out of range", Tr);
+  PCK(cudaSetDevice(p->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long Mt = (long long)B * Lmax, Mc = (long long)B * n_frames;
+  auto al = [](size_t x) { return (x + 63) / 64 * 64; };
+  const size_t rows = (size_t)std::max(Mt, Mc);
+  const size_t need = (al(rows * D) * 3 + al(rows * 4 * D) + al((size_t)B * D) + al((size_t)B * 2 * D)) * 4;
+  if (p->ws_bytes < need) {
+    PCK(cudaStreamSynchronize(st));
+    cudaFree(p->ws);
+    p->ws = nullptr;
+    p->ws_bytes = 0;
+    cudaError_t e = cudaMalloc(&p->ws, need);
+    if (e != cudaSuccess) return fail(SOPRO_ERR_CUDA, "prefill workspace %zu MB: %s", need >> 20, cudaGetErrorString(e));
+    p->ws_bytes = need;
+  }
+  float* x = p->ws;
+  float* h = x + al(rows * D);
+  float* q = h + al(rows * D);
+  float* hid = q + al(rows * D);
+  float* fmid = hid + al(rows * 4 * D);  // [B][D] FiLM hidden
+  float* film = fmid + al((size_t)B * D);  // [B][2D]
+  const float* W = p->dev;
+  int rc;
+  // ---- text encoder
+  text_embed_kernel<<<dim3(Lmax, B), 128, 0, st>>>(text_ids, text_len, W + p->text_emb, W + p->text_pos, x, Lmax, D, c.text_vocab);
+  PCK(cudaGetLastError());
+  for (int i = 0; i < c.n_layers_text; ++i)
+    if ((rc = ssm_block(W, p->blk[i], x, h, hid, text_len, B, Lmax, D, c.text_kernel, 1, false, st))) return rc;
+  dense::rmsnorm_rows_kernel<<<(unsigned)((Mt + 7) / 8), 256, 0, st>>>(x, W + p->text_norm_w, nullptr, nullptr, txt_seq, Mt, D);
+  PCK(cudaGetLastError());
+  mean_pool_kernel<<<B, 128, 0, st>>>(txt_seq, text_len, txt_pool, Lmax, D);
+  PCK(cudaGetLastError());
+  // ---- FiLM parameters from the speaker vector(s)
+  const int Bf = sv_shared ? 1 : B;
+  dense::DenseOp g{};
+  g.A = sv; g.W = W + p->film_w0; g.bias = W + p->film_b0; g.C = fmid; g.M = Bf; g.N = D; g.K = SV; g.ldc = D; g.epi = dense::EPI_GELU;
+  if ((rc = launch_dense(g, 1, st))) return rc;
+  g = dense::DenseOp{};
+  g.A = fmid; g.W = W + p->film_w2; g.bias = W + p->film_b2; g.C = film; g.M = Bf; g.N = 2 * D; g.K = D; g.ldc = 2 * D; g.epi = dense::EPI_BIAS;
+  if ((rc = launch_dense(g, 1, st))) return rc;
+  film_rows_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, st>>>(txt_pool, W + p->frame_pos, W + p->film_ln_w, W + p->film_ln_b, film, sv_shared ? 1 : 0,
+                                                            style_strength, x, Mc, n_frames, D);
+  PCK(cudaGetLastError());
+  // ---- reference cross-attention stack
+  const size_t rsmem = (size_t)8 * (2 * D + ((Tr + 3) & ~3)) * 4;
+  if (c.ref_layers > 0 && rsmem > 48 * 1024) {
+    static bool attr = false;
+    if (!attr) {
+      PCK(cudaFuncSetAttribute(ref_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+  }
+  for (int i = 0; i < c.ref_layers; ++i) {
+    g = dense::DenseOp{};
+    g.A = x; g.W = W + p->ref[i].q_w; g.norm_w = W + p->ref[i].nq_w; g.C = q; g.M = (int)Mc; g.N = D; g.K = D; g.ldc = D; g.epi = dense::EPI_BIAS;
+    if ((rc = launch_dense(g, 1, st))) return rc;
+    ref_attn_kernel<<<(unsigned)((Mc + 7) / 8), 256, rsmem, st>>>(q, x, ref_k[i], ref_v[i], h, Mc, D, H, Tr);
+    PCK(cudaGetLastError());
+    g = dense::DenseOp{};
+    g.A = h; g.W = W + p->ref[i].o_w; g.R = x; g.C = x; g.M = (int)Mc; g.N = D; g.K = D; g.ldc = D; g.epi = dense::EPI_RES_GATE;
+    g.gate = p->ref[i].gate_eff;
+    if ((rc = launch_dense(g, 1, st))) return rc;
+  }
+  dense::rmsnorm_rows_kernel<<<(unsigned)((Mc + 7) / 8), 256, 0, st>>>(x, W + p->cond_norm_w, nullptr, nullptr, cond_ar, Mc, D);
+  PCK(cudaGetLastError());
+  return SOPRO_OK;
+}
+
+}  // extern "C"

@@ -22,6 +22,8 @@ from . import prefill as P
 from .codec import MimiCodec
 from .config import TARGET_SR, SoproTTSConfig
 from .engine import ArEngine, ArSession, Sampling
+from .nar import NarEngine
+from .prefill_cuda import PrefillEngine
 from .prefill import PreparedReference
 from .weights import load_safetensors, read_safetensors_cfg
 
@@ -123,12 +125,8 @@ class SoproModel:
         self._sessions: Dict[Tuple[int, int, int], List[ArSession]] = {}
         self._sessions_busy: set = set()
         self._sessions_lock = threading.Lock()
-        self._prep_graphs: Dict[tuple, tuple] = {}
-        self._prep_seen: Dict[tuple, int] = {}
-        self._nar_cache: dict = {}
-        self._nar_graphs: Dict[Tuple[int, int], tuple] = {}
-        self._nar_seen: Dict[Tuple[int, int], int] = {}
-        self.use_cuda_graphs = os.environ.get("SOPRO_CUDA_GRAPHS", "1") != "0"
+        self.prefill = PrefillEngine(cfg, state_dict, self.device, self.text_pos, self.frame_pos)
+        self.nar = NarEngine(cfg, state_dict, self.device)
 
     # ---- geometry helpers (reference model.py:119-131)
     def rf_ar(self) -> int:
@@ -173,74 +171,32 @@ class SoproModel:
     @torch.no_grad()
     def prepare_conditioning(self, text_ids_1d: torch.Tensor, ref: PreparedReference, *, max_frames: int, device=None,
                              style_strength: float = 1.2) -> Dict[str, torch.Tensor]:
-        """reference model.py:174-216.  ~150 small torch kernels; a (text length, max_frames, style, reference) seen
-        twice is captured into a CUDA graph and replayed (same kernels, same results)."""
-        def eager(ids):
-            return P.prepare_conditioning(self.sd, self.cfg, ids, ref, max_frames=max_frames, device=self.device,
-                                          style_strength=style_strength, text_pos=self.text_pos, frame_pos=self.frame_pos)
-
-        ids = text_ids_1d.to(self.device)
-        on_dev = ref.sv_ref.device == self.device and all(
-            (not isinstance(v, torch.Tensor)) or v.device == self.device for c in ref.ref_kv_caches for v in c.values())
-        if not self.use_cuda_graphs or not on_dev or ids.numel() == 0:
-            return eager(ids)
-        key = (int(ids.numel()), int(max_frames), float(style_strength), id(ref))
-        ent = self._prep_graphs.get(key)
-        if ent is None:
-            self._prep_seen[key] = self._prep_seen.get(key, 0) + 1
-            if self._prep_seen[key] < 2:
-                return eager(ids)
-            if len(self._prep_graphs) >= 8:
-                self._prep_graphs.pop(next(iter(self._prep_graphs)))
-            ids_in = ids.clone()
-            cur = torch.cuda.current_stream(self.device)
-            side = torch.cuda.Stream(self.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                eager(ids_in)
-            cur.wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = eager(ids_in)
-            ent = (graph, ids_in, out, ref)  # `ref` kept alive: the graph reads its tensors in place
-            self._prep_graphs[key] = ent
-        graph, ids_in, out, _ = ent
-        ids_in.copy_(ids)
-        graph.replay()
-        return {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+        """reference model.py:174-216 on the CUDA prefill engine (sopro_b200/csrc/nar_engine.cu: ~25 fused fp32 kernels)."""
+        return self.prepare_conditioning_batch([text_ids_1d], ref, max_frames=max_frames, style_strength=style_strength)[0]
 
     @torch.no_grad()
-    def nar_refine(self, cond_seq: torch.Tensor, rvq1_1xT: torch.Tensor) -> torch.Tensor:
-        """reference model.py:307-347.  The refiner is ~600 small torch kernels; a (B, T) shape seen twice is captured
-        into a CUDA graph and replayed from then on (same kernels, same results, one launch)."""
-        key = (int(cond_seq.size(0)), int(cond_seq.size(1)))
-        if not self.use_cuda_graphs or key[1] == 0:
-            return P.nar_refine(self.sd, self.cfg, cond_seq, rvq1_1xT, self._nar_cache)
-        ent = self._nar_graphs.get(key)
-        if ent is None:
-            self._nar_seen[key] = self._nar_seen.get(key, 0) + 1
-            if self._nar_seen[key] < 2:
-                return P.nar_refine(self.sd, self.cfg, cond_seq, rvq1_1xT, self._nar_cache)
-            if len(self._nar_graphs) >= 12:
-                self._nar_graphs.pop(next(iter(self._nar_graphs)))
-            c_in = cond_seq.detach().clone().contiguous()
-            t_in = rvq1_1xT.detach().to(torch.long).clone().contiguous()
-            cur = torch.cuda.current_stream(self.device)
-            side = torch.cuda.Stream(self.device)
-            side.wait_stream(cur)
-            with torch.cuda.stream(side):
-                P.nar_refine(self.sd, self.cfg, c_in, t_in, self._nar_cache)  # warm-up: cuBLAS workspaces, caches
-            cur.wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = P.nar_refine(self.sd, self.cfg, c_in, t_in, self._nar_cache)
-            ent = (graph, c_in, t_in, out)
-            self._nar_graphs[key] = ent
-        graph, c_in, t_in, out = ent
-        c_in.copy_(cond_seq)
-        t_in.copy_(rvq1_1xT)
-        graph.replay()
-        return out.clone()
+    def prepare_conditioning_batch(self, text_ids: Sequence[torch.Tensor], ref: PreparedReference, *, max_frames: int,
+                                   style_strength: float = 1.2) -> List[Dict[str, torch.Tensor]]:
+        """NEW (the reference is batch-1): the prefill of B texts that share one prepared reference in ONE pass; element i
+        is the `prep` dict of model.py:210-216 for text i (views into the batch tensors)."""
+        txt_seq, lens, txt_pool, cond = self.prefill.run(text_ids, ref, n_frames=int(max_frames) + 1, style_strength=float(style_strength))
+        sv = ref.sv_ref.to(self.device)
+        if sv.dim() == 1:
+            sv = sv.unsqueeze(0)
+        out = []
+        for i, L in enumerate(lens):
+            out.append({"txt_seq": txt_seq[i: i + 1, :L], "text_mask": torch.ones((1, L), dtype=torch.bool, device=self.device),
+                        "txt_pool": txt_pool[i: i + 1], "sv_ref": sv, "cond_ar": cond[i: i + 1]})
+        return out
+
+    @torch.no_grad()
+    def nar_refine(self, cond_seq: torch.Tensor, rvq1_1xT: torch.Tensor, lens: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """reference model.py:307-347 on the CUDA NAR engine (sopro_b200/csrc/nar_engine.cu): 4 stage passes of fused fp32
+        kernels, ids equal to the reference's.  cond [B, T, D], rvq1 [B, T] -> [B, T, Q] int64.  `lens` (extension):
+        valid frames per utterance of a ragged batch (the refiner is not causal)."""
+        if int(cond_seq.size(1)) == 0:
+            return torch.zeros((int(cond_seq.size(0)), 0, int(self.cfg.num_codebooks)), dtype=torch.long, device=self.device)
+        return self.nar.refine(cond_seq, rvq1_1xT, lens)
 
     # ---- the hot path
     def _sampling(self, top_p, temperature, anti_loop, loop_streak, recovery_top_p, recovery_temp, min_gen_frames,
@@ -259,13 +215,17 @@ class SoproModel:
         return int(samp.top_k) if (samp.top_p < 1.0 and samp.recovery_top_p < 1.0) else int(self.cfg.ar_vocab())
 
     @torch.no_grad()
-    def ar_stream(self, prep: Dict[str, torch.Tensor], *, max_frames: int, top_p: float = 0.9, temperature: float = 1.05,
-                  anti_loop: bool = True, loop_streak: int = 8, recovery_top_p: float = 0.85, recovery_temp: float = 1.2,
-                  min_gen_frames: Optional[int] = None, launch_frames: int = 0, seed: Optional[int] = None,
-                  generator: Optional[torch.Generator] = None) -> Iterator[Tuple[int, int, bool]]:
-        """Yields (t, token, is_eos) like the reference generator (model.py:218-305).  The persistent kernel runs
-        `launch_frames` frames per launch (0 = the whole utterance in one launch); a consumer that stops iterating
-        early simply abandons the frames computed ahead, and the RNG is settled to the frames actually consumed."""
+    def ar_chunks(self, prep: Dict[str, torch.Tensor], *, max_frames: int, chunk_frames: int = 0, top_p: float = 0.9,
+                  temperature: float = 1.05, anti_loop: bool = True, loop_streak: int = 8, recovery_top_p: float = 0.85,
+                  recovery_temp: float = 1.2, min_gen_frames: Optional[int] = None, seed: Optional[int] = None,
+                  generator: Optional[torch.Generator] = None, progress: Optional[dict] = None):
+        """The persistent kernel driven `chunk_frames` frames per launch (0 = the whole utterance in one launch).
+        Yields ``(tokens, finished, prefetch)`` per launch: the frames it produced (ints), whether the utterance is over
+        (EOS past min_gen_frames, or max_frames reached), and a callable that enqueues the NEXT launch right away on the
+        current CUDA stream -- a streaming consumer queues it behind its own NAR + Mimi work so it runs while the audio is
+        handed out; without the call the next launch is enqueued when the generator is resumed.  Frames computed ahead
+        of a consumer that stops early are abandoned: on exit the RNG is settled to ``progress["consumed"]`` frames
+        (default: every frame yielded), i.e. exactly the draws the reference would have made."""
         cond, txt = prep["cond_ar"], prep["txt_seq"]
         steps = int(max_frames) + 1
         if cond.size(1) < steps:
@@ -275,31 +235,103 @@ class SoproModel:
         samp = self._sampling(top_p, temperature, anti_loop, loop_streak, recovery_top_p, recovery_temp, min_gen_frames, False)
         nk = self._noise_cols(samp)
         ses = self._checkout(1, steps, L)
-        per = steps if launch_frames <= 0 else int(launch_frames)
-        t = 0
-        used = 0
+        per = steps if chunk_frames <= 0 else int(chunk_frames)
+        st = {"launched": 0, "read": 0, "yielded": 0}
+
+        def launch():
+            """Draw + upload the noise rows of the next launch and enqueue it (no-op while one is in flight)."""
+            if st["launched"] >= steps or st["launched"] > st["read"]:
+                return
+            lo = noise.drawn
+            blk = noise.rows(st["launched"] + per)
+            if blk.size(0):
+                tape[0, lo: lo + blk.size(0)].copy_(blk[:, :nk])
+            ses.run(per)
+            st["launched"] = min(steps, st["launched"] + per)
+
         try:
             # the session keeps a pointer to this device tape; each launch's rows are drawn and uploaded just before it
             tape = torch.zeros(1, steps, nk, device=self.device)
             ses.begin(cond[:, :steps], txt, [L], tape, samp)
+            t = 0
             while t < steps:
-                lo = noise.drawn
-                blk = noise.rows(t + per)
-                if blk.size(0):
-                    tape[0, lo: lo + blk.size(0)].copy_(blk[:, :nk])
-                ses.run(per)
-                toks, n, done = ses.read()
+                launch()
+                toks, n, done = ses.read()  # synchronises the stream the launch ran on
                 upto = int(n[0])
-                while t < upto:
-                    tok = int(toks[0, t])
-                    used = t + 1
-                    yield t, tok, tok == self.eos_id
-                    t += 1
-                if done[0] or upto < min(steps, ses.position):
+                st["read"] = st["launched"]
+                chunk = [int(x) for x in toks[0, t:upto]]
+                finished = bool(done[0]) or upto >= steps or upto < st["launched"]
+                t = upto
+                st["yielded"] = upto
+                yield chunk, finished, (launch if not finished else (lambda: None))
+                if finished:
                     break
         finally:
             self._release(ses)
-            noise.settle(used)
+            noise.settle(int(progress["consumed"]) if progress is not None and "consumed" in progress else st["yielded"])
+
+    @torch.no_grad()
+    def ar_stream(self, prep: Dict[str, torch.Tensor], *, max_frames: int, top_p: float = 0.9, temperature: float = 1.05,
+                  anti_loop: bool = True, loop_streak: int = 8, recovery_top_p: float = 0.85, recovery_temp: float = 1.2,
+                  min_gen_frames: Optional[int] = None, launch_frames: int = 0, seed: Optional[int] = None,
+                  generator: Optional[torch.Generator] = None) -> Iterator[Tuple[int, int, bool]]:
+        """Yields (t, token, is_eos) like the reference generator (model.py:218-305).  The persistent kernel runs
+        `launch_frames` frames per launch (0 = the whole utterance in one launch); a consumer that stops iterating
+        early simply abandons the frames computed ahead, and the RNG is settled to the frames actually consumed."""
+        progress = {"consumed": 0}
+        gen = self.ar_chunks(prep, max_frames=max_frames, chunk_frames=launch_frames, top_p=top_p, temperature=temperature,
+                             anti_loop=anti_loop, loop_streak=loop_streak, recovery_top_p=recovery_top_p,
+                             recovery_temp=recovery_temp, min_gen_frames=min_gen_frames, seed=seed, generator=generator,
+                             progress=progress)
+        t = 0
+        try:
+            for chunk, _finished, _prefetch in gen:
+                for tok in chunk:
+                    progress["consumed"] = t + 1
+                    yield t, tok, tok == self.eos_id
+                    t += 1
+        finally:
+            gen.close()
+
+    def _draw_tapes(self, B: int, steps: int, nk: int, seeds: Optional[Sequence[int]]) -> torch.Tensor:
+        """[B, steps, nk] Exp(1) draws: utterance i's rows are what `steps` multinomial calls consume after
+        torch.manual_seed(seeds[i]) (private generators, drawn on host threads -- the draws release the GIL); without
+        seeds the global generator is consumed utterance after utterance, full length each."""
+        V = self.cfg.ar_vocab()
+        out = torch.empty((B, steps, nk), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+        if seeds is None:
+            for i in range(B):
+                out[i] = _Noise(steps, V, None, None).tape[:, :nk]
+            return out
+        from concurrent.futures import ThreadPoolExecutor
+
+        view = out.numpy()  # worker threads are outside the caller's inference_mode: write through numpy
+
+        def one(i):
+            view[i] = _Noise(steps, V, int(seeds[i]), None).tape[:, :nk].numpy()
+
+        with ThreadPoolExecutor(max_workers=min(B, max(1, len(os.sched_getaffinity(0))))) as ex:
+            list(ex.map(one, range(B)))
+        return out
+
+    @torch.no_grad()
+    def ar_generate_tensors(self, cond: torch.Tensor, txt: torch.Tensor, lens: Sequence[int], *, max_frames: int, top_p: float = 0.9,
+                            temperature: float = 1.05, anti_loop: bool = True, min_gen_frames: Optional[int] = None,
+                            seeds: Optional[Sequence[int]] = None, stop_on_first_eos: bool = True):
+        """B utterances in ONE persistent launch from batch tensors (cond [B, >=steps, D], txt [B, Lmax, D], lens).
+        -> (tokens [B, steps] int32 numpy, n_tokens [B])."""
+        B, steps = int(cond.shape[0]), int(max_frames) + 1
+        samp = self._sampling(top_p, temperature, anti_loop, 8, 0.85, 1.2, min_gen_frames, stop_on_first_eos)
+        nk = self._noise_cols(samp)
+        tapes = self._draw_tapes(B, steps, nk, seeds)  # host threads; the prefill kernels queued before run meanwhile
+        ses = self._checkout(B, steps, max(int(x) for x in lens))
+        try:
+            ses.begin(cond[:, :steps], txt, [int(x) for x in lens], tapes.to(self.device, non_blocking=True), samp)
+            ses.run()
+            toks, n, _ = ses.read()
+        finally:
+            self._release(ses)
+        return toks, n
 
     @torch.no_grad()
     def ar_generate_batch(self, preps: Sequence[Dict[str, torch.Tensor]], *, max_frames: int, top_p: float = 0.9,
@@ -309,29 +341,15 @@ class SoproModel:
         equals the reference run alone with seed seeds[i].  Without seeds the global generator is
         consumed utterance after utterance, full length each."""
         B, steps = len(preps), int(max_frames) + 1
-        D, V = int(self.cfg.d_model), self.cfg.ar_vocab()
+        D = int(self.cfg.d_model)
         lens = [int(p["txt_seq"].size(1)) for p in preps]
-        Ls = max(lens)
         cond = torch.stack([p["cond_ar"][0, :steps] for p in preps])
-        txt = torch.zeros(B, Ls, D, device=self.device)
+        txt = torch.zeros(B, max(lens), D, device=self.device)
         for i, p in enumerate(preps):
             txt[i, : lens[i]] = p["txt_seq"][0]
-        samp = self._sampling(top_p, temperature, anti_loop, 8, 0.85, 1.2, min_gen_frames, stop_on_first_eos)
-        nk = self._noise_cols(samp)
-        if seeds is None:  # one shared generator: utterance after utterance
-            tapes = [_Noise(steps, V, None, None).tape[:, :nk] for _ in range(B)]
-        else:  # independent private generators: draw them on a few host threads (the draws release the GIL)
-            from concurrent.futures import ThreadPoolExecutor
-
-            with ThreadPoolExecutor(max_workers=min(B, max(1, len(os.sched_getaffinity(0))))) as ex:
-                tapes = list(ex.map(lambda sd_: _Noise(steps, V, int(sd_), None).tape[:, :nk].contiguous(), seeds))
-        ses = self._checkout(B, steps, Ls)
-        try:
-            ses.begin(cond, txt, lens, torch.stack(tapes).contiguous(), samp)
-            ses.run()
-            toks, n, _ = ses.read()
-        finally:
-            self._release(ses)
+        toks, n = self.ar_generate_tensors(cond, txt, lens, max_frames=max_frames, top_p=top_p, temperature=temperature,
+                                           anti_loop=anti_loop, min_gen_frames=min_gen_frames, seeds=seeds,
+                                           stop_on_first_eos=stop_on_first_eos)
         return [toks[i, : n[i]].tolist() for i in range(B)]
 
     @torch.no_grad()
@@ -446,38 +464,40 @@ class SoproTTS:
     def synthesize_batch(self, texts: Sequence[str], *, ref: PreparedReference, max_frames: int = 400, top_p: float = 0.9,
                          temperature: float = 1.05, anti_loop: bool = True, style_strength: Optional[float] = None,
                          min_gen_frames: Optional[int] = None, seeds: Optional[Sequence[int]] = None) -> List[torch.Tensor]:
-        """NEW: B texts with one shared prepared reference -> B waveforms [1, 1, N_i]; the AR tokens of all
-        utterances come from one persistent kernel launch."""
+        """NEW: B texts with one shared prepared reference -> B waveforms [1, 1, N_i].  One batched prefill, one
+        persistent AR launch, one ragged NAR pass, padded Mimi decodes; utterance i equals synthesize(texts[i], seed=seeds[i])."""
         st = float(style_strength if style_strength is not None else self.cfg.style_strength)
-        preps = [self.model.prepare_conditioning(self.encode_text(t), ref, max_frames=max_frames, style_strength=st) for t in texts]
-        hists = self.model.ar_generate_batch(preps, max_frames=max_frames, top_p=top_p, temperature=temperature,
-                                             anti_loop=anti_loop, min_gen_frames=min_gen_frames, seeds=seeds)
-        eos = self.model.eos_id
-        Ts = [(h.index(eos) if eos in h else len(h)) for h in hists]
-        # NAR refiner: not causal, so only utterances of equal length share a batch
-        codes: List[Optional[torch.Tensor]] = [None] * len(texts)
-        by_len: Dict[int, List[int]] = {}
-        for i, T in enumerate(Ts):
-            if T > 0:
-                by_len.setdefault(T, []).append(i)
-        for T, idx in by_len.items():
-            cond = torch.cat([preps[i]["cond_ar"][:, :T] for i in idx], dim=0)
-            rvq1 = torch.tensor([hists[i][:T] for i in idx], device=self.device, dtype=torch.long)
-            full = self.model.nar_refine(cond, rvq1)  # [n, T, Q]
-            for j, i in enumerate(idx):
-                codes[i] = full[j]
-        # Mimi decode is causal and per-utterance: right-pad to the longest of a chunk, decode together, cut
+        model = self.model
+        ids = [self.encode_text(t) for t in texts]
+        txt_seq, lens, _pool, cond = model.prefill.run(ids, ref, n_frames=int(max_frames) + 1, style_strength=st)
+        toks, n = model.ar_generate_tensors(cond, txt_seq, lens, max_frames=max_frames, top_p=top_p, temperature=temperature,
+                                            anti_loop=anti_loop, min_gen_frames=min_gen_frames, seeds=seeds)
+        eos, B = model.eos_id, len(texts)
+        Ts = []
+        for i in range(B):
+            row = toks[i, : n[i]]
+            hit = (row == eos).nonzero()[0]
+            Ts.append(int(hit[0]) if hit.size else int(n[i]))
         out: List[torch.Tensor] = [torch.zeros(1, 1, 0, device=self.device) for _ in texts]
-        live = [i for i, T in enumerate(Ts) if T > 0]
+        Tmax = max(Ts)
+        if Tmax == 0:
+            return out
+        # NAR refiner over the ragged batch (not causal: `lens` makes the padding act as each utterance's zero padding)
+        rvq1 = torch.from_numpy(toks[:, :Tmax].copy()).to(self.device)
+        codes = model.nar_refine(cond[:, :Tmax], rvq1.clamp_(0, eos - 1), lens=torch.tensor(Ts, dtype=torch.int32))  # [B, Tmax, Q]
+        # Mimi decode is causal and per-utterance: right-pad to the longest of a chunk, decode together, cut
+        live = sorted((i for i in range(B) if Ts[i] > 0), key=lambda i: -Ts[i])
         hop = self.codec.engine.hop
+        cap = 12800  # frames per decode call (workspace bound)
         while live:
             chunk, frames = [], 0
-            while live and (not chunk or (len(chunk) + 1) * max(frames, Ts[live[0]]) <= 8192):
+            while live and (not chunk or (len(chunk) + 1) * max(frames, Ts[live[0]]) <= cap):
                 frames = max(frames, Ts[live[0]])
                 chunk.append(live.pop(0))
-            batch = torch.zeros(len(chunk), int(self.cfg.num_codebooks), frames, dtype=torch.int32, device=self.device)
-            for j, i in enumerate(chunk):
-                batch[j, :, : Ts[i]] = codes[i].permute(1, 0)
+            idx = torch.tensor(chunk, device=self.device)
+            batch = codes[idx, :frames].permute(0, 2, 1).to(torch.int32)
+            keep = torch.arange(frames, device=self.device)[None, :] < torch.tensor([Ts[i] for i in chunk], device=self.device)[:, None]
+            batch = (batch * keep[:, None, :]).contiguous()  # padding frames decode code 0; their samples are cut below
             wav = self.codec.engine.decode(batch)
             for j, i in enumerate(chunk):
                 out[i] = wav[j: j + 1, :, : Ts[i] * hop].clone()

@@ -20,10 +20,17 @@ class StreamConfig:
 
 
 class SoproTTSStreamer:
+    """Pipelined chunk loop.  Per chunk k, in device order:  AR(k) -> [NAR window + Mimi step](k) -> AR(k+1) -> ...
+    The host enqueues NAR + Mimi of chunk k on a side stream, then immediately enqueues AR(k+1) behind them (an event
+    keeps the persistent kernel, which takes every SM, from cutting in front of chunk k's audio), and only then waits
+    for chunk k's samples and yields them: the next AR launch runs while the consumer handles the audio, and the device
+    never waits for the host between launches.  The reference runs the three stages strictly in turn on one thread
+    (streaming.py:81-130)."""
+
     def __init__(self, tts, cfg: Optional[StreamConfig] = None):
         self.tts = tts
         self.cfg = cfg or StreamConfig()
-        self.mimi_stream = MimiStreamDecoder(tts.codec)
+        self.mimi_stream = MimiStreamDecoder(tts.codec, max_chunk_frames=max(16, int(self.cfg.chunk_frames)))
 
     @torch.inference_mode()
     def stream(self, text: str, *, ref_audio_path: Optional[str] = None, ref_tokens_tq: Optional[torch.Tensor] = None,
@@ -44,9 +51,14 @@ class SoproTTSStreamer:
         ctx = int(model.rf_nar() if ctx is None else ctx)
         hist: List[int] = []
         emitted = 0
-        state = MimiDecodeState()
+        state = self.mimi_stream.new_state()
+        on_gpu = tts.device.type == "cuda"
+        main = torch.cuda.current_stream(tts.device) if on_gpu else None
+        side = torch.cuda.Stream(tts.device) if on_gpu else None
 
         def refine_and_emit(end: int) -> Optional[torch.Tensor]:
+            """NAR over the new frames + `ctx` frames of left context, Mimi stream step on the new frames' codes
+            (reference streaming.py:81-104); enqueued on the side stream."""
             nonlocal emitted, state
             if end <= emitted:
                 return None
@@ -57,20 +69,40 @@ class SoproTTSStreamer:
             emitted = end
             return wav if wav.numel() > 0 else None
 
-        for _t, tok, is_eos in model.ar_stream(prep, max_frames=max_frames, top_p=top_p, temperature=temperature,
-                                               anti_loop=anti_loop, min_gen_frames=min_gen_frames, launch_frames=cf,
-                                               seed=seed, generator=generator):
-            if is_eos:  # streaming stops at the first EOS regardless of min_gen_frames (reference streaming.py:114-115)
-                break
-            hist.append(int(tok))
-            if len(hist) % cf == 0:
-                wav = refine_and_emit(len(hist))
+        progress = {"consumed": 0}
+        chunks = model.ar_chunks(prep, max_frames=max_frames, chunk_frames=cf, top_p=top_p, temperature=temperature,
+                                 anti_loop=anti_loop, min_gen_frames=min_gen_frames, seed=seed, generator=generator,
+                                 progress=progress)
+        try:
+            for toks, finished, prefetch in chunks:
+                # the stream ends at the first EOS regardless of min_gen_frames (reference streaming.py:114-115)
+                stop = model.eos_id in toks
+                if stop:
+                    toks = toks[: toks.index(model.eos_id)]
+                progress["consumed"] += len(toks) + (1 if stop else 0)  # the reference also draws for the EOS step
+                hist.extend(toks)
+                last = stop or finished
+                end = len(hist) if last else (len(hist) // cf) * cf
+                wav = None
+                if on_gpu:
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        wav = refine_and_emit(end)
+                    if not last:
+                        main.wait_stream(side)  # AR(k+1) behind chunk k's NAR + Mimi, never in front of them
+                        prefetch()
+                    side.synchronize()
+                    if wav is not None:
+                        wav.record_stream(main)
+                else:
+                    wav = refine_and_emit(end)
                 if wav is not None:
                     yield wav
-        if emitted < len(hist):
-            wav = refine_and_emit(len(hist))
-            if wav is not None:
-                yield wav
+                if last:
+                    break
+        finally:
+            chunks.close()
+            self.mimi_stream.release(state)
 
 
 @torch.inference_mode()

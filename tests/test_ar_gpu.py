@@ -199,6 +199,24 @@ def test_batch_equals_each_utterance_alone(team):
         assert toks[i, : nn[i]].tolist() == want[i], f"utterance {i} (L={lens[i]})"
 
 
+_WORKER_CACHE = {}
+
+
+def _oracle_tokens_worker(args):
+    """One utterance of the full-size case on the CPU oracle (runs in a worker process: 64 of them are ~1 CPU-minute)."""
+    i, steps, L = args
+    torch.set_num_threads(2)
+    torch.set_grad_enabled(False)
+    if "full" not in _WORKER_CACHE:
+        _WORKER_CACHE["full"] = ar_case_inputs(AR_CASES["default_bf16"])[:2]
+    cfg, sd = _WORKER_CACHE["full"]
+    D = int(cfg.d_model)
+    cond = _unit(steps * D, 7000 + i).view(1, steps, D)
+    txt = _unit(L * D, 7500 + i).view(1, L, D)
+    return i, O.ar_generate(sd, cfg, cond, txt, torch.ones(1, L, dtype=torch.bool), max_frames=steps - 1,
+                            sampling=O.ArSampling(min_gen_frames=10 ** 9), noise_tv=O.noise_tape(300 + i, steps, cfg.ar_vocab()))
+
+
 def _near_tie_margin(sd, cfg, cond_i, txt_i, samp, tape, want, t):
     """Relative distance to the nearest decision boundary of the oracle's sampler at step `t` (oracle history):
     the two best ratios p_sorted[j] / q[j] of the draw, and the top-p cut (cum[j] vs top_p)."""
@@ -248,8 +266,12 @@ def test_full_size_batch64_properties():
         assert (nn == steps).all()
     assert np.array_equal(out[0], out[1])
     assert len({tuple(r) for r in out[0].tolist()}) == n  # 64 different utterances
-    want = [O.ar_generate(sd, cfg, cond[i:i + 1], txt[i:i + 1], torch.ones(1, L, dtype=torch.bool), max_frames=steps - 1,
-                          sampling=samp, noise_tv=full_tapes[i]) for i in range(n)]
+    import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
+
+    workers = max(1, min(16, (os.cpu_count() or 2) // 2))
+    with ProcessPoolExecutor(max_workers=workers, mp_context=mp.get_context("spawn")) as ex:
+        want = [toks for _i, toks in sorted(ex.map(_oracle_tokens_worker, [(i, steps, L) for i in range(n)]))]
     forced = torch.tensor(want, dtype=torch.int32)
     ses.set_forced(forced)
     ses.begin(cond, txt, [L] * n, tapes, _sampling(samp, cfg))

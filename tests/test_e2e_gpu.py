@@ -44,12 +44,20 @@ def test_synthesize_matches_oracle_pipeline():
                                      min_gen_frames=10 ** 9)
     assert toks.shape == (F + 1, 32)
     assert toks[:, 0].tolist() == want  # AR ids bit-identical
-    # NAR: argmax of torch ops on GPU vs CPU may flip on exact near-ties only
-    from sopro_b200 import prefill as P
+    # NAR (CUDA kernels): ids identical to the CPU oracle (pinned to the reference's tokens); a difference is accepted
+    # only at an id whose two best logits are within 1e-5 (relative) of a tie in the oracle, checked teacher-forced
+    from oracle import nar_oracle as N
 
-    nar_cpu = P.nar_refine({k: v.cpu() for k, v in tts.model.sd.items()}, cfg, prep["cond_ar"][:, : F + 1].cpu(),
-                           torch.tensor(want).unsqueeze(0))[0]
-    assert float((nar_cpu == toks.cpu()).float().mean()) >= 0.995
+    nar_cpu, margin = N.nar_refine({k: v.cpu() for k, v in sd.items()}, cfg, prep["cond_ar"][:, : F + 1].cpu(), torch.tensor(want).unsqueeze(0))
+    if not torch.equal(nar_cpu[0], toks.cpu()):
+        tts.model.nar.set_forced(nar_cpu)
+        try:
+            tf = tts.model.nar_refine(prep["cond_ar"][:, : F + 1], torch.tensor(want, device=tts.device).unsqueeze(0)).cpu()
+        finally:
+            tts.model.nar.set_forced(None)
+        bad = [(tuple(i), float(margin[tuple(i)])) for i in (tf != nar_cpu).nonzero().tolist()]
+        print("NAR ids differing from the oracle (teacher-forced) -> oracle top-2 margin:", bad)
+        assert bad and len(bad) <= 1 and all(m < 1e-5 for _i, m in bad), bad
     # Mimi: decode the product's own tokens with the oracle
     ref_wav = M.mimi_decode(mimi_sd, toks.cpu().permute(1, 0).unsqueeze(0))
     err = float((wav.cpu() - ref_wav).abs().max())

@@ -1,9 +1,10 @@
 """Host-side control flow of the public API (synthesize / synthesize_batch / stream) WITHOUT a GPU.
 
-The product has no CPU path, so the two CUDA engines are replaced here, in the test only, by fakes that answer
-through the CPU oracles (oracle/ar_oracle.py, oracle/mimi_oracle.py).  What is under test is everything around the
-kernels in sopro_b200/model.py, streaming.py and codec.py: lazy noise blocks, launch chunking, EOS handling, grouping by
-length for the NAR refiner, right-padding and cutting of the batched Mimi decode, streaming chunk sizes.
+The product has no CPU path, so the four CUDA engines (prefill, AR, NAR, Mimi) are replaced here, in the test only, by
+fakes that answer through the CPU oracles (oracle/ar_oracle.py, oracle/nar_oracle.py, oracle/mimi_oracle.py and the torch
+restatement of the prefill).  What is under test is everything around the kernels in sopro_b200/model.py, streaming.py and
+codec.py: lazy noise blocks, launch chunking, EOS handling, the ragged NAR batch, right-padding and cutting of the batched
+Mimi decode, streaming chunk sizes, session check-out.
 """
 import numpy as np
 import pytest
@@ -11,6 +12,7 @@ import torch
 
 from oracle import ar_oracle as O
 from oracle import mimi_oracle as M
+from oracle import nar_oracle as N
 from sopro_b200 import prefill as P
 from sopro_b200.codec import MimiStreamDecoder
 from sopro_b200.config import SoproTTSConfig
@@ -88,12 +90,58 @@ class _FakeArEngine:
         return _FakeSession(self, B, steps, L)
 
 
+class _FakePrefill:
+    """sopro_b200.prefill_cuda.PrefillEngine.run through the torch restatement (bit-equal to the reference on CPU)."""
+
+    def __init__(self, m):
+        self.m = m
+
+    def run(self, text_ids, ref, *, n_frames, style_strength):
+        preps = [P.prepare_conditioning(self.m.sd, self.m.cfg, ids, ref, max_frames=n_frames - 1, device="cpu",
+                                        style_strength=style_strength, text_pos=self.m.text_pos, frame_pos=self.m.frame_pos)
+                 for ids in text_ids]
+        lens = [int(p["txt_seq"].size(1)) for p in preps]
+        txt = torch.zeros(len(preps), max(lens), int(self.m.cfg.d_model))
+        for i, p in enumerate(preps):
+            txt[i, : lens[i]] = p["txt_seq"][0]
+        return txt, lens, torch.cat([p["txt_pool"] for p in preps]), torch.cat([p["cond_ar"] for p in preps])
+
+
+class _FakeNar:
+    """sopro_b200.nar.NarEngine.refine through oracle/nar_oracle.py, utterance by utterance over its valid frames."""
+
+    def __init__(self, m):
+        self.m = m
+
+    def refine(self, cond, rvq1, lens=None):
+        B, T, _ = cond.shape
+        out = torch.zeros(B, T, int(self.m.cfg.num_codebooks), dtype=torch.long)
+        for b in range(B):
+            n = T if lens is None else int(lens[b])
+            if n:
+                out[b, :n] = N.nar_refine(self.m.sd, self.m.cfg, cond[b:b + 1, :n].cpu(), rvq1[b:b + 1, :n].cpu().long())[0][0]
+        return out
+
+
+class _FakeMimiStream:
+    def __init__(self, eng):
+        self.eng, self.hist = eng, None
+
+    def step(self, codes_qn):
+        self.hist = codes_qn if self.hist is None else torch.cat([self.hist, codes_qn], dim=1)
+        wav = self.eng.decode(self.hist.unsqueeze(0)).reshape(1, -1)
+        return wav[:, (self.hist.shape[1] - codes_qn.shape[1]) * 1920:]
+
+
 class _FakeMimiEngine:
     hop = 1920
     precision = "oracle"
 
     def __init__(self, msd):
         self.msd, self.calls = msd, []
+
+    def stream(self, max_chunk_frames=16):
+        return _FakeMimiStream(self)
 
     def decode(self, codes_bqt):
         self.calls.append(tuple(codes_bqt.shape))
@@ -123,8 +171,10 @@ def tts():
     m.sd = {k: v.float() for k, v in sd.items() if not k.startswith(skip) and v.is_floating_point()}
     m.text_pos = P.sinusoid_table(int(cfg.max_text_len) + 8, int(cfg.d_model), "cpu")
     m.frame_pos = P.sinusoid_table(int(cfg.pos_emb_max) + 8, int(cfg.d_model), "cpu")
-    m._sessions, m._prep_graphs, m._prep_seen, m._nar_cache, m._nar_graphs, m._nar_seen = {}, {}, {}, {}, {}, {}
-    m.use_cuda_graphs = False
+    import threading
+
+    m._sessions, m._sessions_busy, m._sessions_lock = {}, set(), threading.Lock()
+    m.prefill, m.nar = _FakePrefill(m), _FakeNar(m)
     t = SoproTTS(model=m, cfg=cfg, tokenizer=IdsTokenizer(1000), codec=_FakeCodec(M.synth_mimi_state_dict()), device="cpu")
     t.ref = t.prepare_reference(ref_tokens_tq=torch.randint(0, 2048, (12, 32), generator=torch.Generator().manual_seed(7)))
     return t
@@ -190,9 +240,9 @@ def test_stream_nar_windows_follow_the_reference(tts, monkeypatch):
     seen = []
     real = tts.model.nar_refine
 
-    def spy(cond, rvq1):
+    def spy(cond, rvq1, lens=None):
         seen.append((int(cond.shape[1]), rvq1[0].tolist()))
-        return real(cond, rvq1)
+        return real(cond, rvq1, lens)
 
     monkeypatch.setattr(tts.model, "nar_refine", spy)
     prep = tts.model.prepare_conditioning(tts.encode_text(TEXTS[1]), tts.ref, max_frames=KW["max_frames"],

@@ -171,7 +171,10 @@ def test_host_buffer_path_and_stream_decoder(precision):
         parts.append(wav.cpu().numpy())
     got = np.concatenate(parts, axis=1)
     assert got.shape == (1, 20 * 1920) and state.frames_seen == 20
-    np.testing.assert_allclose(got[0], full[0, 0], rtol=0, atol=1e-5 * max(1.0, float(np.abs(full).max())))
+    if precision == "fp32":  # the persistent-state stream decoder computes every sample in the one-shot decode's order
+        np.testing.assert_array_equal(got[0], full[0, 0])
+    else:  # tensor-core mode: same tcgen05 tiles, the attention core runs in fp32 over the K/V ring (tolerance 4e-3 of peak)
+        np.testing.assert_allclose(got[0], full[0, 0], rtol=0, atol=4e-3 * float(np.abs(full).max()))
 
 
 def test_small_decodes_replay_from_graphs_identically():

@@ -66,3 +66,24 @@ def test_repeated_tail():
     assert not O.repeated_tail(list(range(40)))
     h = list(range(16)) * 2
     assert O.repeated_tail(h) and not O.repeated_tail(list(range(17)) * 2, 16)
+
+
+def test_nar_oracle_reproduces_the_reference_tokens():
+    """oracle/nar_oracle.py against the 50 x 32 tokens the unmodified reference wrote (make_golden_e2e.py)."""
+    import numpy as np
+
+    from oracle import nar_oracle as N
+    from sopro_b200 import prefill as P
+    from tests.cases import e2e_inputs
+
+    cfg, sd, inp = e2e_inputs()
+    g = np.load(os.path.join(GOLD, "e2e_prefill.npz"))
+    dev = torch.device("cpu")
+    pr = P.prepare_reference(sd, cfg, inp["ref_tokens_tq"], dev)
+    tpos = P.sinusoid_table(int(cfg.max_text_len) + 8, int(cfg.d_model), dev)
+    fpos = P.sinusoid_table(int(cfg.pos_emb_max) + 8, int(cfg.d_model), dev)
+    prep = P.prepare_conditioning(sd, cfg, inp["text_ids"], pr, max_frames=inp["max_frames"], device=dev,
+                                  style_strength=inp["style_strength"], text_pos=tpos, frame_pos=fpos)
+    codes, margin = N.nar_refine(sd, cfg, prep["cond_ar"][:, : inp["nar_T"]], inp["rvq1"].unsqueeze(0))
+    assert torch.equal(codes[0], torch.from_numpy(g["nar_tokens"].astype(np.int64)))
+    assert float(margin[0, :, 1:].min()) > 0

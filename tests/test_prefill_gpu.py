@@ -1,0 +1,84 @@
+"""GPU parity of the CUDA prefill (sopro_prefill_run through the C-ABI) against (a) rows the unmodified reference
+wrote (tests/golden/e2e_prefill.npz) and (b) the torch-CPU restatement sopro_b200/prefill.py, which is bit-equal to the
+reference on CPU (tests/test_host_cpu.py).  cond_ar / txt_seq are inputs of the id-exact AR kernel: tolerance 2e-5."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.cases import e2e_inputs
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+torch.set_grad_enabled(False)
+_S = {}
+
+
+def _setup():
+    from sopro_b200 import prefill as P
+    from sopro_b200.prefill_cuda import PrefillEngine
+
+    if "e" not in _S:
+        cfg, sd, inp = e2e_inputs()
+        tpos = P.sinusoid_table(int(cfg.max_text_len) + 8, int(cfg.d_model), "cpu")
+        fpos = P.sinusoid_table(int(cfg.pos_emb_max) + 8, int(cfg.d_model), "cpu")
+        _S["e"] = PrefillEngine(cfg, sd, 0, tpos, fpos)
+        _S["pos"] = (tpos, fpos)
+        _S["ref"] = P.prepare_reference(sd, cfg, inp["ref_tokens_tq"], torch.device("cpu"))
+    return _S["e"], _S["ref"], _S["pos"]
+
+
+def test_prefill_matches_reference_fixture_rows():
+    eng, ref, _ = _setup()
+    cfg, sd, inp = e2e_inputs()
+    g = np.load(os.path.join(GOLD, "e2e_prefill.npz"))
+    txt, lens, pool, cond = eng.run([inp["text_ids"]], ref, n_frames=inp["max_frames"] + 1, style_strength=inp["style_strength"])
+    tol = dict(rtol=0, atol=2e-5)
+    np.testing.assert_allclose(txt[0, :4].cpu().numpy(), g["txt_seq_rows"], **tol)
+    np.testing.assert_allclose(pool.cpu().numpy(), g["txt_pool"], **tol)
+    np.testing.assert_allclose(cond[0, g["cond_rows_idx"].tolist()].cpu().numpy(), g["cond_rows"], **tol)
+    assert abs(float(cond.abs().mean()) - float(g["cond_absmean"])) < 1e-5
+    assert cond.shape == (1, inp["max_frames"] + 1, 384) and lens == [52]
+
+
+def test_batched_prefill_equals_the_cpu_restatement_per_text():
+    """Ragged texts (1 .. 300 ids) in one pass: every utterance equals the batch-1 restatement on its own text."""
+    from sopro_b200 import prefill as P
+
+    eng, ref, (tpos, fpos) = _setup()
+    cfg, sd, inp = e2e_inputs()
+    g = torch.Generator().manual_seed(8)
+    texts = [torch.randint(0, 1000, (n,), generator=g) for n in (52, 1, 7, 300, 52, 33)]
+    F = 60
+    txt, lens, pool, cond = eng.run(texts, ref, n_frames=F + 1, style_strength=1.2)
+    assert lens == [52, 1, 7, 300, 52, 33]
+    worst = 0.0
+    for i, ids in enumerate(texts):
+        want = P.prepare_conditioning(sd, cfg, ids, ref, max_frames=F, device="cpu", style_strength=1.2, text_pos=tpos, frame_pos=fpos)
+        for got, w in ((txt[i, : lens[i]], want["txt_seq"][0]), (pool[i], want["txt_pool"][0]), (cond[i], want["cond_ar"][0])):
+            err = float((got.cpu() - w).abs().max())
+            worst = max(worst, err)
+            assert err <= 2e-5, (i, err)
+    print(f"batched prefill vs CPU restatement: max abs err {worst:.2e}")
+    # batch invariance: the same text alone gives the same rows bit for bit
+    t1, l1, p1, c1 = eng.run([texts[2]], ref, n_frames=F + 1, style_strength=1.2)
+    assert torch.equal(c1[0], cond[2]) and torch.equal(t1[0, :7], txt[2, :7])
+
+
+def test_public_prepare_conditioning_feeds_the_ar_kernel():
+    """Through SoproModel: prep dict shapes/keys of reference model.py:210-216."""
+    from oracle import mimi_oracle as M
+    from sopro_b200 import SoproTTS
+    from sopro_b200.tokenizer import IdsTokenizer
+
+    cfg, sd, inp = e2e_inputs()
+    if "tts" not in _S:
+        _S["tts"] = SoproTTS.from_state_dict(cfg, sd, IdsTokenizer(1000), M.synth_mimi_state_dict(), device="cuda:0")
+    tts = _S["tts"]
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    prep = tts.model.prepare_conditioning(inp["text_ids"], ref, max_frames=40, style_strength=1.0)
+    assert set(prep) == {"txt_seq", "text_mask", "txt_pool", "sv_ref", "cond_ar"}
+    assert prep["txt_seq"].shape == (1, 52, 384) and prep["cond_ar"].shape == (1, 41, 384) and prep["text_mask"].all()
+    many = tts.model.prepare_conditioning_batch([inp["text_ids"], inp["text_ids"][:9]], ref, max_frames=40, style_strength=1.0)
+    assert torch.equal(many[0]["cond_ar"], prep["cond_ar"]) and many[1]["txt_seq"].shape == (1, 9, 384)
