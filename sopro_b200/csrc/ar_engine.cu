@@ -111,7 +111,8 @@ struct sopro_ar_session {
   int* n_tiles = nullptr;     // [n_sms]
   unsigned char* stage_tiles = nullptr;  // [n_sms][kMaxStages]
   std::vector<unsigned char> h_stage_tiles;
-  int tile_P = -1, tile_wbuf = -1;
+  int tile_P = -1, tile_wbuf = -1, tile_qatt = -1;
+  bool qatt = false;  // this launch geometry uses the fused q + attention stage
   std::vector<TileDesc> h_tiles;
   std::vector<int> h_ntiles;
   // staging for the host-buffer path
@@ -524,33 +525,50 @@ struct StageW {
   const void* w;
   int N, K, parts;    // parts = 2 for the GLU (value rows + gate rows of the same channels)
   const float* epi;   // GLU: packed [D][KcE] epilogue rows; else the bias vector [N] (or null)
+  bool by_head;       // fused q + attention stage: rank r gets ALL rows of head r % H (ranks >= H * (P / H): none)
 };
+
+// the fused q-projection + attention stage needs at least one CTA per head
+static bool use_qatt(const sopro_engine* e, int P) {
+  static const bool off = getenv("SOPRO_AR_QATT") && atoi(getenv("SOPRO_AR_QATT")) == 0;
+  return !off && P >= e->H;
+}
 
 static int build_tiles(sopro_ar_session* s, int P, int wbuf, cudaStream_t st) {
   sopro_engine* e = s->e;
-  if (s->tile_P == P && s->tile_wbuf == wbuf) return SOPRO_OK;
+  const bool qatt = s->qatt;
+  if (s->tile_P == P && s->tile_wbuf == wbuf && s->tile_qatt == (int)qatt) return SOPRO_OK;
   const size_t wsz = e->cfg.weight_dtype == SOPRO_W_F32 ? 4 : 2;
   std::vector<StageW> prog;
   int si = 0;  // must mirror the stage program built in launch_ar
   for (int i = 0; i < e->n_layers; ++i) {
     const LayerDev& L = e->layer[i];
-    prog.push_back({si++, L.glu_w, e->D, e->D, 2, e->epi[i]});
-    prog.push_back({si++, L.w1, e->F, e->D, 1, L.b1});
-    prog.push_back({si++, L.w2, e->D, e->F, 1, L.b2});
+    prog.push_back({si++, L.glu_w, e->D, e->D, 2, e->epi[i], false});
+    prog.push_back({si++, L.w1, e->F, e->D, 1, L.b1, false});
+    prog.push_back({si++, L.w2, e->D, e->F, 1, L.b2, false});
     if (L.has_attn) {
-      prog.push_back({si++, L.wq, e->D, e->D, 1, nullptr});
-      si++;  // attention core: no weights
-      prog.push_back({si++, L.wo, e->D, e->D, 1, nullptr});
+      if (qatt) {
+        prog.push_back({si++, L.wq, e->D, e->D, 1, nullptr, true});
+      } else {
+        prog.push_back({si++, L.wq, e->D, e->D, 1, nullptr, false});
+        si++;  // attention core: no weights
+      }
+      prog.push_back({si++, L.wo, e->D, e->D, 1, nullptr, false});
     }
   }
-  prog.push_back({si++, e->head_w, e->V, e->D, 1, e->head_b});
+  prog.push_back({si++, e->head_w, e->V, e->D, 1, e->head_b, false});
   s->h_stage_tiles.assign((size_t)P * kMaxStages, 0);
   s->h_tiles.assign((size_t)P * kMaxTilesPerStep, TileDesc{});
   s->h_ntiles.assign(P, 0);
   for (int r = 0; r < P; ++r) {
     int n = 0;
     for (const StageW& sw : prog) {
-      const int n0 = (int)(((long long)sw.N * r) / P), n1 = (int)(((long long)sw.N * (r + 1)) / P);
+      int n0 = (int)(((long long)sw.N * r) / P), n1 = (int)(((long long)sw.N * (r + 1)) / P);
+      if (sw.by_head) {
+        const int PH = P / e->H;
+        n0 = r < e->H * PH ? (r % e->H) * e->Dh : 0;
+        n1 = r < e->H * PH ? n0 + e->Dh : 0;
+      }
       const size_t row_bytes = (size_t)sw.K * wsz;
       // per row: weights (x parts) + epilogue constants (GLU: KcE floats; else 1 bias float, +32 B span slack)
       const size_t epi_row = sw.parts == 2 ? (size_t)e->KcE * 4 : (sw.epi ? 4 : 0);
@@ -591,6 +609,7 @@ static int build_tiles(sopro_ar_session* s, int P, int wbuf, cudaStream_t st) {
   CK(cudaMemcpyAsync(s->stage_tiles, s->h_stage_tiles.data(), s->h_stage_tiles.size(), cudaMemcpyHostToDevice, st));
   s->tile_P = P;
   s->tile_wbuf = wbuf;
+  s->tile_qatt = (int)qatt;
   return SOPRO_OK;
 }
 
@@ -687,18 +706,11 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.t_begin = t_begin;
   p.t_end = t_end;
   const size_t need_act = std::max((size_t)Bt * e->F * 4, (size_t)2 * Bt * e->D * 4 + (size_t)kWarps * kTapSlots * e->KcP * 4);
-  const int att_lc = std::min(128, s->Lmax);
-  const size_t need_att_long = ((size_t)s->Lmax + (size_t)kWarps * e->Dh + (size_t)kWarps * 8 * e->Dh) * 4;
-  const size_t need_att_fast = ((size_t)e->Dh + att_lc + (size_t)16 * e->Dh + (size_t)2 * att_lc * e->Dh) * 4;
-  const size_t need_att = std::max(need_att_fast, s->Lmax > att_lc ? need_att_long : (size_t)0);
+  // attention: per 256-thread group q[Dh] + scores[Lmax] + partial outputs; K / V are read straight from L2
+  const size_t need_att_base = (size_t)2 * (e->Dh + att_group_floats(s->Lmax, e->Dh)) * 4;
   const size_t need_smp = (size_t)e->Vpad * 8 + e->Vpad + 16;
-  const size_t act_bytes = align_up(std::max(need_act, std::max(need_att, need_smp)), 128);
   const size_t kSmemCap = 214 * 1024;  // 227 KB minus static shared memory (sampler scratch, mbarriers)
   const size_t table_bytes = (size_t)kMaxTilesPerStep * sizeof(TileDesc);
-  if (act_bytes + table_bytes + 2 * 4096 > kSmemCap)
-    return fail(SOPRO_ERR_INVALID, "shared memory: activations need %zu B (Bt=%d, Lmax=%d), nothing left for weights",
-                act_bytes, Bt, s->Lmax);
-  const size_t avail = kSmemCap - act_bytes - table_bytes;
   const size_t wsz = e->cfg.weight_dtype == SOPRO_W_F32 ? 4 : 2;
   auto slice_bytes = [&](int N, int K, int parts) {
     const size_t rows = (size_t)((N + P - 1) / P);
@@ -707,15 +719,41 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   size_t full = std::max(std::max(slice_bytes(e->D, e->D, 2), slice_bytes(e->F, e->D, 1)),
                          std::max(slice_bytes(e->D, e->F, 1), slice_bytes(e->V, e->D, 1)));
   full = align_up(full, 128);
-  size_t wbuf;
-  int nbuf;
-  if (2 * full <= avail) {
-    wbuf = full;
-    nbuf = (int)std::min<size_t>(kMaxWBuf, avail / wbuf);
-  } else {
-    wbuf = (avail / 2) / 128 * 128;
-    nbuf = 2;
+  // The fused q + attention stage (one exchange and one GEMV stage fewer per attention layer) streams a whole head's
+  // Wq rows through every serving CTA: taken when that head tile fits at most two ring buffers (batched launches); a
+  // batch-1 launch, whose 148 CTAs hold slivers of every matrix, keeps the q stage spread over all CTAs.
+  size_t act_bytes = 0, wbuf = 0;
+  int nbuf = 0, PH = 1;
+  bool qatt = use_qatt(e, P);
+  for (;;) {
+    size_t need_att = need_att_base;
+    PH = qatt ? P / e->H : 1;
+    if (qatt) need_att += (size_t)((Bt + PH - 1) / PH) * (e->D + e->Dh) * 4;  // + the fused stage's x rows and q rows
+    act_bytes = align_up(std::max(need_act, std::max(need_att, need_smp)), 128);
+    if (act_bytes + table_bytes + 2 * 4096 > kSmemCap) {
+      if (qatt) {
+        qatt = false;
+        continue;
+      }
+      return fail(SOPRO_ERR_INVALID, "shared memory: activations need %zu B (Bt=%d, Lmax=%d), nothing left for weights",
+                  act_bytes, Bt, s->Lmax);
+    }
+    const size_t avail = kSmemCap - act_bytes - table_bytes;
+    if (2 * full <= avail) {
+      wbuf = full;
+      nbuf = (int)std::min<size_t>(kMaxWBuf, avail / wbuf);
+    } else {
+      wbuf = (avail / 2) / 128 * 128;
+      nbuf = 2;
+    }
+    if (qatt && (size_t)e->Dh * e->D * wsz + 64 > 2 * wbuf) {
+      qatt = false;
+      continue;
+    }
+    break;
   }
+  p.PH = PH;
+  s->qatt = qatt;
   int rc = build_tiles(s, P, (int)wbuf, st);
   if (rc != SOPRO_OK) return rc;
   p.tiles = s->tiles;
@@ -724,7 +762,6 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   p.nbuf = nbuf;
   p.wbuf_bytes = (int)wbuf;
   p.act_bytes = (int)act_bytes;
-  p.att_lc = att_lc;
   const size_t smem = act_bytes + (size_t)nbuf * wbuf + table_bytes;
   // ---- stage program of one step
   {
@@ -734,8 +771,12 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
       p.prog[n++] = {K_FFN1, (unsigned char)i};
       p.prog[n++] = {K_FFN2, (unsigned char)i};
       if (e->layer[i].has_attn) {
-        p.prog[n++] = {K_Q, (unsigned char)i};
-        p.prog[n++] = {K_ATT, (unsigned char)i};
+        if (qatt) {
+          p.prog[n++] = {K_QATT, (unsigned char)i};
+        } else {
+          p.prog[n++] = {K_Q, (unsigned char)i};
+          p.prog[n++] = {K_ATT, (unsigned char)i};
+        }
         p.prog[n++] = {K_O, (unsigned char)i};
       }
     }

@@ -43,7 +43,7 @@ constexpr int kMaxStages = 6 * kMaxLayers + 2;
 constexpr int kMaxTilesPerStep = 256;
 constexpr int kMaxWBuf = 8;
 
-enum StageKind { K_GLU = 0, K_FFN1 = 1, K_FFN2 = 2, K_Q = 3, K_O = 4, K_HEAD = 5, K_ATT = 6, K_SAMPLE = 7 };
+enum StageKind { K_GLU = 0, K_FFN1 = 1, K_FFN2 = 2, K_Q = 3, K_O = 4, K_HEAD = 5, K_ATT = 6, K_SAMPLE = 7, K_QATT = 8 };
 
 struct LayerDev {
   const float* norm_w;
@@ -139,10 +139,10 @@ struct ArParams {
   const int* n_tiles;     // [P] tiles per step of each rank
   const unsigned char* stage_tiles;  // [P][kMaxStages] tiles of each stage
   int nbuf, wbuf_bytes, act_bytes;
-  int att_lc;  // keys whose K/V fit the attention stage's shared memory (longer texts take the cold path)
   long long* timing;  // debug: [grid][kTimingSlots] clock64 stamps of step `timing_step` (null = off)
   int timing_step;
   int g, P, Bt;
+  int PH;  // fused Q+attention stage: CTAs per head (P / H); rank r serves head r % H, utterances r / H + j*PH
   int t_begin, t_end;
 };
 
@@ -582,157 +582,115 @@ struct TeamCtx {
 };
 
 // ---------------------------------------------------------------------------
-// COLD path of the cross-attention: texts longer than the shared-memory K/V capacity (p.att_lc keys).
-// One item; the 16 warps split the keys, lanes split the head dimension, K/V rows stream from L2.
-// smem: sc[Lmax] scores, part[kWarps][Dh] per-warp partial outputs, [kWarps][2][4][Dh] K/V rows.
+// Cached text cross-attention core (nn/text.py:101-128): softmax(q.K^T / sqrt(Dh)) . V in fp32 over the keys
+// l < text_len, ONE (utterance, head) item per GROUP of 256 threads, two items side by side in a CTA.
+//   1. scores: 8 threads per key read the key row straight from L2 (the K/V caches are read-only during the launch:
+//      no shared-memory staging, any text length), 3-step shuffle reduction -> sc[l] in shared memory
+//   2. max / sum: every warp of the group, redundantly
+//   3. output: thread (g, c) accumulates the keys l = g mod G for the float4 chunk c of the head dimension
+//      (G = 256 / (Dh/4) key groups, one L2 round trip with every load in flight)
+//   4. fixed-order sum over the key groups, normalise, nan_to_num (nn/text.py:128), store
+// Groups synchronise with named barriers (ids 1, 2), never with the CTA barrier.
+// smem per group: sc[Lp] | part[kAttG][Dh]
 // ---------------------------------------------------------------------------
-__device__ __noinline__ void attention_item_long(const ArParams& p, int li, int item, int b0,
-                                                 float* __restrict__ smem, int ll, unsigned q_seq, unsigned out_seq) {
-  const LayerDev& L = p.layer[li];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int H = p.H, Dh = p.Dh, D = p.D, Lmax = p.Lmax;
-  float* sc = smem;
-  float* part = smem + Lmax;
-  const unsigned kv_s = smem_u32(part + (size_t)kWarps * Dh);
-  const float scale = 1.0f / sqrtf((float)Dh);
-  const int d4 = lane * 4;
-  const bool act_lane = d4 < Dh;
-  constexpr int PF = 4;
-  {
-    const int u = item / H, h = item % H;
-    const int b = b0 + u;
-    const int len = p.text_len[b];
-    const size_t kv_off = ((((size_t)L.attn_slot * p.B + b) * H + h) * Lmax) * Dh;
-    const float* Kp = p.kc + kv_off;
-    const float* Vp = p.vc + kv_off;
-    // q (registers) and the first PF K/V rows of this warp (cp.async -> shared, no registers held)
-    // are requested together
-    const unsigned kS = kv_s + (unsigned)warp * (unsigned)(2 * PF * Dh * 4);
-    const unsigned vS = kS + (unsigned)(PF * Dh * 4);
-    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (act_lane) {
-#pragma unroll 1
-      for (int i = 0; i < PF; ++i) {
-        const int l = warp + i * kWarps;
-        if (l < len) {
-          cp_async16(kS + (unsigned)(i * Dh + d4) * 4u, Kp + (size_t)l * Dh + d4);
-          cp_async16(vS + (unsigned)(i * Dh + d4) * 4u, Vp + (size_t)l * Dh + d4);
-        }
-      }
-      const size_t qoff = (size_t)b * D + (size_t)h * Dh + d4;
-      if (ll) {
-        uint4 a, c;
-        do {
-          a = ll_load2(p.qbuf + qoff * 2);
-          c = ll_load2(p.qbuf + qoff * 2 + 4);
-        } while (a.y != q_seq || a.w != q_seq || c.y != q_seq || c.w != q_seq);
-        q4 = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(c.x), __uint_as_float(c.z));
-      } else {
-        q4 = ldcg4(p.qbuf + qoff);
-      }
-    }
-    cp_async_commit();
-    cp_async_wait0();
-    // phase 1: scores of this warp's keys
-    {
-      int i = 0;
-#pragma unroll 1
-      for (int l = warp; l < len; l += kWarps, ++i) {
-        float s = 0.f;
-        if (act_lane) {
-          const float4 kk = (i < PF) ? lds128(kS + (unsigned)(i * Dh + d4) * 4u)
-                                     : __ldg(reinterpret_cast<const float4*>(Kp + (size_t)l * Dh + d4));
-          s = kk.x * q4.x + kk.y * q4.y + kk.z * q4.z + kk.w * q4.w;
-        }
-        s = warp_sum(s);
-        if (lane == 0) sc[l] = s * scale;
-      }
-    }
-    __syncthreads();
-    // phase 2: max / sum over all keys (every warp, redundantly), weighted V rows of own keys
-    float mx = -INFINITY;
-    for (int l = lane; l < len; l += 32) mx = fmaxf(mx, sc[l]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int l = lane; l < len; l += 32) sum += expf(sc[l] - mx);
-    sum = warp_sum(sum);
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    {
-      int i = 0;
-#pragma unroll 1
-      for (int l = warp; l < len; l += kWarps, ++i) {
-        const float e = expf(sc[l] - mx);
-        if (act_lane) {
-          const float4 vv = (i < PF) ? lds128(vS + (unsigned)(i * Dh + d4) * 4u)
-                                     : __ldg(reinterpret_cast<const float4*>(Vp + (size_t)l * Dh + d4));
-          o.x += e * vv.x;
-          o.y += e * vv.y;
-          o.z += e * vv.z;
-          o.w += e * vv.w;
-        }
-      }
-    }
-    if (act_lane) *reinterpret_cast<float4*>(part + (size_t)warp * Dh + d4) = o;
-    __syncthreads();
-    // phase 3: fixed-order sum of the warp partials, normalise, nan_to_num (nn/text.py:128)
-    for (int d = threadIdx.x; d < Dh; d += kThreads) {
-      float acc = 0.f;
-#pragma unroll 1
-      for (int w = 0; w < kWarps; ++w) acc += part[(size_t)w * Dh + d];
-      acc = acc / sum;
-      if (!isfinite(acc)) acc = 0.f;
-      const size_t aoff = (size_t)b * D + (size_t)h * Dh + d;
-      if (ll) ll_store(p.abuf + aoff * 2, acc, out_seq);
-      else p.abuf[aoff] = acc;
-    }
-    __syncthreads();
-  }
+constexpr int kAttGroup = 256;
+constexpr int kAttG = 32;  // upper bound of the key groups (Dh >= 32)
+
+__device__ __forceinline__ void group_sync(int grp) {
+  asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(kAttGroup) : "memory");
 }
 
-// ---------------------------------------------------------------------------
-// Cached text cross-attention core (nn/text.py:101-128): softmax(q.K^T / sqrt(Dh)) . V in fp32
-// over the keys l < text_len.  One CTA per (utterance, head) item:
-//   1. the item's K and V rows ([len][Dh] each) are copied to shared memory by all threads with one
-//      wave of cp.async (a single L2 round trip); q is read (LL: polled) by the first Dh/4 threads;
-//   2. scores: 8 lanes per key (64 keys per pass), 3-step shuffle reduction;
-//   3. max / sum: every warp, redundantly, from shared memory;
-//   4. output: thread (d, g) accumulates the keys l = g mod G, G = 512 / Dh groups;
-//   5. fixed-order sum over the groups, normalise, nan_to_num (nn/text.py:128), store.
-// smem (floats): qs[Dh] | sc[LC] | part[16][Dh] | Ks[LC][Dh] | Vs[LC][Dh],  LC = p.att_lc
-// ---------------------------------------------------------------------------
+__device__ __forceinline__ void attention_item(const ArParams& p, const LayerDev& L, int b, int h, const float* __restrict__ qs,
+                                               float* __restrict__ sc, float* __restrict__ part, int grp, int gt, int ll,
+                                               unsigned out_seq) {
+  const int lane = gt & 31;
+  const int Dh = p.Dh, D = p.D, H = p.H;
+  const int len = p.text_len[b];
+  const size_t kv_off = ((((size_t)L.attn_slot * p.B + b) * H + h) * p.Lmax) * Dh;
+  const float* __restrict__ Kp = p.kc + kv_off;
+  const float* __restrict__ Vp = p.vc + kv_off;
+  const float scale = 1.0f / sqrtf((float)Dh);
+  // 1. scores
+  {
+    const int sub = gt & 7;
+    for (int l0 = 0; l0 < len; l0 += kAttGroup / 8) {
+      const int l = l0 + (gt >> 3);
+      float sdot = 0.f;
+      if (l < len) {
+        for (int d = sub * 4; d < Dh; d += 32) {
+          const float4 kk = __ldg(reinterpret_cast<const float4*>(Kp + (size_t)l * Dh + d));
+          const float4 qq = *reinterpret_cast<const float4*>(qs + d);
+          sdot += kk.x * qq.x + kk.y * qq.y + kk.z * qq.z + kk.w * qq.w;
+        }
+      }
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+      sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+      if (sub == 0 && l < len) sc[l] = sdot * scale;
+    }
+  }
+  group_sync(grp);
+  // 2. softmax statistics
+  float mx = -INFINITY;
+  for (int l = lane; l < len; l += 32) mx = fmaxf(mx, sc[l]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int l = lane; l < len; l += 32) sum += expf(sc[l] - mx);
+  sum = warp_sum(sum);
+  // 3. partial outputs
+  const int C4 = Dh >> 2;
+  const int G = min(kAttGroup / C4, kAttG);
+  {
+    const int g = gt / C4, c = gt - g * C4;
+    if (g < G) {
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int l = g; l < len; l += G) {
+        const float e = expf(sc[l] - mx);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(Vp + (size_t)l * Dh + c * 4));
+        o.x += e * v.x;
+        o.y += e * v.y;
+        o.z += e * v.z;
+        o.w += e * v.w;
+      }
+      *reinterpret_cast<float4*>(part + (size_t)g * Dh + c * 4) = o;
+    }
+  }
+  group_sync(grp);
+  // 4. combine
+  if (gt < Dh) {
+    float acc = 0.f;
+    for (int g = 0; g < G; ++g) acc += part[(size_t)g * Dh + gt];
+    acc = acc / sum;
+    if (!isfinite(acc)) acc = 0.f;
+    const size_t aoff = (size_t)b * D + (size_t)h * Dh + gt;
+    if (ll) ll_store(p.abuf + aoff * 2, acc, out_seq);
+    else p.abuf[aoff] = acc;
+  }
+  group_sync(grp);  // sc / part are reused by the group's next item
+}
+
+// smem floats per group of the attention stages
+__host__ __device__ inline int att_group_floats(int Lmax, int Dh) { return ((Lmax + 3) & ~3) + kAttG * Dh; }
+
+// The attention stage of the un-fused program (q comes from the q stage through the exchange buffer): work items
+// (utterance, head) round-robin over the team's CTAs, two items at a time per CTA.
+// smem: [qs[Dh] | sc | part] x 2 groups
 __device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank, int P, int b0, int nb,
                                              float* __restrict__ smem, int ll, unsigned q_seq, unsigned out_seq) {
   const LayerDev& L = p.layer[li];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int H = p.H, Dh = p.Dh, D = p.D, LC = p.att_lc;
-  float* qs = smem;
+  const int tid = threadIdx.x;
+  const int grp = tid / kAttGroup, gt = tid - grp * kAttGroup;
+  const int H = p.H, Dh = p.Dh, D = p.D;
+  const int gf = Dh + att_group_floats(p.Lmax, Dh);
+  float* qs = smem + (size_t)grp * gf;
   float* sc = qs + Dh;
-  float* part = sc + LC;
-  float* Ks = part + 16 * Dh;
-  float* Vs = Ks + (size_t)LC * Dh;
-  const unsigned Ks_s = smem_u32(Ks), Vs_s = smem_u32(Vs);
-  const float scale = 1.0f / sqrtf((float)Dh);
-  const int G = min(kThreads / Dh, 16);
+  float* part = sc + ((p.Lmax + 3) & ~3);
   const int n_items = nb * H;
-  for (int item = rank; item < n_items; item += P) {
+  for (int item = rank + grp * P; item < n_items; item += 2 * P) {
     const int u = item / H, h = item % H;
     const int b = b0 + u;
-    const int len = p.text_len[b];
-    if (len > LC) {
-      attention_item_long(p, li, item, b0, smem, ll, q_seq, out_seq);
-      continue;
-    }
-    const size_t kv_off = ((((size_t)L.attn_slot * p.B + b) * H + h) * p.Lmax) * Dh;
-    const float* Kp = p.kc + kv_off;
-    const float* Vp = p.vc + kv_off;
-    const int n4 = len * Dh / 4;
-    for (int e = tid; e < n4; e += kThreads) {
-      cp_async16(Ks_s + (unsigned)e * 16u, Kp + (size_t)e * 4);
-      cp_async16(Vs_s + (unsigned)e * 16u, Vp + (size_t)e * 4);
-    }
-    cp_async_commit();
-    if (tid * 4 < Dh) {
-      const size_t qoff = (size_t)b * D + (size_t)h * Dh + tid * 4;
+    if (gt * 4 < Dh) {
+      const size_t qoff = (size_t)b * D + (size_t)h * Dh + gt * 4;
       float4 q4;
       if (ll) {
         uint4 a, c;
@@ -744,59 +702,12 @@ __device__ __noinline__ void stage_attention(const ArParams& p, int li, int rank
       } else {
         q4 = ldcg4(p.qbuf + qoff);
       }
-      *reinterpret_cast<float4*>(qs + tid * 4) = q4;
+      *reinterpret_cast<float4*>(qs + gt * 4) = q4;
     }
-    cp_async_wait0();
-    __syncthreads();
-    // 2. scores
-    {
-      const int sub = tid & 7;
-      for (int l0 = 0; l0 < len; l0 += kThreads / 8) {
-        const int l = l0 + (tid >> 3);
-        float sdot = 0.f;
-        if (l < len) {
-          for (int d = sub * 4; d < Dh; d += 32) {
-            const float4 kk = *reinterpret_cast<const float4*>(Ks + (size_t)l * Dh + d);
-            const float4 qq = *reinterpret_cast<const float4*>(qs + d);
-            sdot += kk.x * qq.x + kk.y * qq.y + kk.z * qq.z + kk.w * qq.w;
-          }
-        }
-        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
-        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
-        sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
-        if (sub == 0 && l < len) sc[l] = sdot * scale;
-      }
-    }
-    __syncthreads();
-    // 3. softmax statistics
-    float mx = -INFINITY;
-    for (int l = lane; l < len; l += 32) mx = fmaxf(mx, sc[l]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int l = lane; l < len; l += 32) sum += expf(sc[l] - mx);
-    sum = warp_sum(sum);
-    // 4. partial outputs
-    {
-      const int g = tid / Dh, d = tid - g * Dh;
-      if (g < G) {
-        float o = 0.f;
-        for (int l = g; l < len; l += G) o += expf(sc[l] - mx) * Vs[(size_t)l * Dh + d];
-        part[g * Dh + d] = o;
-      }
-    }
-    __syncthreads();
-    // 5. combine
-    if (tid < Dh) {
-      float acc = 0.f;
-      for (int g = 0; g < G; ++g) acc += part[g * Dh + tid];
-      acc = acc / sum;
-      if (!isfinite(acc)) acc = 0.f;
-      const size_t aoff = (size_t)b * D + (size_t)h * Dh + tid;
-      if (ll) ll_store(p.abuf + aoff * 2, acc, out_seq);
-      else p.abuf[aoff] = acc;
-    }
-    __syncthreads();
+    group_sync(grp);
+    attention_item(p, L, b, h, qs, sc, part, grp, gt, ll, out_seq);
   }
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
@@ -1314,6 +1225,112 @@ __device__ __noinline__ void sample_utterance(const ArParams& p, int b, int t, f
 }
 
 // ---------------------------------------------------------------------------
+// Fused q projection + cached text cross-attention (nn/text.py:93-128) WITHOUT an exchange in between: rank r of a
+// team serves head h = r % H for the utterances u = r / H, r / H + PH, ... (PH = P / H CTAs per head).  It computes
+// q[u][h] = Wq[rows of head h] . RMSNorm_q(x[u]) itself (the head's Dh weight rows arrive through the weight ring)
+// and runs the attention of its (u, h) items right away, two items side by side.  One exchange and one full GEMV
+// stage fewer per attention layer than q-stage -> attention-stage.
+// smem (floats): xs[MU][D] | qh[MU][Dh] | [sc | part] x 2 groups,  MU = ceil(Bt / PH)
+// ---------------------------------------------------------------------------
+template <typename WT, bool LL>
+__device__ __forceinline__ void stage_qatt(const ArParams& p, int li, const TeamCtx& tc, WeightRing& ring, int n_tiles,
+                                           float* __restrict__ smem, const float* __restrict__ xsrc, unsigned x_seq,
+                                           unsigned out_seq, Stamp& ts) {
+  const LayerDev& L = p.layer[li];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = p.H, Dh = p.Dh, D = p.D, PH = p.PH;
+  const int h = tc.rank % H, gi = tc.rank / H;
+  const int n_my = (tc.rank < H * PH && gi < tc.nb) ? (tc.nb - gi + PH - 1) / PH : 0;
+  const int MU = (p.Bt + PH - 1) / PH;
+  float* xs = smem;
+  float* qh = xs + (size_t)MU * D;
+  if (n_my == 0) {  // no item here: only keep the weight ring in step
+    ts.mark();
+    ts.mark();
+#pragma unroll 1
+    for (int ti = n_tiles; ti > 0; --ti) {
+      const TileDesc* td;
+      ring.acquire(td);
+      ring.release();
+    }
+    return;
+  }
+  // ---- x rows of my utterances
+#pragma unroll 1
+  for (int j = 0; j < n_my; ++j) {
+    const int u = gi + j * PH;
+    const float* src = xsrc + (size_t)(tc.b0 + u) * D * (LL ? 2 : 1);
+    if (LL) {
+      ll_fetch(src, D, D, x_seq, xs + (size_t)j * D);
+    } else {
+      for (int e = tid * 4; e < D; e += kThreads * 4) *reinterpret_cast<float4*>(xs + (size_t)j * D + e) = ldcg4(src + e);
+    }
+  }
+  __syncthreads();
+  // RMSNorm_q (nn/blocks.py:32-37), one warp per row
+#pragma unroll 1
+  for (int j = warp; j < n_my; j += kWarps) {
+    float* d = xs + (size_t)j * D;
+    float ss = 0.f;
+    for (int k = lane * 4; k < D; k += 128) {
+      const float4 v = *reinterpret_cast<float4*>(d + k);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.0f / sqrtf(ss / (float)D + 1e-6f);
+    for (int k = lane * 4; k < D; k += 128) {
+      float4 v = *reinterpret_cast<float4*>(d + k);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(L.nq_w + k));
+      v.x = (v.x * inv) * w.x;
+      v.y = (v.y * inv) * w.y;
+      v.z = (v.z * inv) * w.z;
+      v.w = (v.w * inv) * w.w;
+      *reinterpret_cast<float4*>(d + k) = v;
+    }
+  }
+  __syncthreads();
+  ts.mark();  // activations staged
+  // ---- q rows of my head: 8 rows x 2 utterances per warp task
+  const unsigned xs_s = smem_u32(xs);
+  const unsigned row_bytes = (unsigned)D * (unsigned)sizeof(WT);
+  const int n_up = (n_my + 1) / 2;
+#pragma unroll 1
+  for (int ti = n_tiles; ti > 0; --ti) {
+    const TileDesc* td;
+    const unsigned wb = ring.acquire(td);
+    const int nr = td->nrows;
+    const int n_rt = (nr + 7) / 8;
+#pragma unroll 1
+    for (int task = warp; task < n_rt * n_up; task += kWarps) {
+      const int rt = n_up == 1 ? task : task / n_up;
+      const int up = task - rt * n_up;
+      unsigned wr[8];
+#pragma unroll
+      for (int jr = 0; jr < 8; ++jr) wr[jr] = wb + (unsigned)min(rt * 8 + jr, nr - 1) * row_bytes;
+      const int j0 = min(up * 2, max(n_my - 2, 0));
+      const float v = warp_rows_s<8, 2, WT>(wr, xs_s + (unsigned)j0 * (unsigned)D * 4u, D, lane);
+      const int o = (lane >> 1) & 15;  // after the transposed reduction: output o = row i * 2 + utterance uu
+      const int i = o >> 1, uu = o & 1;
+      const int ri = rt * 8 + i, j = j0 + uu;
+      if ((lane & 1) == 0 && ri < nr && j >= up * 2 && j < n_my) qh[(size_t)j * Dh + (td->row0 - h * Dh) + ri] = v;
+    }
+    ring.release();
+  }
+  ts.mark();  // tiles done
+  // ---- the attention of my items, two side by side
+  {
+    const int grp = tid / kAttGroup, gt = tid - grp * kAttGroup;
+    float* sc = qh + (size_t)MU * Dh + (size_t)grp * att_group_floats(p.Lmax, Dh);
+    float* part = sc + ((p.Lmax + 3) & ~3);
+#pragma unroll 1
+    for (int j = grp; j < n_my; j += 2) {
+      const int u = gi + j * PH;
+      attention_item(p, L, tc.b0 + u, h, qh + (size_t)j * Dh, sc, part, grp, gt, LL ? 1 : 0, out_seq);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // the persistent kernel: an interpreter over p.prog with one shared GEMV body
 // ---------------------------------------------------------------------------
 template <typename WT, int TU, bool LL>
@@ -1586,6 +1603,8 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
           nxt = tmp;
         }
         if (kind == K_GLU || kind == K_FFN2 || kind == K_O) x_seq = seq;
+      } else if (kind == K_QATT) {
+        stage_qatt<WT, LL>(p, li, tc, ring, stage_tiles[si], act, cur, x_seq, seq, ts);
       } else if (kind == K_ATT) {
         ts.mark();
         ts.mark();

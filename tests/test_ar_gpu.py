@@ -219,7 +219,9 @@ def _oracle_tokens_worker(args):
 
 def _near_tie_margin(sd, cfg, cond_i, txt_i, samp, tape, want, t):
     """Relative distance to the nearest decision boundary of the oracle's sampler at step `t` (oracle history):
-    the two best ratios p_sorted[j] / q[j] of the draw, and the top-p cut (cum[j] vs top_p)."""
+    the two best ratios p_sorted[j] / q[j] of the draw, the top-p cut (cum[j] vs top_p), and the order of the sorted
+    probabilities around the winning rank (the noise is assigned by RANK, sampling.py:83-84: two candidates whose
+    probabilities differ by an ulp-scale amount swap ranks, and with them their noise, under any fp32 reordering)."""
     logits, rec = [], []
     gen = O.ar_stream(sd, cfg, cond_i, txt_i, torch.ones(1, txt_i.size(1), dtype=torch.bool), max_frames=t, sampling=samp,
                       noise_tv=tape, logits_out=logits, recovery_out=rec)
@@ -233,7 +235,12 @@ def _near_tie_margin(sd, cfg, cond_i, txt_i, samp, tape, want, t):
     r = (sp / tape[t][:50].double()).sort(descending=True).values
     draw = float((r[0] - r[1]) / r[0])
     cut = float((tr["cum"][:50].double() - top_p).abs().min())
-    return min(draw, cut)
+    cum = tr["cum"][:51].double()
+    raw = torch.diff(cum, prepend=torch.zeros(1, dtype=torch.double))  # sorted probabilities before the top-p cut
+    win = int((sp / tape[t][:50].double()).argmax())
+    lo, hi = max(win - 1, 0), min(win + 1, 50)
+    order = float(((raw[lo:hi] - raw[lo + 1:hi + 1]) / raw[lo:hi]).min())
+    return min(draw, cut, order)
 
 
 def test_full_size_batch64_properties():

