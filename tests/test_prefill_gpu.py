@@ -61,9 +61,13 @@ def test_batched_prefill_equals_the_cpu_restatement_per_text():
             worst = max(worst, err)
             assert err <= 2e-5, (i, err)
     print(f"batched prefill vs CPU restatement: max abs err {worst:.2e}")
-    # batch invariance: the same text alone gives the same rows bit for bit
-    t1, l1, p1, c1 = eng.run([texts[2]], ref, n_frames=F + 1, style_strength=1.2)
-    assert torch.equal(c1[0], cond[2]) and torch.equal(t1[0, :7], txt[2, :7])
+    # batch invariance.  Stages with more than 16 rows run the 128x128 tile kernel, whose per-output summation order does
+    # not depend on the row count: a 52-token text alone (M = 52) equals its rows in the batch (M = 6 x 300) bit for bit.
+    t0, _, p0, c0 = eng.run([texts[0]], ref, n_frames=F + 1, style_strength=1.2)
+    assert torch.equal(c0[0], cond[0]) and torch.equal(t0[0, :52], txt[0, :52]) and torch.equal(p0[0], pool[0])
+    # A 7-token text alone (M <= 16) takes the skinny kernel (lanes split K: another summation order): equal to rounding
+    t1, _, p1, c1 = eng.run([texts[2]], ref, n_frames=F + 1, style_strength=1.2)
+    assert float((c1[0] - cond[2]).abs().max()) <= 2e-5 and float((t1[0, :7] - txt[2, :7]).abs().max()) <= 2e-5
 
 
 def test_public_prepare_conditioning_feeds_the_ar_kernel():

@@ -60,3 +60,30 @@ with torch.inference_mode():
     print(f"mimi decode T=401 B=64 {t:8.3f} ms")
     t, _ = timed(lambda: next(iter(tts.stream(text, ref=ref, max_frames=400, seed=1, min_gen_frames=10 ** 9))), n=10)
     print(f"stream first chunk     {t:8.3f} ms")
+    # steady-state streaming chunk: NAR over ctx + chunk frames, Mimi stream step of one chunk
+    ctx = tts.model.rf_nar()
+    n = ctx + 6
+    toksw = torch.randint(0, 2048, (1, n), device=dev)
+    t, winw = timed(lambda: tts.model.nar_refine(prep["cond_ar"][:, :n], toksw), n=5)
+    print(f"nar_refine T={n} B=1   {t:8.3f} ms")
+    from sopro_b200.codec import MimiStreamDecoder
+    msd = MimiStreamDecoder(tts.codec, max_chunk_frames=16)
+    st = msd.new_state()
+    ts = []
+    for i in range(40):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        wv, st = msd.decode_step(winw.squeeze(0)[i * 4 % 100:i * 4 % 100 + 6], st)
+        torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+    print(f"mimi stream step 6 fr  {np.median(ts[5:]) * 1e3:8.3f} ms")
+    msd.release(st)
+    t, _ = timed(lambda: sum(1 for _ in tts.stream(text, ref=ref, max_frames=400, seed=1, min_gen_frames=10 ** 9)), n=3, warm=1)
+    print(f"stream 400 frames      {t:8.3f} ms")
+    # synthesize_batch(64) phases
+    texts = [" ".join(str((17 * i + 5 + 31 * j) % 1000) for i in range(50)) for j in range(64)]
+    ids64 = [tts.encode_text(x) for x in texts]
+    t, preps = timed(lambda: tts.model.prepare_conditioning_batch(ids64, ref, max_frames=400, style_strength=cfg.style_strength), n=3, warm=1)
+    print(f"prefill batch 64       {t:8.3f} ms")
+    t, tapes = timed(lambda: tts.model._draw_tapes(64, 401, 50, list(range(64))), n=3, warm=1)
+    print(f"draw 64 noise tapes    {t:8.3f} ms")
+    t, _ = timed(lambda: tts.synthesize_batch(texts, ref=ref, max_frames=400, seeds=list(range(64)), min_gen_frames=10 ** 9), n=3, warm=1)
+    print(f"synthesize_batch(64)   {t:8.3f} ms")
