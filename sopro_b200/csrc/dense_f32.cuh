@@ -63,17 +63,24 @@ __device__ __forceinline__ int w_row(const DenseOp& op, int n0, int j, int BN) {
 
 constexpr int kBM = 128, kBN = 128, kBK = 16, kTileThreads = 256;
 
+// BM x BN x 16 tiles, 256 threads as a 16 x 16 grid, (BM/16) x (BN/16) outputs per thread.  Three sizes
+// (128x128 / 64x64 / 32x32): the host picks the largest one that still gives every SM a CTA.  Every output is ONE
+// fma chain over k = 0 .. K-1 whatever the tile size, so the choice never changes a bit of the result.
+template <int BM, int BN>
 __global__ void __launch_bounds__(kTileThreads, 2) dense_tile_kernel(const DenseOp op_in) {
+  constexpr int TM = BM / 16, TN = BN / 16, TP = TN / 2;  // thread tile; accumulators paired over columns
+  static_assert((TM == 8 || TM == 4 || TM == 2) && (TN == 8 || TN == 4 || TN == 2), "tile sizes 128 / 64 / 32");
+  constexpr int HA = BM >= 64 ? BM / 64 : 1, HB = BN >= 64 ? BN / 64 : 1;  // loader passes over the rows / columns
   const DenseOp op = group_of(op_in);
-  __shared__ __align__(16) float As[2][kBK][kBM + 4];
-  __shared__ __align__(16) float Bs[2][kBK][kBN + 4];
-  __shared__ float inv_rms[kBM];
+  __shared__ __align__(16) float As[2][kBK][BM + 4];
+  __shared__ __align__(16) float Bs[2][kBK][BN + 4];
+  __shared__ float inv_rms[BM];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int K = op.K;
-  // ---- prologue: 1/rms of this tile's rows (one warp per row, 16 rows each)
+  // ---- prologue: 1/rms of this tile's rows (one warp per row)
   if (op.norm_w) {
-    for (int r = warp; r < kBM; r += kTileThreads / 32) {
+    for (int r = warp; r < BM; r += kTileThreads / 32) {
       const int m = m0 + r;
       float ss = 0.f;
       if (m < op.M) {
@@ -89,20 +96,21 @@ __global__ void __launch_bounds__(kTileThreads, 2) dense_tile_kernel(const Dense
     }
     __syncthreads();
   }
-  // loader mapping: row = tid / 4 (+64), 4 consecutive k at (tid % 4) * 4
+  // loader mapping: row = tid / 4 (+64 per pass), 4 consecutive k at (tid % 4) * 4
   const int lrow = tid >> 2, lk = (tid & 3) * 4;
-  int wrow[2];
+  const bool la = lrow < BM, lb = lrow < BN;  // 32-wide tiles: only the first 128 threads load
+  int wrow[HB];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
+  for (int h = 0; h < HB; ++h) {
     const int j = lrow + 64 * h;
-    const int r = w_row(op, n0, j, kBN);
-    const bool ok = op.epi == EPI_GLU ? (n0 / kBN) * (kBN / 2) + (j % (kBN / 2)) < op.N / 2 : r < op.N;
+    const int r = w_row(op, n0, j, BN);
+    const bool ok = lb && (op.epi == EPI_GLU ? (n0 / BN) * (BN / 2) + (j % (BN / 2)) < op.N / 2 : r < op.N);
     wrow[h] = ok ? r : -1;
   }
   auto load_a = [&](int k0, int h) -> float4 {
     const int m = m0 + lrow + 64 * h;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (m < op.M) {
+    if (la && m < op.M) {
       v = *reinterpret_cast<const float4*>(op.A + (size_t)m * K + k0 + lk);
       if (op.norm_w) {
         const float inv = inv_rms[lrow + 64 * h];
@@ -125,71 +133,101 @@ __global__ void __launch_bounds__(kTileThreads, 2) dense_tile_kernel(const Dense
   auto load_b = [&](int k0, int h) -> float4 {
     return wrow[h] >= 0 ? __ldg(reinterpret_cast<const float4*>(op.W + (size_t)wrow[h] * K + k0 + lk)) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  auto store = [&](int buf, const float4 (&a)[2], const float4 (&b)[2]) {
+  auto store = [&](int buf, const float4 (&a)[HA], const float4 (&b)[HB]) {
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < HA; ++h) {
       const int r = lrow + 64 * h;
-      As[buf][lk + 0][r] = a[h].x;
-      As[buf][lk + 1][r] = a[h].y;
-      As[buf][lk + 2][r] = a[h].z;
-      As[buf][lk + 3][r] = a[h].w;
-      Bs[buf][lk + 0][r] = b[h].x;
-      Bs[buf][lk + 1][r] = b[h].y;
-      Bs[buf][lk + 2][r] = b[h].z;
-      Bs[buf][lk + 3][r] = b[h].w;
+      if (la) {
+        As[buf][lk + 0][r] = a[h].x;
+        As[buf][lk + 1][r] = a[h].y;
+        As[buf][lk + 2][r] = a[h].z;
+        As[buf][lk + 3][r] = a[h].w;
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < HB; ++h) {
+      const int r = lrow + 64 * h;
+      if (lb) {
+        Bs[buf][lk + 0][r] = b[h].x;
+        Bs[buf][lk + 1][r] = b[h].y;
+        Bs[buf][lk + 2][r] = b[h].z;
+        Bs[buf][lk + 3][r] = b[h].w;
+      }
     }
   };
-  // thread tile: rows {ty*4..+3, 64+ty*4..+3}, columns {tx*4..+3, 64+tx*4..+3}; accumulators paired over columns
+  // thread tile rows.  128: {ty*4..+3, 64+ty*4..+3}; 64: ty*4..+3; 32: ty*2, ty*2+1.  Columns.  128: {tx*4..+3, 64+tx*4..+3};
+  // 64: {tx*2, tx*2+1, 32+tx*2, 32+tx*2+1} (a GLU thread holds a channel's value AND gate column); 32: tx*2, tx*2+1 (no GLU)
   const int ty = tid >> 4, tx = tid & 15;
-  float2 acc[8][4];
+  auto row_of = [&](int i) { return TM == 8 ? (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4)) : ty * TM + i; };
+  auto col_of = [&](int j) {  // first column of accumulator pair j
+    return TN == 8 ? (j < 2 ? tx * 4 + 2 * j : 64 + tx * 4 + 2 * (j - 2)) : TN == 4 ? (j == 0 ? tx * 2 : 32 + tx * 2) : tx * 2;
+  };
+  float2 acc[TM][TP];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
-  float4 ra[2], rb[2];
-  ra[0] = load_a(0, 0);
-  ra[1] = load_a(0, 1);
-  rb[0] = load_b(0, 0);
-  rb[1] = load_b(0, 1);
+    for (int j = 0; j < TP; ++j) acc[i][j] = make_float2(0.f, 0.f);
+  float4 ra[HA], rb[HB];
+#pragma unroll
+  for (int h = 0; h < HA; ++h) ra[h] = load_a(0, h);
+#pragma unroll
+  for (int h = 0; h < HB; ++h) rb[h] = load_b(0, h);
   store(0, ra, rb);
   __syncthreads();
   const int nk = K / kBK;
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nk) {
-      ra[0] = load_a((kt + 1) * kBK, 0);
-      ra[1] = load_a((kt + 1) * kBK, 1);
-      rb[0] = load_b((kt + 1) * kBK, 0);
-      rb[1] = load_b((kt + 1) * kBK, 1);
+#pragma unroll
+      for (int h = 0; h < HA; ++h) ra[h] = load_a((kt + 1) * kBK, h);
+#pragma unroll
+      for (int h = 0; h < HB; ++h) rb[h] = load_b((kt + 1) * kBK, h);
     }
 #pragma unroll
     for (int k = 0; k < kBK; ++k) {
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
-      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float2 b[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+      float a[TM];
+      float2 b[TP];
+      if constexpr (TM == 8) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+        a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a0.w, a[4] = a1.x, a[5] = a1.y, a[6] = a1.z, a[7] = a1.w;
+      } else if constexpr (TM == 4) {
+        const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+        a[0] = a0.x, a[1] = a0.y, a[2] = a0.z, a[3] = a0.w;
+      } else {
+        const float2 a0 = *reinterpret_cast<const float2*>(&As[buf][k][ty * 2]);
+        a[0] = a0.x, a[1] = a0.y;
+      }
+      if constexpr (TN == 8) {
+        const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+        b[0] = make_float2(b0.x, b0.y), b[1] = make_float2(b0.z, b0.w), b[2] = make_float2(b1.x, b1.y), b[3] = make_float2(b1.z, b1.w);
+      } else if constexpr (TN == 4) {
+        b[0] = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 2]);
+        b[1] = *reinterpret_cast<const float2*>(&Bs[buf][k][32 + tx * 2]);
+      } else {
+        b[0] = *reinterpret_cast<const float2*>(&Bs[buf][k][tx * 2]);
+      }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < TM; ++i) {
         const float2 aa = make_float2(a[i], a[i]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(aa, b[j], acc[i][j]);
+        for (int j = 0; j < TP; ++j) acc[i][j] = __ffma2_rn(aa, b[j], acc[i][j]);
       }
     }
     if (kt + 1 < nk) store(buf ^ 1, ra, rb);
     __syncthreads();
   }
   // ---- epilogue
-  const int half = kBN / 2;
+  constexpr int half = BN / 2;
   if (op.epi == EPI_ARGMAX) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
+    for (int i = 0; i < TM; ++i) {
       float bv = -INFINITY;
       int bi = 0x7fffffff;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = n0 + (j < 2 ? tx * 4 + 2 * j : 64 + tx * 4 + 2 * (j - 2));
+      for (int j = 0; j < TP; ++j) {
+        const int c = n0 + col_of(j);
         const float v0 = acc[i][j].x + (op.bias && c < op.N ? __ldg(op.bias + c) : 0.f);
         const float v1 = acc[i][j].y + (op.bias && c + 1 < op.N ? __ldg(op.bias + c + 1) : 0.f);
         if (c < op.N && before(v0, c, bv, bi)) bv = v0, bi = c;
@@ -201,7 +239,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) dense_tile_kernel(const Dense
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (before(ov, oi, bv, bi)) bv = ov, bi = oi;
       }
-      const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      const int m = m0 + row_of(i);
       if (tx == 0 && m < op.M) {
         op.amax_val[(size_t)m * op.parts + blockIdx.y] = bv;
         op.amax_idx[(size_t)m * op.parts + blockIdx.y] = bi;
@@ -210,46 +248,39 @@ __global__ void __launch_bounds__(kTileThreads, 2) dense_tile_kernel(const Dense
     return;
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+  for (int i = 0; i < TM; ++i) {
+    const int m = m0 + row_of(i);
     if (m >= op.M) continue;
     if (op.epi == EPI_GLU) {
-      // columns [0, 64) of the tile are value rows, [64, 128) the gate rows of the same channels
-      const int cbase = (n0 / kBN) * half + tx * 4;
+      // columns [0, BN/2) of the tile are value rows, [BN/2, BN) the gate rows of the same channels: the value pairs
+      // j < TP/2 of a thread meet their gate pairs j + TP/2 (TN == 2: value and gate live in different threads -> not used)
       const int D = op.N / 2;
-      float o[4];
+      if constexpr (TP >= 2) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int c = cbase + 2 * j;
-        const float v0 = acc[i][j].x + (c < D ? __ldg(op.bias + c) : 0.f), g0 = acc[i][j + 2].x + (c < D ? __ldg(op.bias + D + c) : 0.f);
-        const float v1 = acc[i][j].y + (c + 1 < D ? __ldg(op.bias + c + 1) : 0.f), g1 = acc[i][j + 2].y + (c + 1 < D ? __ldg(op.bias + D + c + 1) : 0.f);
-        o[2 * j] = v0 * sigmoid_ref(g0);
-        o[2 * j + 1] = v1 * sigmoid_ref(g1);
+        for (int j = 0; j < TP / 2; ++j) {
+          const int c = (n0 / BN) * half + (TN == 8 ? tx * 4 + 2 * j : tx * 2);
+          const float v0 = acc[i][j].x + (c < D ? __ldg(op.bias + c) : 0.f), g0 = acc[i][j + TP / 2].x + (c < D ? __ldg(op.bias + D + c) : 0.f);
+          const float v1 = acc[i][j].y + (c + 1 < D ? __ldg(op.bias + c + 1) : 0.f), g1 = acc[i][j + TP / 2].y + (c + 1 < D ? __ldg(op.bias + D + c + 1) : 0.f);
+          if (c < D) op.C[(size_t)m * op.ldc + c] = v0 * sigmoid_ref(g0);
+          if (c + 1 < D) op.C[(size_t)m * op.ldc + c + 1] = v1 * sigmoid_ref(g1);
+        }
       }
-      if (cbase + 3 < D) *reinterpret_cast<float4*>(op.C + (size_t)m * op.ldc + cbase) = make_float4(o[0], o[1], o[2], o[3]);
-      else
-        for (int e = 0; e < 4; ++e)
-          if (cbase + e < D) op.C[(size_t)m * op.ldc + cbase + e] = o[e];
       continue;
     }
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      const int c = n0 + g * 64 + tx * 4;
-      float v[4] = {acc[i][2 * g].x, acc[i][2 * g].y, acc[i][2 * g + 1].x, acc[i][2 * g + 1].y};
+    for (int j = 0; j < TP; ++j) {
+      const int c = n0 + col_of(j);
+      float v[2] = {acc[i][j].x, acc[i][j].y};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < 2; ++e) {
         if (c + e >= op.N) continue;
         float x = v[e];
         if (op.bias) x += __ldg(op.bias + c + e);
         if (op.epi == EPI_GELU) x = gelu_erf(x);
         else if (op.epi == EPI_RES) x = op.R[(size_t)m * op.ldc + c + e] + x;
         else if (op.epi == EPI_RES_GATE) x = op.R[(size_t)m * op.ldc + c + e] + op.gate * x;
-        v[e] = x;
+        op.C[(size_t)m * op.ldc + c + e] = x;
       }
-      if (c + 3 < op.N && (op.ldc & 3) == 0) *reinterpret_cast<float4*>(op.C + (size_t)m * op.ldc + c) = make_float4(v[0], v[1], v[2], v[3]);
-      else
-        for (int e = 0; e < 4; ++e)
-          if (c + e < op.N) op.C[(size_t)m * op.ldc + c + e] = v[e];
     }
   }
 }

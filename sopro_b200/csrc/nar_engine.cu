@@ -69,7 +69,20 @@ bool block_ok(const sopro_ssm_block_weights_t& L) {
   return L.norm_w && L.glu_w && L.glu_b && L.dw_w && L.dw_b && L.ffn_norm_w && L.ffn_w1 && L.ffn_b1 && L.ffn_w2 && L.ffn_b2;
 }
 
-// C = epi(prologue(A) . W^T): picks the skinny kernel for M <= 16 rows, the 128x128 tile kernel otherwise.
+// Tile edge of the tile kernel for an [M x N] output in `groups` groups: the largest of 128 / 64 / 32 that still gives
+// (about) every SM a CTA -- a streaming window of ~190 rows would otherwise run on a handful of SMs.  The result does
+// not depend on the choice (one fma chain over k per output, dense_f32.cuh).  GLU pairs value / gate columns inside a
+// thread, which the 32-wide tile cannot: 64 is its smallest.
+int tile_edge(int M, int N, int groups, int epi) {
+  const int target = 120;
+  for (int e : {128, 64}) {
+    const long long ctas = (long long)((M + e - 1) / e) * ((N + e - 1) / e) * groups;
+    if (ctas >= target) return e;
+  }
+  return epi == dense::EPI_GLU ? 64 : 32;
+}
+
+// C = epi(prologue(A) . W^T): picks the skinny kernel for M <= 16 rows, a tile kernel otherwise.
 // groups > 1 (argmax heads): blockIdx.z = group.
 int launch_dense(dense::DenseOp op, int groups, cudaStream_t st) {
   if (op.K % 16 || op.M < 1 || op.N < 1) return fail(SOPRO_ERR_INVALID, "dense: bad shape M=%d N=%d K=%d", op.M, op.N, op.K);
@@ -89,9 +102,12 @@ int launch_dense(dense::DenseOp op, int groups, cudaStream_t st) {
     if (smem > (size_t)16 * 2048 * 4) return fail(SOPRO_ERR_INVALID, "dense: K=%d too large for the skinny kernel", op.K);
     dense::dense_skinny_kernel<<<dim3(parts, 1, groups), dense::kSkinnyThreads, smem, st>>>(op, cols);
   } else {
-    const int gy = (op.N + dense::kBN - 1) / dense::kBN;
-    if (op.epi == dense::EPI_ARGMAX) op.parts = gy;
-    dense::dense_tile_kernel<<<dim3((op.M + dense::kBM - 1) / dense::kBM, gy, groups), dense::kTileThreads, 0, st>>>(op);
+    const int e = tile_edge(op.M, op.N, groups, op.epi);
+    const dim3 grid((op.M + e - 1) / e, (op.N + e - 1) / e, groups);
+    if (op.epi == dense::EPI_ARGMAX) op.parts = (int)grid.y;
+    if (e == 128) dense::dense_tile_kernel<128, 128><<<grid, dense::kTileThreads, 0, st>>>(op);
+    else if (e == 64) dense::dense_tile_kernel<64, 64><<<grid, dense::kTileThreads, 0, st>>>(op);
+    else dense::dense_tile_kernel<32, 32><<<grid, dense::kTileThreads, 0, st>>>(op);
   }
   PCK(cudaGetLastError());
   return SOPRO_OK;
@@ -104,7 +120,8 @@ int argmax_parts(int M, int N, int groups) {
     cols = (cols + 7) / 8 * 8;
     return (N + cols - 1) / cols;
   }
-  return (N + dense::kBN - 1) / dense::kBN;
+  const int e = tile_edge(M, N, groups, dense::EPI_ARGMAX);
+  return (N + e - 1) / e;
 }
 
 // one SSMLiteBlock (nn/blocks.py:143-148) over rows [B][Tmax][D], in place on x; h [M][D] and hid [M][4D] are scratch

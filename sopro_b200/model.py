@@ -63,6 +63,19 @@ def _complete_state_dict(cfg: SoproTTSConfig, sd: Dict[str, torch.Tensor]) -> Di
     return out
 
 
+_TAPE_POOL = None
+
+
+def _tape_pool():
+    """Host threads that draw noise tapes (the Exp(1) draws release the GIL)."""
+    global _TAPE_POOL
+    if _TAPE_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _TAPE_POOL = ThreadPoolExecutor(max_workers=max(1, len(os.sched_getaffinity(0))))
+    return _TAPE_POOL
+
+
 class _Noise:
     """The Exp(1) draws `steps` successive torch.multinomial calls would consume (see sopro_b200/sampling.py),
     produced block by block as the kernel launches need them (a [n, V] draw equals n successive [V] draws), with
@@ -323,11 +336,42 @@ class SoproModel:
         B, steps = int(cond.shape[0]), int(max_frames) + 1
         samp = self._sampling(top_p, temperature, anti_loop, 8, 0.85, 1.2, min_gen_frames, stop_on_first_eos)
         nk = self._noise_cols(samp)
-        tapes = self._draw_tapes(B, steps, nk, seeds)  # host threads; the prefill kernels queued before run meanwhile
         ses = self._checkout(B, steps, max(int(x) for x in lens))
         try:
-            ses.begin(cond[:, :steps], txt, [int(x) for x in lens], tapes.to(self.device, non_blocking=True), samp)
-            ses.run()
+            if seeds is None or steps < 64:
+                tapes = self._draw_tapes(B, steps, nk, seeds)  # host threads; the prefill kernels queued before run meanwhile
+                ses.begin(cond[:, :steps], txt, [int(x) for x in lens], tapes.to(self.device, non_blocking=True), samp)
+                ses.run()
+            else:
+                # Private generators: the tape is drawn in growing blocks of steps and the persistent kernel is launched
+                # block by block (it resumes from its device state), so the host draws block k+1 while the device
+                # generates block k; only the first, short block is exposed (and that one overlaps the prefill).
+                V = self.cfg.ar_vocab()
+                gens = [_Noise(steps, V, int(seeds[i]), None) for i in range(B)]
+                host = torch.empty((B, steps, nk), dtype=torch.float32, pin_memory=torch.cuda.is_available())
+                view = host.numpy()
+                dev = torch.empty((B, steps, nk), dtype=torch.float32, device=self.device)
+                pool = _tape_pool()
+
+                def draw(a: int, b: int) -> None:
+                    def one(i):
+                        view[i, a:b] = gens[i].rows(b)[:, :nk].numpy()
+                    list(pool.map(one, range(B)))
+                    dev[:, a:b].copy_(host[:, a:b], non_blocking=True)
+
+                edges, a, step = [], 0, 40
+                while a < steps:
+                    b = min(steps, a + step)
+                    if steps - b < 24:
+                        b = steps
+                    edges.append((a, b))
+                    a, step = b, step * 2
+                draw(*edges[0])
+                ses.begin(cond[:, :steps], txt, [int(x) for x in lens], dev, samp)
+                ses.run(edges[0][1])
+                for a, b in edges[1:]:
+                    draw(a, b)
+                    ses.run(b - a)
             toks, n, _ = ses.read()
         finally:
             self._release(ses)
