@@ -121,6 +121,13 @@ int sopro_ar_session_destroy(sopro_ar_session_t* s);
 /* Launch geometry override (0 = automatic): utterances per CTA team. */
 int sopro_ar_session_set_team(sopro_ar_session_t* s, int utts_per_team);
 
+/* Arithmetic unit of the step's contractions: 0 or -1 = packed fp32 FMA (FFMA2) tiles -- the default and the faster one at
+ * the 22..86 weight rows a CTA owns per stage; 1 = tensor cores (tcgen05, every fp32 activation split into three exact bf16
+ * terms against bf16 weights, fp32 accumulation) or fail when the launch cannot use them (needs bf16 weight storage,
+ * d_model % 64 == 0, teams of 5..8 utterances).  -1 also honours the environment variable SOPRO_AR_TC=1.  Both produce the
+ * reference's token ids (tests/test_ar_gpu.py). */
+int sopro_ar_session_set_contraction(sopro_ar_session_t* s, int mode);
+
 /* Start `batch` utterances.  Zeroes the rings, builds the text K/V caches on the
  * device (TextXAttnBlock.build_kv_cache, nn/text.py:75-83), resets history.
  *   cond_ar   [batch, steps, D] f32   prep["cond_ar"] rows 0..steps-1 (model.py:272)

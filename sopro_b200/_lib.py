@@ -124,6 +124,7 @@ SYMBOLS = {
     "sopro_ar_session_create": (_I, [_VP, _I, _I, _I, C.POINTER(_VP)]),
     "sopro_ar_session_destroy": (_I, [_VP]),
     "sopro_ar_session_set_team": (_I, [_VP, _I]),
+    "sopro_ar_session_set_contraction": (_I, [_VP, _I]),
     "sopro_ar_begin": (_I, [_VP, _I, _I, _VP, _VP, _I, _I32P, _VP, _I, C.POINTER(ArSampling), _VP]),
     "sopro_ar_run": (_I, [_VP, _I, _VP]),
     "sopro_ar_outputs": (_I, [_VP, C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),

@@ -40,7 +40,7 @@ constexpr int kMaxVocab = 8 * kThreads;
 constexpr int kTapSlots = 16;     // dwconv tap rows staged per warp in the GLU stage (channels per task x utterances)
 constexpr int kTimingSlots = 224;  // [0,160) stage stamps, [160,192) sampler phases, [192,224) attention phases
 constexpr int kMaxStages = 6 * kMaxLayers + 2;
-constexpr int kMaxTilesPerStep = 256;
+constexpr int kMaxTilesPerStep = 128;
 constexpr int kMaxWBuf = 8;
 
 enum StageKind { K_GLU = 0, K_FFN1 = 1, K_FFN2 = 2, K_Q = 3, K_O = 4, K_HEAD = 5, K_ATT = 6, K_SAMPLE = 7, K_QATT = 8 };
@@ -93,7 +93,9 @@ struct TileDesc {
   int off2;                 // float index of the tile's first row inside part 2
   int row0;                 // first output feature of the tile
   int nrows;
-  int pad;
+  int ngrp;                 // tensor-core tiles: 8-row groups in part 0 (0 = row-major tile of the FFMA2 path)
+  int kc0;                  // tensor-core tiles: first 64-wide K chunk of the B operand this tile contracts with
+  int flags;                // tensor-core tiles: bit 0 = first K slice of its rows (accumulator reset), bit 1 = last (epilogue)
 };
 
 struct StageOp {
@@ -139,6 +141,11 @@ struct ArParams {
   const int* n_tiles;     // [P] tiles per step of each rank
   const unsigned char* stage_tiles;  // [P][kMaxStages] tiles of each stage
   int nbuf, wbuf_bytes, act_bytes;
+  // dynamic shared-memory map (bytes from the 1024-byte aligned base): FFMA2 path [act | ring | table]; tensor-core
+  // path [ring | B operand + staging | table]
+  int act_off, ring_off, table_off;
+  int tc;   // 1: the GEMV stages contract on tcgen05 (bf16 weights, teams of <= 8 utterances)
+  int ksc;  // tensor-core path: 64-wide K chunks per K slice (= D / 64); a [.. x F] matrix is F / D slices
   long long* timing;  // debug: [grid][kTimingSlots] clock64 stamps of step `timing_step` (null = off)
   int timing_step;
   int g, P, Bt;
@@ -323,6 +330,178 @@ __device__ __forceinline__ float4 ldsw4<__nv_bfloat16>(unsigned a) {
   r.z = __uint_as_float(y << 16);
   r.w = __uint_as_float(y & 0xffff0000u);
   return r;
+}
+
+// ---------------------------------------------------------------------------
+// tcgen05 contraction of the batched launches (bf16 weight storage, teams of <= 8 utterances).
+//   D[64 rows x 32] (+)= A[64 x 16] . B[32 x 16]^T per instruction, fp32 accumulation in tensor memory.
+//   A = this CTA's weight rows: the host stores them as the shared-memory IMAGE the tensor core reads (K-major,
+//       128-byte swizzle, 8-row groups of [K chunks][8 x 128 B]; group stride = SBO), so the 1-D TMA bulk copy of the
+//       weight ring delivers a ready operand.  A tile has <= 8 groups; the instruction always reads 64 rows, the rows
+//       past the tile are whatever follows in shared memory and only reach accumulator lanes nobody reads.
+//       (M = 64: accumulator row m lives in tensor-memory lane 32 * (m / 16) + m % 16, cute's "half subpartitions" atom.)
+//   B = the team's activations, each fp32 value split into THREE bf16 terms x = hi + mid + lo (exact: 3 x 8 mantissa
+//       bits): B row 4u + s holds term s of utterance u (row 4u + 3 is zero).  bf16 x bf16 products are exact in fp32,
+//       so D column 4u+0..2 summed = sum_k w[k] * x[k] with fp32 accumulation -- the same arithmetic as the FFMA2 path
+//       up to the order of the fp32 additions.
+// ---------------------------------------------------------------------------
+constexpr int kTcCols = 32;            // tensor-memory columns (= B rows)
+constexpr int kTcBChunk = 32 * 128;    // bytes of one 64-wide K chunk of the B operand
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc,
+                                            unsigned accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 8 consecutive fp32 columns -> 8 registers of this thread's lane
+__device__ __forceinline__ void tc_ld8(unsigned taddr, unsigned (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups `sbo` bytes apart (bit layout:
+// cute/arch/mma_sm100_desc.hpp; the same constructor the Mimi kernels use, mimi_tc.cuh)
+__device__ __forceinline__ unsigned long long tc_desc(unsigned addr, unsigned sbo) {
+  return (unsigned long long)((addr & 0x3FFFFu) >> 4) | ((unsigned long long)(sbo >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor kind::f16: D fp32, A / B bf16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr unsigned tc_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ void sts128(unsigned a, unsigned x, unsigned y, unsigned z, unsigned w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+// 8 consecutive k of utterance u (K-chunk `chunk`, 16-byte unit `unit`) -> the three bf16 terms, stored swizzled
+__device__ __forceinline__ void tc_store_split8(unsigned bt, int u, int chunk, int unit, const float (&x)[8]) {
+  unsigned hi[4], mi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float a = x[2 * e], b = x[2 * e + 1];
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float ra = a - __low2float(h), rb = b - __high2float(h);
+    const __nv_bfloat162 m = __floats2bfloat162_rn(ra, rb);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(ra - __low2float(m), rb - __high2float(m));
+    hi[e] = *reinterpret_cast<const unsigned*>(&h);
+    mi[e] = *reinterpret_cast<const unsigned*>(&m);
+    lo[e] = *reinterpret_cast<const unsigned*>(&l);
+  }
+  // B row n = 4u + s: 8-row group n >> 3, row r = n & 7 of the group; 16-byte unit index XOR r (128-byte swizzle)
+  const int n0 = 4 * u, r0 = n0 & 7;
+  const unsigned base = bt + (unsigned)chunk * (unsigned)kTcBChunk + (unsigned)(n0 >> 3) * 1024u;
+  sts128(base + (unsigned)(r0 + 0) * 128u + (unsigned)((unit ^ (r0 + 0)) << 4), hi[0], hi[1], hi[2], hi[3]);
+  sts128(base + (unsigned)(r0 + 1) * 128u + (unsigned)((unit ^ (r0 + 1)) << 4), mi[0], mi[1], mi[2], mi[3]);
+  sts128(base + (unsigned)(r0 + 2) * 128u + (unsigned)((unit ^ (r0 + 2)) << 4), lo[0], lo[1], lo[2], lo[3]);
+  sts128(base + (unsigned)(r0 + 3) * 128u + (unsigned)((unit ^ (r0 + 3)) << 4), 0u, 0u, 0u, 0u);
+}
+// B operand from fp32 rows in shared memory ([nb][K], already normalised)
+__device__ __forceinline__ void tc_btile_from_rows(const float* __restrict__ rows, int nb, int K, unsigned bt) {
+  const int upr = K >> 3;  // 16-byte units per row
+  for (int idx = threadIdx.x; idx < nb * upr; idx += kThreads) {
+    const int u = idx / upr, j8 = idx - u * upr;
+    const float4 a = *reinterpret_cast<const float4*>(rows + (size_t)u * K + j8 * 8);
+    const float4 b = *reinterpret_cast<const float4*>(rows + (size_t)u * K + j8 * 8 + 4);
+    const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    tc_store_split8(bt, u, j8 >> 3, j8 & 7, x);
+  }
+}
+// One 4-byte word (k, k+1 of one split term) of B row n: chunk k / 64, 16-byte unit (k % 64) / 8 XOR (n & 7)
+__device__ __forceinline__ unsigned tc_b_word_addr(unsigned bt, int n, int k) {
+  const int r = n & 7;
+  return bt + (unsigned)(k >> 6) * (unsigned)kTcBChunk + (unsigned)(n >> 3) * 1024u + (unsigned)r * 128u +
+         (unsigned)(((((k & 63) >> 3) ^ r) << 4) + ((k & 7) << 1));
+}
+__device__ __forceinline__ void sts32(unsigned a, unsigned v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// two consecutive elements (k even) of utterance u -> the three bf16 terms + the zero row: four conflict-free 4-byte stores
+// (a warp's 64 consecutive k fill one 128-byte row of the operand per term)
+__device__ __forceinline__ void tc_store_split2(unsigned bt, int u, int k, float a, float b) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const float ra = a - __low2float(h), rb = b - __high2float(h);
+  const __nv_bfloat162 m = __floats2bfloat162_rn(ra, rb);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra - __low2float(m), rb - __high2float(m));
+  sts32(tc_b_word_addr(bt, 4 * u + 0, k), *reinterpret_cast<const unsigned*>(&h));
+  sts32(tc_b_word_addr(bt, 4 * u + 1, k), *reinterpret_cast<const unsigned*>(&m));
+  sts32(tc_b_word_addr(bt, 4 * u + 2, k), *reinterpret_cast<const unsigned*>(&l));
+  sts32(tc_b_word_addr(bt, 4 * u + 3, k), 0u);
+}
+// Stage-in of the tensor-core path in ONE pass over the exchange buffer: every thread polls (LL) / loads its element pairs
+// with coalesced 16-byte requests, all in flight; with a norm weight the rows' sums of squares meet through a
+// [row][K / 64] table of warp partials (summed in a fixed order) and one block barrier; then each thread normalises,
+// splits and stores its own pairs into the B operand.  No fp32 staging copy of the activations.
+//   raw_copy: un-normalised rows as plain floats (the GLU stage's residual operand), or null
+//   part:     shared [kMaxUttPerTeam * 32] floats
+template <bool LL, int NJ>
+__device__ __forceinline__ void tc_stage_in(const float* __restrict__ src, int nb, int K, int e_begin, int total, unsigned seq,
+                                            const float* __restrict__ norm_w, float* __restrict__ raw_copy, float* __restrict__ part,
+                                            unsigned bt) {
+  // elements [e_begin, total) of the [nb][K] block, NJ pairs per thread (e_begin = 0 whenever norm_w / raw_copy is set)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float2 x[NJ];
+  if (LL) {
+    uint4 v[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int e = e_begin + threadIdx.x * 2 + j * (kThreads * 2);
+      if (e < total) v[j] = ll_load2(src + (size_t)e * 2);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int e = e_begin + threadIdx.x * 2 + j * (kThreads * 2);
+      if (e < total) {
+        while (v[j].y != seq || v[j].w != seq) v[j] = ll_load2(src + (size_t)e * 2);
+        x[j] = make_float2(__uint_as_float(v[j].x), __uint_as_float(v[j].z));
+      } else {
+        x[j] = make_float2(0.f, 0.f);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int e = e_begin + threadIdx.x * 2 + j * (kThreads * 2);
+      x[j] = e < total ? __ldcg(reinterpret_cast<const float2*>(src + e)) : make_float2(0.f, 0.f);
+    }
+  }
+  const int cpr = K >> 6;  // 64-element chunks (= warps' spans) per row
+  if (norm_w || raw_copy) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int e = e_begin + threadIdx.x * 2 + j * (kThreads * 2);
+      if (raw_copy && e < total) *reinterpret_cast<float2*>(raw_copy + e) = x[j];
+      if (norm_w) {
+        const float ss = warp_sum(x[j].x * x[j].x + x[j].y * x[j].y);
+        const int ci = warp + j * kWarps;  // chunk index: row ci / cpr, slot ci % cpr
+        if (lane == 0 && ci * 64 < total) part[ci] = ss;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) {
+    const int e = e_begin + threadIdx.x * 2 + j * (kThreads * 2);
+    if (e >= total) continue;
+    const int u = e / K, k = e - u * K;
+    float a = x[j].x, b = x[j].y;
+    if (norm_w) {
+      float ss = 0.f;
+      for (int c = 0; c < cpr; ++c) ss += part[u * cpr + c];
+      const float inv = 1.0f / sqrtf(ss / (float)K + 1e-6f);
+      const float2 w = __ldg(reinterpret_cast<const float2*>(norm_w + k));
+      a = (a * inv) * w.x;
+      b = (b * inv) * w.y;
+    }
+    tc_store_split2(bt, u, k, a, b);
+  }
 }
 
 // The weight ring of a CTA: nbuf shared buffers filled by TMA in tile order.  Tile i lives in
@@ -1333,7 +1512,7 @@ __device__ __forceinline__ void stage_qatt(const ArParams& p, int li, const Team
 // ---------------------------------------------------------------------------
 // the persistent kernel: an interpreter over p.prog with one shared GEMV body
 // ---------------------------------------------------------------------------
-template <typename WT, int TU, bool LL>
+template <typename WT, int TU, bool LL, bool TC = false>
 __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid_constant__ ArParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ SamplerSmem ssm;
@@ -1341,8 +1520,15 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
   __shared__ unsigned char stage_tiles[kMaxStages];
   __shared__ int conv_phase[kMaxLayers], conv_slot[kMaxLayers];
   __shared__ int s_tok[kMaxUttPerTeam], s_done[kMaxUttPerTeam];
+  __shared__ __align__(8) unsigned long long accbar;  // tensor-core path: "accumulator ready" mbarrier
+  __shared__ unsigned tmem_slot;
+  __shared__ float tc_part[TC ? 8 * 32 : 1];  // tensor-core stage-in: per-row partial sums of squares
   constexpr int EL = LL ? 2 : 1;  // floats per activation element in the exchange buffers
-  float* act = reinterpret_cast<float*>(smem_raw);  // [nb][max(D,F)] (or 2 x [nb][D] + tap scratch)
+  constexpr bool kTcBuild = TC;  // the tcgen05 instantiations (bf16 weights, TU == 8) carry no FFMA2 tile loop and vice versa
+  static_assert(!TC || (TU == 8 && sizeof(WT) == 2), "tensor-core path: bf16 weights, 8-utterance B operand");
+  // dynamic shared memory, 1024-byte aligned (the swizzled tensor-core operands need it): p.act_off / ring_off / table_off
+  unsigned char* const smem_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* act = reinterpret_cast<float*>(smem_base + p.act_off);  // [nb][max(D,F)] (or 2 x [nb][D] + tap scratch)
   TeamCtx tc;
   tc.team = blockIdx.x / p.P;
   tc.rank = blockIdx.x % p.P;
@@ -1355,25 +1541,40 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
   unsigned* bar = p.barrier + (size_t)tc.team * 32;
   unsigned epoch = 0;
   const int D = p.D, F = p.F;
-  float* xraw = act + (size_t)tc.nb * D;  // second [nb][D] buffer (GLU stage only)
+  constexpr bool use_tc = TC;
   const unsigned act_s = smem_u32(act);
-  const unsigned scratch_s = act_s + (unsigned)(2 * tc.nb * D) * 4u;  // GLU stage: per-warp dwconv tap rows
+  // tensor-core path: the act region starts with the B operand ([F / 64 chunks][32 rows x 128 B]); the fp32 staging rows
+  // of the K = D stages sit behind the D / 64 chunks those stages use (the FFN2 stage, K = F, converts straight from
+  // the exchange buffer and needs no staging), the dwconv tap scratch behind them
+  float* gact = use_tc ? act + (size_t)p.ksc * (kTcBChunk / 4) : act;
+  const unsigned gact_s = smem_u32(gact);
+  float* xraw = gact + (size_t)tc.nb * D;  // second [nb][D] buffer (GLU stage only)
+  const unsigned scratch_s = gact_s + (unsigned)(2 * tc.nb * D) * 4u;  // GLU stage: dwconv tap rows
+  unsigned acc_phase = 0;
   const int n_ut = (tc.nb + TU - 1) / TU;
   // ---- weight ring: [act region][nbuf x wbuf][tile table]
   WeightRing ring;
   {
-    TileDesc* tab = reinterpret_cast<TileDesc*>(smem_raw + p.act_bytes + (size_t)p.nbuf * p.wbuf_bytes);
+    TileDesc* tab = reinterpret_cast<TileDesc*>(smem_base + p.table_off);
     const int nt = p.n_tiles[tc.rank];
     const TileDesc* gt = p.tiles + (size_t)tc.rank * kMaxTilesPerStep;
     for (int i = threadIdx.x; i < nt; i += kThreads) tab[i] = gt[i];
     for (int i = threadIdx.x; i < p.n_stage; i += kThreads) stage_tiles[i] = p.stage_tiles[(size_t)tc.rank * kMaxStages + i];
     if (threadIdx.x == 0) {
       for (int i = 0; i < p.nbuf; ++i) mbar_init(&wbars[i], 1);
+      mbar_init(&accbar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (TC && warp == 0) {  // 32 tensor-memory columns for the whole launch
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((unsigned)kTcCols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (TC) tc_fence_before();
     __syncthreads();
+    if (TC) tc_fence_after();
     ring.bars = wbars;
-    ring.base = smem_u32(smem_raw + p.act_bytes);
+    ring.base = smem_u32(smem_base + p.ring_off);
     ring.wbuf = (unsigned)p.wbuf_bytes;
     ring.nbuf = p.nbuf;
     ring.table = tab;
@@ -1469,27 +1670,44 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
           for (int u = warp; u < tc.nb; u += kWarps) {
             const int b = tc.b0 + u;
             const float* cr = p.cond + ((size_t)b * p.steps + t) * D;
-            for (int k = lane * 4; k < D; k += 128) cp_async16(act_s + (unsigned)(u * D + k) * 4u, cr + k);
+            for (int k = lane * 4; k < D; k += 128) cp_async16(gact_s + (unsigned)(u * D + k) * 4u, cr + k);
             const int row = (t == 0) ? p.V : s_tok[u];
             const float* er = p.emb + (size_t)row * D;
-            for (int k = lane * 4; k < D; k += 128) cp_async16(act_s + (unsigned)((tc.nb + u) * D + k) * 4u, er + k);
+            for (int k = lane * 4; k < D; k += 128) cp_async16(gact_s + (unsigned)((tc.nb + u) * D + k) * 4u, er + k);
           }
           cp_async_commit();
           cp_async_wait0();
           __syncwarp();
           for (int u = warp; u < tc.nb; u += kWarps) {
             for (int k = lane * 4; k < D; k += 128) {
-              const float4 c = *reinterpret_cast<float4*>(act + (size_t)u * D + k);
+              const float4 c = *reinterpret_cast<float4*>(gact + (size_t)u * D + k);
               const float4 e = *reinterpret_cast<float4*>(xraw + (size_t)u * D + k);
               const float4 x = make_float4(c.x + e.x, c.y + e.y, c.z + e.z, c.w + e.w);
-              *reinterpret_cast<float4*>(act + (size_t)u * D + k) = x;
+              *reinterpret_cast<float4*>(gact + (size_t)u * D + k) = x;
               *reinterpret_cast<float4*>(xraw + (size_t)u * D + k) = x;
             }
           }
           __syncwarp();
         }
-        stage_rows<LL>(src ? src + (size_t)tc.b0 * K * EL : nullptr, tc.nb, K, act, norm_w,
-                       (kind == K_GLU && src) ? xraw : nullptr, src_seq);
+        if (use_tc && src) {
+          // one pass: poll, (sum of squares, normalise,) split into three bf16 terms, store into the B operand
+          const float* xs = src + (size_t)tc.b0 * K * EL;
+          float* raw = kind == K_GLU ? xraw : nullptr;
+          if (norm_w || raw) {  // K = D: the whole block in one round (the rows' sums of squares need all of it)
+            tc_stage_in<LL, 3>(xs, tc.nb, K, 0, tc.nb * K, src_seq, norm_w, raw, tc_part, act_s);
+          } else {              // K = F: rounds of 6 pairs per thread
+            for (int e0 = 0; e0 < tc.nb * K; e0 += 6 * kThreads * 2)
+              tc_stage_in<LL, 6>(xs, tc.nb, K, e0, min(tc.nb * K, e0 + 6 * kThreads * 2), src_seq, nullptr, nullptr, tc_part, act_s);
+          }
+        } else {
+          stage_rows<LL>(src ? src + (size_t)tc.b0 * K * EL : nullptr, tc.nb, K, gact, norm_w,
+                         (kind == K_GLU && src) ? xraw : nullptr, src_seq);
+          if (use_tc) {  // layer 0: x was built in shared memory
+            __syncthreads();
+            tc_btile_from_rows(gact, tc.nb, K, act_s);
+          }
+        }
+        if (use_tc) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
         __syncthreads();
         ts.mark();  // activations staged
         // ---- this CTA's rows, tile by tile from the weight ring
@@ -1498,6 +1716,135 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
         float* state = p.ring + L.ring_off;
         const int dil = L.dil;
         const int phase = conv_phase[li], slot_now = conv_slot[li];
+        if constexpr (TC) {
+          // ================= tensor-core tiles: thread = (accumulator row, two utterances)
+          // M = 64: accumulator row m sits in tensor-memory lane 32 * (m / 16) + m % 16 -> lanes 0..15 of every warp work
+          const int q = warp & 3, jc = warp >> 2;  // tensor-memory lane quarter; columns 8jc..8jc+7 = utterances 2jc, 2jc+1
+          const int rt = lane < 16 ? 16 * q + lane : 64;  // row of the tile (64 = none)
+          const unsigned tmem = tmem_slot;
+          long long* tdbg = (ts.buf && (si == 1 || si == 7)) ? ts.buf + (si == 1 ? 192 : 208) : nullptr;  // tile phase stamps
+          int tdn = 0;
+#define TCMARK() do { if (tdbg && tdn < 16) tdbg[tdn++] = clock64(); } while (0)
+          TCMARK();
+#pragma unroll 1
+          for (int ti = stage_tiles[si]; ti > 0; --ti) {
+            const TileDesc* td;
+            const unsigned wb = ring.acquire(td);
+            TCMARK();  // weights landed
+            const bool last = (td->flags & 2) != 0;
+            // GLU: a group of 8 operand rows = 4 channels (value rows 0..3, their gate rows 4..7)
+            const int g8 = rt & 7;
+            const int ri = glu ? ((rt >> 3) * 4 + (g8 & 3)) : rt;  // row (GLU: channel) index inside the tile
+            const bool row_ok = rt < td->ngrp * 8 && ri < td->nrows && (!glu || g8 < 4);
+            const int r = td->row0 + (row_ok ? ri : 0);             // output feature (GLU: channel)
+            const unsigned epi_s = wb + td->bytes0 + td->bytes1;
+            float res_v[2] = {0.f, 0.f};
+            float* rbp[2] = {nullptr, nullptr};
+            if (last) {  // epilogue operands: their latency hides under the contraction
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int u = 2 * jc + e;
+                const bool mine = row_ok && u < tc.nb;
+                const int b = tc.b0 + (mine ? u : 0);
+                if (glu) {
+                  rbp[e] = state + (((size_t)b * D + r) * dil + phase) * p.KcP;
+                  if (mine) {
+                    const unsigned tap_w = scratch_s + (unsigned)((ri * 8 + u) * p.KcP) * 4u;
+                    for (int q4 = 0; q4 < p.KcP; q4 += 4) cp_async16(tap_w + (unsigned)q4 * 4u, rbp[e] + q4);
+                  }
+                } else if (mine && (kind == K_FFN2 || kind == K_O)) {
+                  res_v[e] = ldcg1(dst + ((size_t)b * ld_dst + r) * EL);  // own rows, written at an earlier stage
+                }
+              }
+              cp_async_commit();
+            }
+            // ---- the contraction: one thread issues (K slices of the tile) x (D / 64) x 4 instructions [64 x 32 x 16]
+            if (threadIdx.x == 0) {
+              tc_fence_after();
+              constexpr unsigned idesc = tc_idesc(64, kTcCols);
+              const bool first = (td->flags & 1) != 0;
+              const int nsl = td->bytes1 ? 2 : 1;  // part 1 = the same rows' next K slice
+#pragma unroll 1
+              for (int sl = 0; sl < nsl; ++sl) {
+                const unsigned long long da = tc_desc(wb + (unsigned)sl * td->bytes0, (unsigned)p.ksc * 1024u);
+                const unsigned long long db = tc_desc(act_s + (unsigned)(td->kc0 + sl * p.ksc) * (unsigned)kTcBChunk, 1024u);
+#pragma unroll 1
+                for (int c = 0; c < p.ksc; ++c) {
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    tc_mma_bf16(tmem, da + (unsigned long long)(c * 64 + k * 2), db + (unsigned long long)(c * (kTcBChunk >> 4) + k * 2), idesc,
+                                (first && sl == 0 && c == 0 && k == 0) ? 0u : 1u);
+                }
+              }
+              tc_commit(&accbar);  // arrives when every instruction above has completed (also frees the weight buffer)
+              TCMARK();  // instructions issued
+            }
+            mbar_wait(&accbar, acc_phase);
+            acc_phase ^= 1u;
+            TCMARK();  // accumulator complete
+            if (last) {
+              tc_fence_after();
+              unsigned d8[8];
+              tc_ld8(tmem + ((unsigned)(32 * q) << 16) + (unsigned)(8 * jc), d8);
+              tc_fence_before();
+              cp_async_wait0();
+              TCMARK();  // accumulator in registers
+              // x = hi + mid + lo: add the small terms first
+              const float vv[2] = {(__uint_as_float(d8[2]) + __uint_as_float(d8[1])) + __uint_as_float(d8[0]),
+                                   (__uint_as_float(d8[6]) + __uint_as_float(d8[5])) + __uint_as_float(d8[4])};
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                float v = vv[e];
+                const float gate_v = __shfl_xor_sync(0xffffffffu, v, 4);  // GLU: the gate row sits 4 lanes up
+                const int u = 2 * jc + e;
+                const bool mine = row_ok && u < tc.nb;
+                if (!mine) continue;
+                const int b = tc.b0 + u;
+                float* d = dst + ((size_t)b * ld_dst + r) * EL;
+                if (glu) {
+                  const int Kc = p.Kc;
+                  const unsigned er = epi_s + (unsigned)(ri * p.KcE) * 4u;  // [w0..w(Kc-1), dw_b, b_value, b_gate]
+                  const unsigned tap_w = scratch_s + (unsigned)((ri * 8 + u) * p.KcP) * 4u;
+                  const float a = v + lds32(er + (unsigned)(Kc + 1) * 4u);
+                  const float gt = gate_v + lds32(er + (unsigned)(Kc + 2) * 4u);
+                  const float h = a * sigmoid_ref(gt);
+                  rbp[e][slot_now] = h;
+                  float y = 0.f;
+                  int pos = slot_now + 1;
+#pragma unroll 1
+                  for (int j = 0; j < Kc - 1; ++j) {
+                    if (pos == Kc) pos = 0;
+                    y += lds32(tap_w + (unsigned)pos * 4u) * lds32(er + (unsigned)j * 4u);
+                    ++pos;
+                  }
+                  y += h * lds32(er + (unsigned)(Kc - 1) * 4u);
+                  y += lds32(er + (unsigned)Kc * 4u);
+                  v = xraw[(size_t)u * D + r] + y;
+                } else {
+                  const float bias_v = (kind == K_Q || kind == K_O) ? 0.f : lds32(epi_s + (unsigned)(td->off2 + ri) * 4u);
+                  if (kind == K_FFN1) {
+                    v = gelu_erf(v + bias_v);
+                  } else if (kind == K_FFN2) {
+                    v = res_v[e] + (v + bias_v);
+                    if (trace) trace[(size_t)b * D + r] = v;
+                  } else if (kind == K_O) {
+                    v = res_v[e] + scale * v;
+                    if (trace) trace[(size_t)b * D + r] = v;
+                  } else if (kind == K_HEAD) {
+                    v += bias_v;
+                    if (trace) trace[(size_t)b * p.V + r] = v;
+                  }
+                }
+                if (LL) ll_store(d, v, seq);
+                else *d = v;
+              }
+            }
+            TCMARK();  // epilogue done (thread 0)
+            ring.release();  // (block barrier inside) every warp has read its accumulator columns before the next reset
+            TCMARK();  // released
+          }
+#undef TCMARK
+        } else {
 #pragma unroll 1
         for (int ti = stage_tiles[si]; ti > 0; --ti) {
           const TileDesc* td;
@@ -1551,7 +1898,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
               res_v = ldcg1(d);  // own slice: written by this CTA at an earlier stage (value word)
             }
             cp_async_commit();
-            float v = warp_rows_s<R, TU, WT>(wr, act_s + (unsigned)ub * (unsigned)K * 4u, K, lane);
+            float v = warp_rows_s<R, TU, WT>(wr, gact_s + (unsigned)ub * (unsigned)K * 4u, K, lane);
             // GLU: the gate total of (channel i, utterance uu) lives in the lanes of output (RC + i)*TU + uu
             const float gate_v = __shfl_sync(0xffffffffu, v, (((RC + (i % RC)) * TU + uu) << SH) & 31);
             cp_async_wait0();
@@ -1596,6 +1943,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
           }
           ring.release();
         }
+        }
         ts.mark();  // tiles done
         if (glu) {
           float* tmp = cur;
@@ -1633,6 +1981,14 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
     }
   }
   ring.drain();  // early team exit: prefetched tiles must land before the CTA exits
+  if (TC) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"((unsigned)kTcCols) : "memory");
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
