@@ -183,6 +183,12 @@ int sopro_ar_debug_sampled(sopro_ar_session_t* s, int32_t* dst, void* stream);
 /* copy the text K/V built by sopro_ar_begin into k_dst / v_dst, each
  * [n_attn_layers, batch, H, Lpad, Dh] f32 (device), Lpad = max_text_len rounded up to 4 */
 int sopro_ar_debug_kv(sopro_ar_session_t* s, float* k_dst, float* v_dst, void* stream);
+/* The kernel's sampler (sample_token, sampling.py:24-93) on ONE logits row, outside the step: HOST buffers; `hist` = the
+ * n_hist tokens generated so far (repetition penalty looks at the last 50), `noise` = the Exp(1) draws of this step (first
+ * noise_k columns of the tape row: >= top_k when top_p < 1, vocab otherwise), `recovery` != 0 samples with the recovery
+ * (top_p, temperature).  -> token_out.  Needs a device but no engine. */
+int sopro_debug_sample(const float* logits, int vocab, const int32_t* hist, int n_hist, const float* noise, int noise_k,
+                       const sopro_ar_sampling_t* sampling, int recovery, int device, int32_t* token_out);
 
 
 /* ======================= Mimi codec decode (codes -> waveform) =======================

@@ -1095,6 +1095,89 @@ int sopro_ar_debug_sampled(sopro_ar_session_t* s, int32_t* dst, void* stream) {
   return SOPRO_OK;
 }
 
+}  // extern "C"
+
+namespace {
+__global__ void __launch_bounds__(kThreads, 1) sampler_debug_kernel(const __grid_constant__ ArParams p, int t) {
+  extern __shared__ __align__(16) unsigned char dbg_smem[];
+  __shared__ SamplerSmem ssm;
+  float* sx = reinterpret_cast<float*>(dbg_smem);
+  float* sp = sx + p.Vpad;
+  unsigned char* flags = reinterpret_cast<unsigned char*>(sx + 2 * p.Vpad);
+  sample_utterance(p, 0, t, sx, sp, flags, ssm, 0, 0u, 0u);
+}
+}  // namespace
+
+extern "C" {
+
+int sopro_debug_sample(const float* logits, int vocab, const int32_t* hist, int n_hist, const float* noise, int noise_k,
+                       const sopro_ar_sampling_t* q, int recovery, int device, int32_t* token_out) {
+  if (!logits || !noise || !q || !token_out || (n_hist > 0 && !hist)) return fail(SOPRO_ERR_INVALID, "null argument");
+  if (vocab < 2 || vocab > kMaxVocab || n_hist < 0 || q->top_k < 1 || q->top_k > kMaxTopK)
+    return fail(SOPRO_ERR_INVALID, "sampler hook: vocab in [2,%d], top_k in [1,%d]", kMaxVocab, kMaxTopK);
+  const int need = (q->top_p < 1.0f && q->recovery_top_p < 1.0f) ? std::min(q->top_k, vocab) : vocab;
+  if (noise_k < need) return fail(SOPRO_ERR_INVALID, "sampler hook: noise_k=%d, need %d", noise_k, need);
+  CK(cudaSetDevice(device));
+  const int Vpad = (int)align_up((size_t)vocab, 4), steps = n_hist + 1;
+  float *d_logits = nullptr, *d_noise = nullptr;
+  int *d_tok = nullptr, *d_sampled = nullptr, *d_n = nullptr, *d_done = nullptr;
+  UttState* d_st = nullptr;
+  SamplingDev* d_samp = nullptr;
+  unsigned* d_ll = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_logits); cudaFree(d_noise); cudaFree(d_tok); cudaFree(d_sampled); cudaFree(d_n); cudaFree(d_done);
+    cudaFree(d_st); cudaFree(d_samp); cudaFree(d_ll);
+  };
+  cudaError_t err = cudaMalloc(&d_logits, (size_t)Vpad * 4);
+  if (err == cudaSuccess) err = cudaMalloc(&d_noise, (size_t)steps * noise_k * 4);
+  if (err == cudaSuccess) err = cudaMalloc(&d_tok, (size_t)steps * 4);
+  if (err == cudaSuccess) err = cudaMalloc(&d_sampled, (size_t)steps * 4);
+  if (err == cudaSuccess) err = cudaMalloc(&d_n, 4);
+  if (err == cudaSuccess) err = cudaMalloc(&d_done, 4);
+  if (err == cudaSuccess) err = cudaMalloc(&d_st, sizeof(UttState));
+  if (err == cudaSuccess) err = cudaMalloc(&d_samp, sizeof(SamplingDev));
+  if (err == cudaSuccess) err = cudaMalloc(&d_ll, 8);
+  if (err == cudaSuccess) err = cudaMemset(d_logits, 0, (size_t)Vpad * 4);
+  if (err == cudaSuccess) err = cudaMemcpy(d_logits, logits, (size_t)vocab * 4, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemset(d_noise, 0, (size_t)steps * noise_k * 4);
+  if (err == cudaSuccess) err = cudaMemcpy(d_noise + (size_t)n_hist * noise_k, noise, (size_t)noise_k * 4, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemset(d_tok, 0, (size_t)steps * 4);
+  if (err == cudaSuccess && n_hist) err = cudaMemcpy(d_tok, hist, (size_t)n_hist * 4, cudaMemcpyHostToDevice);
+  UttState st{n_hist, n_hist ? hist[n_hist - 1] : -1, 0, recovery ? 1 : 0, 0, {0, 0, 0}};
+  SamplingDev sd{q->top_p, q->temperature, q->recovery_top_p, q->recovery_temp, q->repetition_penalty, q->top_k, 0, q->loop_streak,
+                 q->min_gen_frames, q->stop_on_first_eos};
+  if (err == cudaSuccess) err = cudaMemcpy(d_st, &st, sizeof(st), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemcpy(d_samp, &sd, sizeof(sd), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    cleanup();
+    return fail(SOPRO_ERR_CUDA, "sampler hook: %s", cudaGetErrorString(err));
+  }
+  ArParams p{};
+  p.V = vocab;
+  p.Vpad = Vpad;
+  p.eos_id = vocab - 1;
+  p.B = 1;
+  p.steps = steps;
+  p.noise_k = noise_k;
+  p.noise = d_noise;
+  p.logits = d_logits;
+  p.tokens = d_tok;
+  p.sampled = d_sampled;
+  p.n_tokens = d_n;
+  p.done = d_done;
+  p.st = d_st;
+  p.samp = d_samp;
+  p.tok_ll = d_ll;
+  const size_t smem = (size_t)Vpad * 8 + Vpad + 16;
+  sampler_debug_kernel<<<1, kThreads, smem>>>(p, n_hist);
+  err = cudaGetLastError();
+  if (err == cudaSuccess) err = cudaDeviceSynchronize();
+  if (err == cudaSuccess) err = cudaMemcpy(token_out, d_sampled + n_hist, 4, cudaMemcpyDeviceToHost);
+  cleanup();
+  if (err != cudaSuccess) return fail(SOPRO_ERR_CUDA, "sampler hook: %s", cudaGetErrorString(err));
+  return SOPRO_OK;
+}
+
 int sopro_ar_debug_kv(sopro_ar_session_t* s, float* k_dst, float* v_dst, void* stream) {
   if (!s) return fail(SOPRO_ERR_INVALID, "null argument");
   const size_t n = (size_t)s->e->n_attn * s->B * s->Lmax * s->e->D * 4;

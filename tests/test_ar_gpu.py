@@ -185,6 +185,43 @@ def test_tensor_core_contraction_is_refused_where_it_cannot_run():
     ses.close()
 
 
+def test_sampler_known_answers_on_the_device_sampler():
+    """The 29 sampler known-answer cases of the reference (tests/golden/sampler_kat.json, written by the reference's
+    sample_token) through the kernel's sampler IN ISOLATION (sopro_debug_sample): flat / mid / peaked rows, history
+    lengths 0..80 with periodic histories, recovery parameters, temperature 1, no repetition penalty, top_p = 1 (the
+    unsorted multinomial branch, noise indexed by token id), a spike, NaN / +-inf logits, small vocabularies, top_k
+    larger than the vocabulary, a tiny top_p.  Skipped: the two top_k = 0 cases (ar_stream always passes top_k = 50,
+    reference model.py:283-292; the C-ABI rejects top_k = 0)."""
+    import ctypes as C
+    import json
+
+    from sopro_b200 import _lib
+    from tests.cases import SAMPLER_CASES, sampler_case_inputs
+
+    lib = _lib.load()
+    with open(os.path.join(GOLD, "sampler_kat.json")) as f:
+        kat = json.load(f)
+    ran = 0
+    for name, spec in SAMPLER_CASES.items():
+        logits, hist, kw, seed = sampler_case_inputs(spec)
+        if int(kw["top_k"]) < 1:
+            continue
+        V = int(logits.numel())
+        tape = O.noise_tape(seed, 1, V)[0].contiguous()
+        top_k = min(int(kw["top_k"]), 64)
+        q = _lib.ArSampling(float(kw["top_p"]), float(kw["temperature"]), float(kw["top_p"]), float(kw["temperature"]),
+                            float(kw["repetition_penalty"]), top_k, 0, 8, 2 ** 31 - 1, 0)
+        lg = logits.to(torch.float32).contiguous()
+        h = np.asarray(hist, dtype=np.int32)
+        out = C.c_int32(-1)
+        nk = V if float(kw["top_p"]) >= 1.0 else min(top_k, V)
+        _lib.check(lib.sopro_debug_sample(lg.data_ptr(), V, h.ctypes.data if len(hist) else None, len(hist), tape.data_ptr(), nk,
+                                          C.byref(q), 0, 0, C.byref(out)))
+        assert out.value == kat[name], f"{name}: device sampler {out.value}, reference {kat[name]}"
+        ran += 1
+    assert ran == len(SAMPLER_CASES) - 2
+
+
 def test_kv_cache_matches_oracle():
     spec, cfg, sd, inp, g, eng, steps, tape = _case("default_fp32")
     L = inp["txt_seq"].shape[1]
