@@ -167,6 +167,17 @@ int sopro_ar_generate_host(sopro_ar_session_t* s, int batch, int steps, const fl
                            const float* noise, int noise_k, const sopro_ar_sampling_t* sampling,
                            int32_t* tokens_out, int32_t* n_tokens_out, void* stream);
 
+/* ---- host-side noise tapes --------------------------------------------------------------------------------------
+ * The Exp(1) draws torch.multinomial consumes on the CPU (reference sampling.py:83-93: multinomial == argmax(p / q),
+ * q ~ Exp(1) from torch's CPU generator, `vocab` draws per step), reproduced bit for bit by a host-side mt19937 for a
+ * PRIVATE generator seeded like torch.manual_seed(seed).  Only the first `keep` columns of each [vocab] row are
+ * materialised (the sampler reads top_k of them); the generator still advances by the whole row.  Pure host code. */
+typedef struct sopro_noise sopro_noise_t;
+int sopro_noise_create(uint64_t seed, sopro_noise_t** out);
+/* next n_rows rows of the tape -> out [n_rows, keep] f32 (host) */
+int sopro_noise_rows(sopro_noise_t* g, int n_rows, int vocab, int keep, float* out);
+int sopro_noise_destroy(sopro_noise_t* g);
+
 /* ---- test / debug hooks (used by tests/, not by the product path) ---- */
 /* teacher forcing: token fed back at step t is forced[b, t]; the sampled one goes to
  * `sampled` (sopro_ar_debug_sampled).  NULL disables. [batch, steps] i32 device. */

@@ -136,6 +136,9 @@ SYMBOLS = {
     "sopro_ar_set_timing": (_I, [_VP, _VP, _I]),
     "sopro_ar_debug_sampled": (_I, [_VP, _VP, _VP]),
     "sopro_ar_debug_kv": (_I, [_VP, _VP, _VP, _VP]),
+    "sopro_noise_create": (_I, [C.c_uint64, _VP]),
+    "sopro_noise_rows": (_I, [_VP, _I, _I, _I, _VP]),
+    "sopro_noise_destroy": (_I, [_VP]),
     "sopro_debug_sample": (_I, [_VP, _I, _VP, _I, _VP, _I, _VP, _I, _I, _VP]),
     "sopro_mimi_create": (_I, [C.POINTER(MimiConfigC), C.POINTER(MimiWeights), _I, C.POINTER(_VP)]),
     "sopro_mimi_destroy": (_I, [_VP]),

@@ -345,7 +345,9 @@ __device__ __forceinline__ float4 ldsw4<__nv_bfloat16>(unsigned a) {
 //       so D column 4u+0..2 summed = sum_k w[k] * x[k] with fp32 accumulation -- the same arithmetic as the FFMA2 path
 //       up to the order of the fp32 additions.
 // ---------------------------------------------------------------------------
-constexpr int kTcCols = 32;            // tensor-memory columns (= B rows)
+constexpr int kTcCols = 32;            // B rows = accumulator columns of one instruction
+constexpr int kTcAcc = 4;              // independent accumulator tiles: consecutive instructions of a tile's K loop go to
+                                       // different tiles (summed in the epilogue), so none waits for its predecessor's result
 constexpr int kTcBChunk = 32 * 128;    // bytes of one 64-wide K chunk of the B operand
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -1562,11 +1564,12 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
     for (int i = threadIdx.x; i < p.n_stage; i += kThreads) stage_tiles[i] = p.stage_tiles[(size_t)tc.rank * kMaxStages + i];
     if (threadIdx.x == 0) {
       for (int i = 0; i < p.nbuf; ++i) mbar_init(&wbars[i], 1);
-      mbar_init(&accbar, 1);
+      mbar_init(&accbar, TC ? kTcAcc : 1);  // one commit per issuing thread
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (TC && warp == 0) {  // 32 tensor-memory columns for the whole launch
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"((unsigned)kTcCols)
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)),
+                   "r"((unsigned)(kTcCols * kTcAcc))
                    : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -1759,7 +1762,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
               cp_async_commit();
             }
             // ---- the contraction: one thread issues (K slices of the tile) x (D / 64) x 4 instructions [64 x 32 x 16]
-            if (threadIdx.x == 0) {
+            if (lane == 0 && warp < kTcAcc) {  // one issuing thread per accumulator tile (K slice `warp` of every chunk)
               tc_fence_after();
               constexpr unsigned idesc = tc_idesc(64, kTcCols);
               const bool first = (td->flags & 1) != 0;
@@ -1770,10 +1773,9 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
                 const unsigned long long db = tc_desc(act_s + (unsigned)(td->kc0 + sl * p.ksc) * (unsigned)kTcBChunk, 1024u);
 #pragma unroll 1
                 for (int c = 0; c < p.ksc; ++c) {
-#pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    tc_mma_bf16(tmem, da + (unsigned long long)(c * 64 + k * 2), db + (unsigned long long)(c * (kTcBChunk >> 4) + k * 2), idesc,
-                                (first && sl == 0 && c == 0 && k == 0) ? 0u : 1u);
+                  const int k = warp;  // K slice k of every chunk accumulates in tile k (kTcAcc == 4)
+                  tc_mma_bf16(tmem + (unsigned)(k * kTcCols), da + (unsigned long long)(c * 64 + k * 2),
+                              db + (unsigned long long)(c * (kTcBChunk >> 4) + k * 2), idesc, (first && sl == 0 && c == 0) ? 0u : 1u);
                 }
               }
               tc_commit(&accbar);  // arrives when every instruction above has completed (also frees the weight buffer)
@@ -1784,14 +1786,18 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
             TCMARK();  // accumulator complete
             if (last) {
               tc_fence_after();
-              unsigned d8[8];
-              tc_ld8(tmem + ((unsigned)(32 * q) << 16) + (unsigned)(8 * jc), d8);
+              float vv[2] = {0.f, 0.f};
+#pragma unroll
+              for (int a = 0; a < kTcAcc; ++a) {  // the accumulator tiles in a fixed order
+                unsigned d8[8];
+                tc_ld8(tmem + ((unsigned)(32 * q) << 16) + (unsigned)(a * kTcCols + 8 * jc), d8);
+                // x = hi + mid + lo: add the small terms first
+                vv[0] += (__uint_as_float(d8[2]) + __uint_as_float(d8[1])) + __uint_as_float(d8[0]);
+                vv[1] += (__uint_as_float(d8[6]) + __uint_as_float(d8[5])) + __uint_as_float(d8[4]);
+              }
               tc_fence_before();
               cp_async_wait0();
               TCMARK();  // accumulator in registers
-              // x = hi + mid + lo: add the small terms first
-              const float vv[2] = {(__uint_as_float(d8[2]) + __uint_as_float(d8[1])) + __uint_as_float(d8[0]),
-                                   (__uint_as_float(d8[6]) + __uint_as_float(d8[5])) + __uint_as_float(d8[4])};
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
                 float v = vv[e];
@@ -1986,7 +1992,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
     __syncthreads();
     if (warp == 0) {
       tc_fence_after();
-      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"((unsigned)kTcCols) : "memory");
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"((unsigned)(kTcCols * kTcAcc)) : "memory");
     }
   }
 }

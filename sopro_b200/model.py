@@ -76,6 +76,33 @@ def _tape_pool():
     return _TAPE_POOL
 
 
+_NATIVE_NOISE = None
+
+
+def _native_noise_ok() -> bool:
+    """The host-side mt19937 tape generator of the library (csrc/noise_host.cu) is used for private generators when it
+    reproduces THIS torch build's CPU exponential_ bit for bit (checked once per process; a torch built with another
+    sampling kernel falls back to torch itself)."""
+    global _NATIVE_NOISE
+    if _NATIVE_NOISE is None:
+        try:
+            import ctypes as C
+
+            from . import _lib
+
+            lib = _lib.load()
+            h = C.c_void_p()
+            _lib.check(lib.sopro_noise_create(C.c_uint64(987654321), C.byref(h)))
+            got = torch.empty(3, 7)
+            _lib.check(lib.sopro_noise_rows(h, 3, 97, 7, got.data_ptr()))
+            lib.sopro_noise_destroy(h)
+            want = torch.empty(3, 97).exponential_(1.0, generator=torch.Generator().manual_seed(987654321))[:, :7]
+            _NATIVE_NOISE = bool(torch.equal(got, want))
+        except Exception:
+            _NATIVE_NOISE = False
+    return _NATIVE_NOISE
+
+
 class _Noise:
     """The Exp(1) draws `steps` successive torch.multinomial calls would consume (see sopro_b200/sampling.py),
     produced block by block as the kernel launches need them (a [n, V] draw equals n successive [V] draws), with
@@ -87,6 +114,48 @@ class _Noise:
         self.gen = torch.Generator().manual_seed(int(seed)) if seed is not None else (generator or torch.default_generator)
         self.marks: List[Tuple[int, torch.Tensor]] = []  # (first row of a block, generator state before it)
         self.drawn = 0
+        self._native = None  # private generators: the library's host-side mt19937 (bit-equal to torch, skips unread draws)
+        if seed is not None and _native_noise_ok():
+            import ctypes as C
+
+            from . import _lib
+
+            self._lib = _lib.load()
+            h = C.c_void_p()
+            _lib.check(self._lib.sopro_noise_create(C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), C.byref(h)))
+            self._native = h
+
+    def __del__(self):
+        if getattr(self, "_native", None) is not None:
+            self._lib.sopro_noise_destroy(self._native)
+            self._native = None
+
+    def rows_keep(self, upto: int, keep: int) -> torch.Tensor:
+        """Rows [drawn, upto), first `keep` columns -> [n, keep] (empty when already drawn)."""
+        upto = min(int(upto), self.steps)
+        n = upto - self.drawn
+        if n <= 0:
+            return torch.empty(0, int(keep))
+        if self._native is not None:
+            out = torch.empty(n, int(keep))
+            self.rows_into(upto, keep, out.numpy())
+            return out
+        return self.rows(upto)[:, : int(keep)]
+
+    def rows_into(self, upto: int, keep: int, out) -> None:
+        """Rows [drawn, upto), first `keep` columns, written into the float32 numpy array `out` [n, keep] (C-contiguous)."""
+        upto = min(int(upto), self.steps)
+        n = upto - self.drawn
+        if n <= 0:
+            return
+        if self._native is not None:
+            assert out.flags["C_CONTIGUOUS"] and out.shape == (n, keep)
+            from . import _lib
+
+            _lib.check(self._lib.sopro_noise_rows(self._native, n, self.vocab, int(keep), out.ctypes.data))
+            self.drawn = upto
+        else:
+            out[...] = self.rows(upto)[:, :keep].numpy()
 
     def rows(self, upto: int) -> torch.Tensor:
         """Draw rows [drawn, upto) -> [n, V] (empty when already drawn)."""
@@ -96,6 +165,10 @@ class _Noise:
             return torch.empty(0, self.vocab)
         if not self.private:
             self.marks.append((self.drawn, self.gen.get_state()))
+        if self._native is not None:
+            out = torch.empty(n, self.vocab)
+            self.rows_into(upto, self.vocab, out.numpy())
+            return out
         self.drawn = upto
         return torch.empty(n, self.vocab).exponential_(1.0, generator=self.gen)
 
@@ -256,9 +329,9 @@ class SoproModel:
             if st["launched"] >= steps or st["launched"] > st["read"]:
                 return
             lo = noise.drawn
-            blk = noise.rows(st["launched"] + per)
+            blk = noise.rows_keep(st["launched"] + per, nk)
             if blk.size(0):
-                tape[0, lo: lo + blk.size(0)].copy_(blk[:, :nk])
+                tape[0, lo: lo + blk.size(0)].copy_(blk)
             ses.run(per)
             st["launched"] = min(steps, st["launched"] + per)
 
@@ -321,7 +394,7 @@ class SoproModel:
         view = out.numpy()  # worker threads are outside the caller's inference_mode: write through numpy
 
         def one(i):
-            view[i] = _Noise(steps, V, int(seeds[i]), None).tape[:, :nk].numpy()
+            _Noise(steps, V, int(seeds[i]), None).rows_into(steps, nk, view[i])
 
         with ThreadPoolExecutor(max_workers=min(B, max(1, len(os.sched_getaffinity(0))))) as ex:
             list(ex.map(one, range(B)))
@@ -355,17 +428,19 @@ class SoproModel:
 
                 def draw(a: int, b: int) -> None:
                     def one(i):
-                        view[i, a:b] = gens[i].rows(b)[:, :nk].numpy()
+                        gens[i].rows_into(b, nk, view[i, a:b])
                     list(pool.map(one, range(B)))
                     dev[:, a:b].copy_(host[:, a:b], non_blocking=True)
 
-                edges, a, step = [], 0, 40
+                # block k+1 must be drawn faster than the device generates block k: the host draws ~10 steps per ms
+                # (64 utterances, 16 threads), the kernel runs ~6 steps per ms -> blocks grow by 1.5x
+                edges, a, step = [], 0, 24
                 while a < steps:
                     b = min(steps, a + step)
                     if steps - b < 24:
                         b = steps
                     edges.append((a, b))
-                    a, step = b, step * 2
+                    a, step = b, (step * 3) // 2
                 draw(*edges[0])
                 ses.begin(cond[:, :steps], txt, [int(x) for x in lens], dev, samp)
                 ses.run(edges[0][1])

@@ -178,3 +178,30 @@ def test_missing_checkpoint_tensors_get_reference_defaults_or_one_clear_error():
     with pytest.raises(KeyError) as ei:
         _complete_state_dict(cfg, cut)
     assert "ar.head.weight" in str(ei.value) and "cond_norm.weight" in str(ei.value)
+
+
+def test_native_noise_tape_is_bit_equal_to_torch_and_skips_the_unread_draws():
+    """csrc/noise_host.cu (host-side mt19937 + ATen's uniform -> -log1p(-u) transform) against this torch build's CPU
+    exponential_: same bits for private generators, also when only the first `keep` columns of each row are materialised
+    and across blocks of rows; the Python _Noise wrapper uses it only after this check (model._native_noise_ok)."""
+    import ctypes as C
+
+    from sopro_b200 import _lib
+    from sopro_b200.model import _Noise, _native_noise_ok
+
+    lib = _lib.load()
+    for seed in (0, 1, 1234, 2 ** 31 + 7, 2 ** 40 + 3):
+        h = C.c_void_p()
+        _lib.check(lib.sopro_noise_create(C.c_uint64(seed), C.byref(h)))
+        g = torch.Generator().manual_seed(seed)
+        for n, V, keep in ((3, 2049, 50), (1, 33, 33), (5, 2049, 2049), (2, 257, 50), (700, 5, 2)):
+            want = torch.empty(n, V).exponential_(1.0, generator=g)[:, :keep].contiguous()
+            got = torch.empty(n, keep)
+            _lib.check(lib.sopro_noise_rows(h, n, V, keep, got.data_ptr()))
+            assert torch.equal(got, want), (seed, n, V, keep)
+        lib.sopro_noise_destroy(h)
+    assert _native_noise_ok()
+    a = _Noise(40, 2049, 77, None)
+    first, second = a.rows_keep(13, 50), a.rows_keep(40, 50)
+    ref = torch.empty(40, 2049).exponential_(1.0, generator=torch.Generator().manual_seed(77))[:, :50]
+    assert torch.equal(torch.cat([first, second]), ref)
