@@ -369,6 +369,11 @@ int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_strid
 /* test hook (teacher forcing): when non-NULL, every stage conditions on the previous codebooks of forced_codes
  * [B, Tmax, Q] i32 (device) instead of on its own argmax results, so one near-tie flip cannot cascade. */
 int sopro_nar_set_forced(sopro_nar_t* n, const int32_t* forced_codes);
+/* Arithmetic unit of the refiner's contractions: -1 = automatic (tensor cores -- tcgen05, every fp32 operand split into
+ * three exact bf16 terms, the six products that reach fp32's last bit, fp32 accumulation -- whenever more than 16 rows are
+ * refined; the fp32 FMA skinny kernel below that), 0 = fp32 FMA kernels only (also: environment SOPRO_NAR_TC=0), 1 = as -1
+ * but fails if the geometry has no tensor-core images. */
+int sopro_nar_set_contraction(sopro_nar_t* n, int mode);
 
 /* ------------------------------------------------------------------------------------------------
  * Prefill: SoproTTSModel.prepare_conditioning (reference model.py:172-216) for B texts that share one prepared

@@ -39,6 +39,8 @@ struct TcOp {
   long long c_bs;      // batch stride of R / outputs (elements)
   int M, N, K, Cin, dil, pad, bias_mod, epi, out_elu;
   int stages;          // filled in by launch()
+  int tap_col[8];      // A column offset of tap j (0 everywhere for convolutions; the NAR refiner's exact three-way bf16 split
+                       // pairs W's K block j with the A term it multiplies: taps over COLUMN groups of the same rows, dil = 0)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -197,7 +199,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) igemm_tc_kernel(const __grid_
         const int k0 = kc * BK;
         const int j = k0 / op.Cin, ci = k0 - j * op.Cin;
         const uint32_t sa = tiles + s * Cfg::kStageBytes;
-        tma_load_3d(sa, &tmA, full0 + 8 * s, ci, m0 + j * op.dil - op.pad, b);
+        tma_load_3d(sa, &tmA, full0 + 8 * s, ci + op.tap_col[j & 7], m0 + j * op.dil - op.pad, b);
         tma_load_2d(sa + Cfg::kABytes, &tmW, full0 + 8 * s, k0, n0);
       }
     }
@@ -538,7 +540,7 @@ struct AttnOp {
 constexpr int kAttnKeys = 384, kAttnDh = 64;
 constexpr int kAttnSmem = 65536 + 49152 + 32768 + 1024;
 
-__global__ void __launch_bounds__(kThreads) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+static __global__ void __launch_bounds__(kThreads) attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                                                            const __grid_constant__ CUtensorMap tmVt, const AttnOp op) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[5];
@@ -826,11 +828,12 @@ inline cudaError_t launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, con
   return cudaGetLastError();
 }
 
-// X: bf16 [B][Min][Cin]; W: bf16 [N][K]
-inline cudaError_t launch(const void* X, long long Min, const void* W, const TcOp& op, int B, cudaStream_t st) {
+// X: bf16 [B][Min][a_cols] (a_cols = 0: Cin columns; larger when op.tap_col addresses column groups); W: bf16 [N][K]
+inline cudaError_t launch(const void* X, long long Min, const void* W, const TcOp& op, int B, cudaStream_t st, int a_cols = 0) {
   const int BN = pick_bn(op.N), BK = pick_bk(op.Cin);
   CUtensorMap tmA, tmW;
-  if (!make_act_map(&tmA, X, B, Min, op.Cin, BK) || !make_weight_map(&tmW, W, op.N, op.K, BN, BK)) return cudaErrorInvalidValue;
+  if (!make_act_map(&tmA, X, B, Min, a_cols > 0 ? a_cols : op.Cin, BK) || !make_weight_map(&tmW, W, op.N, op.K, BN, BK))
+    return cudaErrorInvalidValue;
   if (BK == 64) {
     switch (BN) {
       case 128: return launch_bn<128, 64>(tmA, tmW, op, B, st);

@@ -15,6 +15,7 @@
 
 #include "../../include/sopro_b200.h"
 #include "dense_f32.cuh"
+#include "mimi_tc.cuh"  // tc::launch: the tcgen05 / TMEM / TMA implicit-GEMM kernel, reused for the exact split products
 
 namespace mimi {
 void set_error(const char* msg);  // ar_engine.cu: the string behind sopro_last_error()
@@ -124,6 +125,184 @@ int argmax_parts(int M, int N, int groups) {
   return (N + e - 1) / e;
 }
 
+// =================================================================================================
+// Exact fp32 products on the tensor cores (row counts above the skinny kernel's).  Every fp32 operand is the exact sum
+// of three bf16 terms (h + m + l: 3 x 8 mantissa bits), a product of two bf16 numbers is exact in fp32, so
+//   x . w = sum over the six term pairs whose magnitude reaches fp32's last bit (mm, lh, hl, mh, hm, hh; the pairs ml, lm,
+//   ll are below 2^-26 of the product)
+// accumulated in fp32 in tensor memory: the same quantity the fp32 FMA kernels compute, up to the order of the fp32
+// additions.  One GEMM launch does all six: the weights are stored as W6 [N][6K] (K blocks = the w term of each pair,
+// built once on the host), the activations as A3 [M][3K] = [h | m | l] written by split3_rows_kernel (fused with the
+// RMSNorm of the rows), and the GEMM kernel's "tap" j (mimi_tc.cuh: K block j of W against A columns tap_col[j] + ...)
+// selects the x term.  M = batch x frames rows fill 128-row tiles, which is what the tensor cores need (the AR step's
+// 22..86 rows per CTA do not).
+// =================================================================================================
+constexpr int kPairs = 6;
+constexpr int kPairX[kPairs] = {1, 2, 0, 1, 0, 0};  // x term of pair j (0 = h, 1 = m, 2 = l), smallest products first
+constexpr int kPairW[kPairs] = {1, 0, 2, 0, 1, 0};  // w term of pair j
+
+inline uint16_t bf16_rne(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+inline float bf16_f32(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+// W [N][K] fp32 -> W6 [N][6K] bf16 appended to `dst`; returns the element offset
+size_t pack_w6(std::vector<uint16_t>& dst, const float* W, size_t N, size_t K) {
+  const size_t off = (dst.size() + 63) / 64 * 64;
+  dst.resize(off + N * kPairs * K);
+  for (size_t n = 0; n < N; ++n)
+    for (size_t k = 0; k < K; ++k) {
+      const float w = W[n * K + k];
+      uint16_t t[3];
+      t[0] = bf16_rne(w);
+      const float r1 = w - bf16_f32(t[0]);
+      t[1] = bf16_rne(r1);
+      t[2] = bf16_rne(r1 - bf16_f32(t[1]));
+      for (int j = 0; j < kPairs; ++j) dst[off + (n * kPairs + j) * K + k] = t[kPairW[j]];
+    }
+  return off;
+}
+
+// rows [M][K] fp32 (optionally RMS-normalised, nn/blocks.py:32-37) -> A3 [M][3K] bf16 = [h | m | l], one warp per row
+__global__ void __launch_bounds__(256) split3_rows_kernel(const float* __restrict__ x, const float* __restrict__ norm_w,
+                                                          __nv_bfloat16* __restrict__ out, long long rows, int K) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * K;
+  float inv = 1.f;
+  if (norm_w) {
+    float ss = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 v = *reinterpret_cast<const float4*>(xr + k);
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    inv = 1.0f / sqrtf(ss / (float)K + 1e-6f);
+  }
+  __nv_bfloat16* o = out + row * 3 * K;
+  for (int k = lane * 4; k < K; k += 128) {
+    float4 v = *reinterpret_cast<const float4*>(xr + k);
+    if (norm_w) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(norm_w + k));
+      v.x = (v.x * inv) * w.x;
+      v.y = (v.y * inv) * w.y;
+      v.z = (v.z * inv) * w.z;
+      v.w = (v.w * inv) * w.w;
+    }
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+    const float rx = v.x - __low2float(h0), ry = v.y - __high2float(h0), rz = v.z - __low2float(h1), rw = v.w - __high2float(h1);
+    const __nv_bfloat162 m0 = __floats2bfloat162_rn(rx, ry), m1 = __floats2bfloat162_rn(rz, rw);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(rx - __low2float(m0), ry - __high2float(m0));
+    const __nv_bfloat162 l1 = __floats2bfloat162_rn(rz - __low2float(m1), rw - __high2float(m1));
+    uint2 ph, pm, pl;
+    ph.x = *reinterpret_cast<const unsigned*>(&h0), ph.y = *reinterpret_cast<const unsigned*>(&h1);
+    pm.x = *reinterpret_cast<const unsigned*>(&m0), pm.y = *reinterpret_cast<const unsigned*>(&m1);
+    pl.x = *reinterpret_cast<const unsigned*>(&l0), pl.y = *reinterpret_cast<const unsigned*>(&l1);
+    *reinterpret_cast<uint2*>(o + k) = ph;
+    *reinterpret_cast<uint2*>(o + K + k) = pm;
+    *reinterpret_cast<uint2*>(o + 2 * K + k) = pl;
+  }
+}
+
+// GLU (nn/blocks.py:16-23) on the GEMM's [M][2D] output (bias included): h = value * sigmoid(gate)
+__global__ void __launch_bounds__(256) glu_rows_kernel(const float* __restrict__ v, float* __restrict__ h, long long rows, int D) {
+  const long long i = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+  if (i >= rows * D) return;
+  const long long r = i / D;
+  const int c = (int)(i - r * D);
+  const float4 a = *reinterpret_cast<const float4*>(v + r * 2 * D + c);
+  const float4 g = *reinterpret_cast<const float4*>(v + r * 2 * D + D + c);
+  float4 o;
+  o.x = a.x * dense::sigmoid_ref(g.x);
+  o.y = a.y * dense::sigmoid_ref(g.y);
+  o.z = a.z * dense::sigmoid_ref(g.z);
+  o.w = a.w * dense::sigmoid_ref(g.w);
+  *reinterpret_cast<float4*>(h + i) = o;
+}
+
+// first maximum (torch.argmax) of each head's V logits: one warp per (row, head)
+__global__ void __launch_bounds__(256) argmax_heads_kernel(const float* __restrict__ logits, long long rows, int heads, int V,
+                                                           int* __restrict__ codes, int Q) {
+  const long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (w >= rows * heads) return;
+  const long long r = w / heads;
+  const int hd = (int)(w - r * heads);
+  const float* lg = logits + (r * heads + hd) * V;
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int c = lane * 4; c < V; c += 128) {
+    const float4 q = *reinterpret_cast<const float4*>(lg + c);
+    const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (dense::before(vv[e], c + e, bv, bi)) bv = vv[e], bi = c + e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (dense::before(ov, oi, bv, bi)) bv = ov, bi = oi;
+  }
+  if (lane == 0) codes[r * Q + hd] = bi;
+}
+
+// C [M][N] = epi(A . W^T + bias): A3 [M][3K] bf16 (split3_rows_kernel), W6 [N][6K] bf16 (pack_w6)
+int launch_tc6(const __nv_bfloat16* A3, const uint16_t* W6, const float* bias, const float* R, float* C, long long M, int N, int K, int epi,
+               cudaStream_t st) {
+  tc::TcOp o{};
+  o.bias = bias;
+  o.R = R;
+  o.out_f32 = C;
+  o.c_bs = M * N;
+  o.M = (int)M;
+  o.N = N;
+  o.K = kPairs * K;
+  o.Cin = K;
+  o.dil = 0;
+  o.pad = 0;
+  o.bias_mod = N;
+  o.epi = epi;
+  for (int j = 0; j < kPairs; ++j) o.tap_col[j] = kPairX[j] * K;
+  if (!tc::supported(N, o.K, K)) return fail(SOPRO_ERR_INVALID, "tensor-core NAR GEMM: unsupported shape N=%d K=%d", N, K);
+  const cudaError_t e = tc::launch(A3, M, W6, o, 1, st, 3 * K);
+  if (e != cudaSuccess) return fail(SOPRO_ERR_CUDA, "tensor-core NAR GEMM (N=%d K=%d M=%lld): %s", N, K, M, cudaGetErrorString(e));
+  return SOPRO_OK;
+}
+
+struct BlockTc {
+  size_t glu, w1, w2;  // W6 element offsets
+};
+
+// one SSMLiteBlock with the three contractions on the tensor cores; a3 [M][3*4D] bf16 and v [M][4D] fp32 are scratch
+int ssm_block_tc(const float* W, const BlockOff& o, const uint16_t* T, const BlockTc& t, float* x, float* h, float* v, __nv_bfloat16* a3,
+                 const int* lens, int B, int Tmax, int D, int k, int dil, cudaStream_t st) {
+  const long long M = (long long)B * Tmax;
+  const unsigned rb = (unsigned)((M + 7) / 8);
+  split3_rows_kernel<<<rb, 256, 0, st>>>(x, W + o.norm_w, a3, M, D);
+  int rc = launch_tc6(a3, T + t.glu, W + o.glu_b, nullptr, v, M, 2 * D, D, tc::EPI_NONE, st);
+  if (rc) return rc;
+  glu_rows_kernel<<<(unsigned)((M * D / 4 + 255) / 256), 256, 0, st>>>(v, h, M, D);
+  const int total = (k - 1) * dil;
+  dense::dwconv_res_kernel<<<dim3(Tmax, B), 128, 0, st>>>(h, x, W + o.dw_w, W + o.dw_b, x, lens, Tmax, D, k, dil, total / 2);
+  split3_rows_kernel<<<rb, 256, 0, st>>>(x, W + o.ffn_norm_w, a3, M, D);
+  if ((rc = launch_tc6(a3, T + t.w1, W + o.b1, nullptr, v, M, 4 * D, D, tc::EPI_GELU, st))) return rc;
+  split3_rows_kernel<<<rb, 256, 0, st>>>(v, nullptr, a3, M, 4 * D);
+  if ((rc = launch_tc6(a3, T + t.w2, W + o.b2, x, x, M, D, 4 * D, tc::EPI_RES, st))) return rc;
+  PCK(cudaGetLastError());
+  return SOPRO_OK;
+}
+
 // one SSMLiteBlock (nn/blocks.py:143-148) over rows [B][Tmax][D], in place on x; h [M][D] and hid [M][4D] are scratch
 int ssm_block(const float* W, const BlockOff& o, float* x, float* h, float* hid, const int* lens, int B, int Tmax, int D, int k, int dil,
               bool causal, cudaStream_t st) {
@@ -213,12 +392,19 @@ struct sopro_nar {
     int first, count, n_prev;
     size_t w_prev, mul, add, head_w, head_b, head_id;
     float mix0, mix1;
+    size_t tc_heads = 0, head_b_folded = 0;  // tensor-core path: W6 of the stage's heads; bias + W . id_embedding
   };
+  // tensor-core path (exact six-product split): W6 images of every contraction, bf16
+  uint16_t* tcw = nullptr;
+  BlockTc tblk[SOPRO_MAX_SSM_LAYERS]{};
+  size_t tc_pre = 0;
+  bool tc_ok = false;
   std::vector<Stage> stages;
   // workspace
   float* ws = nullptr;
   size_t ws_bytes = 0;
   const int32_t* forced = nullptr;  // test hook: the previous codebooks every stage conditions on
+  int tc_mode = -1;                 // -1 automatic (tensor cores above the skinny kernel's row count), 0 fp32 FMA kernels only
 };
 
 extern "C" {
@@ -313,15 +499,50 @@ int sopro_nar_create(const sopro_nar_config_t* cfg, const sopro_nar_weights_t* w
       memcpy(A.host.data() + S.head_b + (size_t)j * V, w->head_b[S.first + j], (size_t)V * 4);
     }
     S.head_id = A.add(w->head_id_emb[s], (size_t)S.count * Hn);
+    {  // (z + e_h) . W_h^T + b_h = z . W_h^T + (b_h + W_h e_h): the head's id embedding folded into its bias
+      std::vector<float> fb((size_t)S.count * V);
+      for (int j = 0; j < S.count; ++j) {
+        const float* Wh = w->head_w[S.first + j];
+        const float* e = w->head_id_emb[s] + (size_t)j * Hn;
+        for (int v = 0; v < V; ++v) {
+          double acc = w->head_b[S.first + j][v];
+          for (int c = 0; c < Hn; ++c) acc += (double)Wh[(size_t)v * Hn + c] * (double)e[c];
+          fb[(size_t)j * V + v] = (float)acc;
+        }
+      }
+      S.head_b_folded = A.add(fb.data(), fb.size());
+    }
     n->stages.push_back(S);
+  }
+  // tensor-core images (W6) of every contraction; geometry the implicit-GEMM kernel takes: K blocks of 64, N tiles of 32+
+  std::vector<uint16_t> T;
+  const bool tc_ok = D % 64 == 0 && Hn % 64 == 0 && V % 32 == 0 && (2 * D) % 32 == 0;
+  if (tc_ok) {
+    for (int i = 0; i < NL; ++i) {
+      n->tblk[i].glu = pack_w6(T, w->block[i].glu_w, (size_t)2 * D, D);
+      n->tblk[i].w1 = pack_w6(T, w->block[i].ffn_w1, (size_t)4 * D, D);
+      n->tblk[i].w2 = pack_w6(T, w->block[i].ffn_w2, D, (size_t)4 * D);
+    }
+    n->tc_pre = pack_w6(T, w->pre_w, Hn, D);
+    for (auto& S : n->stages) {
+      std::vector<float> hw((size_t)S.count * V * Hn);
+      for (int j = 0; j < S.count; ++j) memcpy(hw.data() + (size_t)j * V * Hn, w->head_w[S.first + j], (size_t)V * Hn * 4);
+      S.tc_heads = pack_w6(T, hw.data(), (size_t)S.count * V, Hn);
+    }
   }
   n->n_floats = A.host.size();
   cudaError_t err = cudaMalloc(&n->dev, n->n_floats * 4);
   if (err == cudaSuccess) err = cudaMemcpy(n->dev, A.host.data(), n->n_floats * 4, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess && tc_ok) {
+    err = cudaMalloc(&n->tcw, T.size() * 2);
+    if (err == cudaSuccess) err = cudaMemcpy(n->tcw, T.data(), T.size() * 2, cudaMemcpyHostToDevice);
+    n->tc_ok = err == cudaSuccess;
+  }
   if (err != cudaSuccess) {
     if (n->dev) cudaFree(n->dev);
+    if (n->tcw) cudaFree(n->tcw);
     delete n;
-    return fail(SOPRO_ERR_CUDA, "NAR weight upload (%zu MB) failed: %s", (A.host.size() * 4) >> 20, cudaGetErrorString(err));
+    return fail(SOPRO_ERR_CUDA, "NAR weight upload (%zu MB) failed: %s", (A.host.size() * 4 + T.size() * 2) >> 20, cudaGetErrorString(err));
   }
   *out = n;
   return SOPRO_OK;
@@ -331,8 +552,16 @@ int sopro_nar_destroy(sopro_nar_t* n) {
   if (!n) return SOPRO_OK;
   cudaSetDevice(n->device);
   cudaFree(n->dev);
+  cudaFree(n->tcw);
   cudaFree(n->ws);
   delete n;
+  return SOPRO_OK;
+}
+
+int sopro_nar_set_contraction(sopro_nar_t* n, int mode) {
+  if (!n || mode < -1 || mode > 1) return fail(SOPRO_ERR_INVALID, "bad argument");
+  if (mode == 1 && !n->tc_ok) return fail(SOPRO_ERR_INVALID, "this NAR geometry has no tensor-core images");
+  n->tc_mode = mode;
   return SOPRO_OK;
 }
 
@@ -355,10 +584,19 @@ int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_strid
   int max_heads = 1;
   for (const auto& S : n->stages) max_heads = std::max(max_heads, S.count);
   const size_t parts_max = (size_t)std::max(argmax_parts((int)M, V, 1), argmax_parts((int)M, V, max_heads));
+  // Tensor cores (exact six-product split) for every row count the skinny fp32 kernel does not take; SOPRO_NAR_TC=0 keeps
+  // the fp32 FMA tile kernels (the reference for tests/test_nar_gpu.py::test_tensor_core_path_equals_the_fp32_path)
+  static const bool tc_env_off = getenv("SOPRO_NAR_TC") && atoi(getenv("SOPRO_NAR_TC")) == 0;
+  const bool use_tc = n->tc_ok && !tc_env_off && n->tc_mode != 0 && M > dense::kSkinnyRows;
+  // rows per head-logits chunk of the tensor-core path (logits [chunk][heads * V] fp32 reach memory there, <= 256 MB)
+  long long mc = ((256ll << 20) / ((long long)max_heads * V * 4)) / 128 * 128;
+  mc = std::max<long long>(128, std::min<long long>(mc, (M + 127) / 128 * 128));
   const size_t fx = (size_t)M * D, fh = (size_t)M * D, fhid = (size_t)M * 4 * D, fz = (size_t)M * Hn,
-               famax = (size_t)max_heads * M * parts_max;
+               famax = use_tc ? 0 : (size_t)max_heads * M * parts_max;
   auto al = [](size_t x) { return (x + 63) / 64 * 64; };
-  const size_t need = (al(fx) + al(fh) + al(fhid) + al(fz) + 2 * al(famax)) * 4;
+  const size_t fa3 = use_tc ? ((size_t)M * 3 * 4 * D + 1) / 2 : 0;          // bf16 [M][3 * 4D], in floats
+  const size_t flog = use_tc ? (size_t)mc * max_heads * V : 0;
+  const size_t need = (al(fx) + al(fh) + al(fhid) + al(fz) + 2 * al(famax) + al(fa3) + al(flog)) * 4;
   if (n->ws_bytes < need) {
     PCK(cudaStreamSynchronize(st));
     cudaFree(n->ws);
@@ -374,6 +612,8 @@ int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_strid
   float* z = hid + al(fhid);
   float* amax_v = z + al(fz);
   int* amax_i = reinterpret_cast<int*>(amax_v + al(famax));
+  __nv_bfloat16* a3 = reinterpret_cast<__nv_bfloat16*>(amax_v + 2 * al(famax));
+  float* logits = amax_v + 2 * al(famax) + al(fa3);
   const float* W = n->dev;
   set_first_codebook_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(rvq1, codes, M, Q);
   PCK(cudaGetLastError());
@@ -385,6 +625,22 @@ int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_strid
     nar_embed_mix_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(em, M);
     PCK(cudaGetLastError());
     int rc;
+    if (use_tc) {
+      for (int i = 0; i < c.n_layers; ++i)
+        if ((rc = ssm_block_tc(W, n->blk[i], n->tcw, n->tblk[i], x, h, hid, a3, lens, B, Tmax, D, c.kernel, c.dilation[i], st))) return rc;
+      const unsigned rb = (unsigned)((M + 7) / 8);
+      split3_rows_kernel<<<rb, 256, 0, st>>>(x, W + n->norm_w, a3, M, D);
+      if ((rc = launch_tc6(a3, n->tcw + n->tc_pre, W + n->pre_b, nullptr, z, M, Hn, D, tc::EPI_NONE, st))) return rc;
+      split3_rows_kernel<<<rb, 256, 0, st>>>(z, nullptr, a3, M, Hn);
+      for (long long m0 = 0; m0 < M; m0 += mc) {
+        const long long rows = std::min<long long>(mc, M - m0);
+        if ((rc = launch_tc6(a3 + m0 * 3 * Hn, n->tcw + S.tc_heads, W + S.head_b_folded, nullptr, logits, rows, S.count * V, Hn, tc::EPI_NONE, st)))
+          return rc;
+        argmax_heads_kernel<<<(unsigned)((rows * S.count + 7) / 8), 256, 0, st>>>(logits, rows, S.count, V, codes + m0 * Q + S.first, Q);
+      }
+      PCK(cudaGetLastError());
+      continue;
+    }
     for (int i = 0; i < c.n_layers; ++i)
       if ((rc = ssm_block(W, n->blk[i], x, h, hid, lens, B, Tmax, D, c.kernel, c.dilation[i], false, st))) return rc;
     dense::DenseOp g{};

@@ -91,6 +91,10 @@ class NarEngine:
                                              int(B), int(T), out.data_ptr(), int(torch.cuda.current_stream(self.device).cuda_stream)))
         return out.long()
 
+    def set_contraction(self, mode: int) -> None:
+        """-1 automatic (tensor cores with the exact six-product bf16 split above 16 rows), 0 fp32 FMA kernels only."""
+        _lib.check(self.lib.sopro_nar_set_contraction(self._h, int(mode)))
+
     def set_forced(self, forced_btq: Optional[torch.Tensor]) -> None:
         """Test hook: every stage conditions on these codes' previous codebooks (teacher forcing)."""
         self._forced = None if forced_btq is None else forced_btq.to(device=self.device, dtype=torch.int32).contiguous()

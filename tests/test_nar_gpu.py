@@ -127,3 +127,24 @@ def test_nar_strided_conditioning_rows():
     a = eng.refine(full[:, :25], rvq1)
     b = eng.refine(full[:, :25].contiguous(), rvq1)
     assert torch.equal(a, b)
+
+
+def test_tensor_core_path_equals_the_fp32_path():
+    """Above 16 rows the contractions run on tcgen05 with every fp32 operand split into three exact bf16 terms (six
+    products, fp32 accumulation: the fp32 result up to summation order).  Same ids as the fp32 FMA kernels and as the CPU
+    oracle on 4 x 300 frames; a differing id must be an oracle near-tie (the _check rule)."""
+    eng = _engine()
+    cfg, sd, _ = e2e_inputs()
+    B, T = 4, 300
+    cond = _cond(B, T, int(cfg.d_model), 9300)
+    rvq1 = torch.randint(0, 2048, (B, T), generator=torch.Generator().manual_seed(31))
+    eng.set_contraction(0)
+    try:
+        fp32_ids = eng.refine(cond, rvq1).cpu()
+    finally:
+        eng.set_contraction(-1)
+    tc_ids = eng.refine(cond, rvq1).cpu()
+    n_diff = int((fp32_ids != tc_ids).sum())
+    print(f"tensor-core vs fp32 NAR ids: {n_diff} of {tc_ids.numel()} differ")
+    ties = _check(eng, cfg, sd, cond[:2], rvq1[:2])  # tensor-core path (automatic) against the oracle
+    assert n_diff <= 2 + len(ties)
