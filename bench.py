@@ -551,8 +551,9 @@ def main():
         ncu_note = tj.get("ncu")
     W = max(world, 1)
     # launches of OUR kernels inside the timed regions, per rank: resident leg = kv_build + persistent AR per step; API leg per
-    # step = prefill 24 + kv_build 1 + AR 1 + NAR (1 + 4 stages x 28) + Mimi (about 85 per decode call x 3 calls at 12,800 frames)
-    api_launches = 24 + 2 + 113 + 85 * 3
+    # step = prefill 24 + kv_build 1 + AR 6 (the launch resumes once per noise-tape block) + NAR on the tensor cores (1 + 4
+    # stages x 54) + Mimi (about 85 per decode call x 3 calls at 12,800 frames)
+    api_launches = 24 + 7 + 217 + 85 * 3
     line = {
         "metric": "ar_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": W, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_total_ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -374,6 +374,9 @@ int sopro_nar_set_forced(sopro_nar_t* n, const int32_t* forced_codes);
  * refined; the fp32 FMA skinny kernel below that), 0 = fp32 FMA kernels only (also: environment SOPRO_NAR_TC=0), 1 = as -1
  * but fails if the geometry has no tensor-core images. */
 int sopro_nar_set_contraction(sopro_nar_t* n, int mode);
+/* One utterance's streaming windows (B == 1, <= 256 frames, no lens / forced codes) are replayed from CUDA graphs captured
+ * over internal static buffers (a window is 113..217 launches): identical results, launch overhead removed.  Default on. */
+int sopro_nar_set_graphs(sopro_nar_t* n, int enabled);
 
 /* ------------------------------------------------------------------------------------------------
  * Prefill: SoproTTSModel.prepare_conditioning (reference model.py:172-216) for B texts that share one prepared

@@ -158,6 +158,7 @@ SYMBOLS = {
     "sopro_nar_destroy": (_I, [_VP]),
     "sopro_nar_set_forced": (_I, [_VP, _VP]),
     "sopro_nar_set_contraction": (_I, [_VP, _I]),
+    "sopro_nar_set_graphs": (_I, [_VP, _I]),
     "sopro_nar_refine": (_I, [_VP, _VP, C.c_int64, _VP, _VP, _I, _I, _VP, _VP]),
     "sopro_prefill_create": (_I, [_VP, _VP, _I, C.POINTER(_VP)]),
     "sopro_prefill_destroy": (_I, [_VP]),

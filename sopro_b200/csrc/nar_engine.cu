@@ -405,7 +405,27 @@ struct sopro_nar {
   size_t ws_bytes = 0;
   const int32_t* forced = nullptr;  // test hook: the previous codebooks every stage conditions on
   int tc_mode = -1;                 // -1 automatic (tensor cores above the skinny kernel's row count), 0 fp32 FMA kernels only
+  // launch-bound streaming windows (one utterance, <= kNarGraphRows frames: 113..217 launches each) are replayed from
+  // CUDA graphs captured over static buffers; every graph dies when the workspace is reallocated
+  struct Replay {
+    int T, tc;
+    cudaGraphExec_t exec;
+  };
+  std::vector<Replay> replays;
+  float* g_cond = nullptr;
+  int32_t* g_rvq1 = nullptr;
+  int32_t* g_codes = nullptr;
+  bool graphs = true;
+  cudaStream_t cap_stream = nullptr;
+  size_t reserve_bytes = 0;         // workspace floor (so that no graph-sized call reallocates)
 };
+
+constexpr int kNarGraphRows = 256;
+
+static void nar_drop_replays(sopro_nar* n) {
+  for (auto& r : n->replays) cudaGraphExecDestroy(r.exec);
+  n->replays.clear();
+}
 
 extern "C" {
 
@@ -551,6 +571,11 @@ int sopro_nar_create(const sopro_nar_config_t* cfg, const sopro_nar_weights_t* w
 int sopro_nar_destroy(sopro_nar_t* n) {
   if (!n) return SOPRO_OK;
   cudaSetDevice(n->device);
+  nar_drop_replays(n);
+  if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
+  cudaFree(n->g_cond);
+  cudaFree(n->g_rvq1);
+  cudaFree(n->g_codes);
   cudaFree(n->dev);
   cudaFree(n->tcw);
   cudaFree(n->ws);
@@ -571,9 +596,12 @@ int sopro_nar_set_forced(sopro_nar_t* n, const int32_t* forced_codes) {
   return SOPRO_OK;
 }
 
-int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_stride, const int32_t* rvq1, const int32_t* lens, int B,
-                     int Tmax, int32_t* codes, void* stream) {
-  if (!n || !cond || !rvq1 || !codes) return fail(SOPRO_ERR_INVALID, "null argument");
+}  // extern "C"
+
+// the refiner's launches on `st`; reserve_only: size (and grow) the workspace for this shape, launch nothing
+static int nar_refine_impl(sopro_nar_t* n, const float* cond, int64_t cond_batch_stride, const int32_t* rvq1, const int32_t* lens, int B,
+                           int Tmax, int32_t* codes, void* stream, bool reserve_only = false) {
+  if (!n || (!reserve_only && (!cond || !rvq1 || !codes))) return fail(SOPRO_ERR_INVALID, "null argument");
   if (B < 1 || Tmax < 1 || (long long)B * Tmax > 0x3fffffffLL) return fail(SOPRO_ERR_INVALID, "bad B=%d Tmax=%d", B, Tmax);
   const sopro_nar_config_t& c = n->cfg;
   const int D = c.d_model, Q = c.n_codebooks, V = c.codebook_size, Hn = c.head_dim;
@@ -596,15 +624,20 @@ int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_strid
   auto al = [](size_t x) { return (x + 63) / 64 * 64; };
   const size_t fa3 = use_tc ? ((size_t)M * 3 * 4 * D + 1) / 2 : 0;          // bf16 [M][3 * 4D], in floats
   const size_t flog = use_tc ? (size_t)mc * max_heads * V : 0;
-  const size_t need = (al(fx) + al(fh) + al(fhid) + al(fz) + 2 * al(famax) + al(fa3) + al(flog)) * 4;
+  const size_t need = std::max(n->reserve_bytes, (al(fx) + al(fh) + al(fhid) + al(fz) + 2 * al(famax) + al(fa3) + al(flog)) * 4);
   if (n->ws_bytes < need) {
     PCK(cudaStreamSynchronize(st));
+    nar_drop_replays(n);  // the graphs hold pointers into the old workspace
     cudaFree(n->ws);
     n->ws = nullptr;
     n->ws_bytes = 0;
     cudaError_t e = cudaMalloc(&n->ws, need);
     if (e != cudaSuccess) return fail(SOPRO_ERR_CUDA, "NAR workspace %zu MB: %s", need >> 20, cudaGetErrorString(e));
     n->ws_bytes = need;
+  }
+  if (reserve_only) {
+    n->reserve_bytes = std::max(n->reserve_bytes, need);
+    return SOPRO_OK;
   }
   float* x = n->ws;
   float* h = x + al(fx);
@@ -655,6 +688,69 @@ int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_strid
     dense::argmax_finish_kernel<<<dim3((unsigned)((M + 127) / 128), S.count), 128, 0, st>>>(amax_v, amax_i, (int)M, parts, codes + S.first, Q);
     PCK(cudaGetLastError());
   }
+  return SOPRO_OK;
+}
+
+extern "C" {
+
+int sopro_nar_set_graphs(sopro_nar_t* n, int enabled) {
+  if (!n) return fail(SOPRO_ERR_INVALID, "null argument");
+  n->graphs = enabled != 0;
+  return SOPRO_OK;
+}
+
+int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_stride, const int32_t* rvq1, const int32_t* lens, int B,
+                     int Tmax, int32_t* codes, void* stream) {
+  if (!n || !cond || !rvq1 || !codes) return fail(SOPRO_ERR_INVALID, "null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  PCK(cudaSetDevice(n->device));
+  PCK(cudaStreamIsCapturing(st, &cap));
+  // one utterance's streaming window: replay the whole pass (113..217 launches) from a graph over static buffers
+  if (!n->graphs || B != 1 || Tmax < 1 || Tmax > kNarGraphRows || lens || n->forced || cap != cudaStreamCaptureStatusNone)
+    return nar_refine_impl(n, cond, cond_batch_stride, rvq1, lens, B, Tmax, codes, stream);
+  const sopro_nar_config_t& c = n->cfg;
+  const int D = c.d_model, Q = c.n_codebooks;
+  if (!n->g_cond) {
+    PCK(cudaMalloc(&n->g_cond, (size_t)kNarGraphRows * D * 4));
+    PCK(cudaMalloc(&n->g_rvq1, (size_t)kNarGraphRows * 4));
+    PCK(cudaMalloc(&n->g_codes, (size_t)kNarGraphRows * Q * 4));
+  }
+  // no graph-sized call may reallocate the workspace: reserve the largest graph shape of either arithmetic path once
+  if (n->reserve_bytes == 0) {
+    int rc = nar_refine_impl(n, nullptr, (int64_t)kNarGraphRows * D, nullptr, nullptr, 1, kNarGraphRows, nullptr, stream, true);
+    if (!rc) rc = nar_refine_impl(n, nullptr, (int64_t)dense::kSkinnyRows * D, nullptr, nullptr, 1, dense::kSkinnyRows, nullptr, stream, true);
+    if (rc) return rc;
+  }
+  const int tc = n->tc_mode;
+  cudaGraphExec_t exec = nullptr;
+  for (auto& r : n->replays)
+    if (r.T == Tmax && r.tc == tc) exec = r.exec;
+  if (!exec) {
+    if (n->replays.size() >= 96) nar_drop_replays(n);
+    // warm-up outside the capture (first use of a kernel sets function attributes), then capture on a private stream
+    int rc = nar_refine_impl(n, cond, cond_batch_stride, rvq1, nullptr, 1, Tmax, codes, stream);
+    if (rc) return rc;
+    if (!n->cap_stream) PCK(cudaStreamCreateWithFlags(&n->cap_stream, cudaStreamNonBlocking));
+    PCK(cudaStreamBeginCapture(n->cap_stream, cudaStreamCaptureModeThreadLocal));
+    rc = nar_refine_impl(n, n->g_cond, (int64_t)Tmax * D, n->g_rvq1, nullptr, 1, Tmax, n->g_codes, n->cap_stream);
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamEndCapture(n->cap_stream, &graph);
+    if (rc || ce != cudaSuccess) {  // this call already ran eagerly; just do not cache
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      return SOPRO_OK;
+    }
+    ce = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce == cudaSuccess) n->replays.push_back({Tmax, tc, exec});
+    else cudaGetLastError();
+    return SOPRO_OK;  // the eager warm-up produced this call's result
+  }
+  PCK(cudaMemcpyAsync(n->g_cond, cond, (size_t)Tmax * D * 4, cudaMemcpyDeviceToDevice, st));
+  PCK(cudaMemcpyAsync(n->g_rvq1, rvq1, (size_t)Tmax * 4, cudaMemcpyDeviceToDevice, st));
+  PCK(cudaGraphLaunch(exec, st));
+  PCK(cudaMemcpyAsync(codes, n->g_codes, (size_t)Tmax * Q * 4, cudaMemcpyDeviceToDevice, st));
   return SOPRO_OK;
 }
 

@@ -95,6 +95,10 @@ class NarEngine:
         """-1 automatic (tensor cores with the exact six-product bf16 split above 16 rows), 0 fp32 FMA kernels only."""
         _lib.check(self.lib.sopro_nar_set_contraction(self._h, int(mode)))
 
+    def set_graphs(self, enabled: bool) -> None:
+        """CUDA-graph replay of single-utterance windows of <= 256 frames (default on; identical results)."""
+        _lib.check(self.lib.sopro_nar_set_graphs(self._h, 1 if enabled else 0))
+
     def set_forced(self, forced_btq: Optional[torch.Tensor]) -> None:
         """Test hook: every stage conditions on these codes' previous codebooks (teacher forcing)."""
         self._forced = None if forced_btq is None else forced_btq.to(device=self.device, dtype=torch.int32).contiguous()

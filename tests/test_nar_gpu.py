@@ -148,3 +148,25 @@ def test_tensor_core_path_equals_the_fp32_path():
     print(f"tensor-core vs fp32 NAR ids: {n_diff} of {tc_ids.numel()} differ")
     ties = _check(eng, cfg, sd, cond[:2], rvq1[:2])  # tensor-core path (automatic) against the oracle
     assert n_diff <= 2 + len(ties)
+
+
+@pytest.mark.parametrize("T", [6, 17, 187])
+def test_streaming_windows_replay_from_graphs_identically(T):
+    """Single-utterance windows are captured into a CUDA graph on first use and replayed afterwards (skinny fp32 path at 6
+    frames, tensor-core path above 16): first call (eager + capture), replays and the plain launches give the same ids,
+    also for a different window of the same length and for a strided conditioning slice."""
+    eng = _engine()
+    cfg, sd, _ = e2e_inputs()
+    D = int(cfg.d_model)
+    full = _cond(1, T + 9, D, 9700 + T).to("cuda:0")
+    rv = torch.randint(0, 2048, (1, T + 9), generator=torch.Generator().manual_seed(T))
+    eng.set_graphs(False)
+    try:
+        plain_a = eng.refine(full[:, :T], rv[:, :T]).cpu()
+        plain_b = eng.refine(full[:, 9:T + 9], rv[:, 9:T + 9]).cpu()
+    finally:
+        eng.set_graphs(True)
+    first = eng.refine(full[:, :T], rv[:, :T]).cpu()        # eager + capture
+    replay_a = eng.refine(full[:, :T], rv[:, :T]).cpu()     # replay
+    replay_b = eng.refine(full[:, 9:T + 9], rv[:, 9:T + 9]).cpu()
+    assert torch.equal(first, plain_a) and torch.equal(replay_a, plain_a) and torch.equal(replay_b, plain_b)
