@@ -827,7 +827,11 @@ static int launch_ar(sopro_ar_session* s, int t_begin, int t_end, cudaStream_t s
   if (g > e->n_sms) return fail(SOPRO_ERR_INVALID, "batch %d needs %d teams > %d SMs", s->B, g, e->n_sms);
   Bt = (s->B + g - 1) / g;  // balance
   g = (s->B + Bt - 1) / Bt;
-  const int P = e->n_sms / g;
+  int P = e->n_sms / g;
+  if (const char* env = getenv("SOPRO_AR_MAX_P")) {  // experiment knob: fewer CTAs per team (larger slices, fewer exchange partners)
+    const int cap = atoi(env);
+    if (cap >= 1) P = std::min(P, cap);
+  }
   p.g = g;
   p.P = P;
   p.Bt = Bt;

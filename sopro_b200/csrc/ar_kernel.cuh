@@ -1526,7 +1526,7 @@ __global__ void __launch_bounds__(kThreads, 1) ar_persistent_kernel(const __grid
   __shared__ unsigned tmem_slot;
   __shared__ float tc_part[TC ? 8 * 32 : 1];  // tensor-core stage-in: per-row partial sums of squares
   constexpr int EL = LL ? 2 : 1;  // floats per activation element in the exchange buffers
-  constexpr bool kTcBuild = TC;  // the tcgen05 instantiations (bf16 weights, TU == 8) carry no FFMA2 tile loop and vice versa
+  // the tcgen05 instantiations (TC: bf16 weights, TU == 8) carry no FFMA2 tile loop and vice versa
   static_assert(!TC || (TU == 8 && sizeof(WT) == 2), "tensor-core path: bf16 weights, 8-utterance B operand");
   // dynamic shared memory, 1024-byte aligned (the swizzled tensor-core operands need it): p.act_off / ring_off / table_off
   unsigned char* const smem_base = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);

@@ -417,6 +417,7 @@ struct sopro_nar {
   int32_t* g_codes = nullptr;
   bool graphs = true;
   cudaStream_t cap_stream = nullptr;
+  cudaEvent_t g_done = nullptr;     // last replay's completion: the static buffers are reused across caller streams
   size_t reserve_bytes = 0;         // workspace floor (so that no graph-sized call reallocates)
 };
 
@@ -573,6 +574,7 @@ int sopro_nar_destroy(sopro_nar_t* n) {
   cudaSetDevice(n->device);
   nar_drop_replays(n);
   if (n->cap_stream) cudaStreamDestroy(n->cap_stream);
+  if (n->g_done) cudaEventDestroy(n->g_done);
   cudaFree(n->g_cond);
   cudaFree(n->g_rvq1);
   cudaFree(n->g_codes);
@@ -747,10 +749,14 @@ int sopro_nar_refine(sopro_nar_t* n, const float* cond, int64_t cond_batch_strid
     else cudaGetLastError();
     return SOPRO_OK;  // the eager warm-up produced this call's result
   }
+  // replays from different caller streams share the static buffers: each waits for the previous one to finish
+  if (!n->g_done) PCK(cudaEventCreateWithFlags(&n->g_done, cudaEventDisableTiming));
+  else PCK(cudaStreamWaitEvent(st, n->g_done, 0));
   PCK(cudaMemcpyAsync(n->g_cond, cond, (size_t)Tmax * D * 4, cudaMemcpyDeviceToDevice, st));
   PCK(cudaMemcpyAsync(n->g_rvq1, rvq1, (size_t)Tmax * 4, cudaMemcpyDeviceToDevice, st));
   PCK(cudaGraphLaunch(exec, st));
   PCK(cudaMemcpyAsync(codes, n->g_codes, (size_t)Tmax * Q * 4, cudaMemcpyDeviceToDevice, st));
+  PCK(cudaEventRecord(n->g_done, st));
   return SOPRO_OK;
 }
 
