@@ -99,11 +99,14 @@ class MimiEngine:
         """CUDA-graph replay of small (<= 64 frame) decodes inside the library; on by default."""
         _lib.check(self.lib.sopro_mimi_set_graphs(self._h, 1 if enabled else 0))
 
-    def _validated(self, codes: torch.Tensor) -> torch.Tensor:
+    def _validated(self, codes: torch.Tensor, trusted: bool = False) -> torch.Tensor:
         """int32 codes on the device; like the reference's embedding lookup, a code outside [0, 2048) is an IndexError
-        (an uncut EOS id would otherwise read past the codebook; the kernel itself clamps and flags)."""
+        (an uncut EOS id would otherwise read past the codebook; the kernel itself clamps and flags).  `trusted`: codes
+        this process produced itself (the NAR refiner's argmax over 2048 logits, clamped first codebook) skip the host
+        check -- it is a device synchronisation in the middle of the streaming pipeline -- and rely on the device-side
+        flag (``check()``)."""
         codes = codes.to(device=self.device, dtype=torch.int32).contiguous()
-        if codes.numel():
+        if codes.numel() and not trusted:
             lo, hi = torch.aminmax(codes)
             lo, hi = int(lo), int(hi)
             if lo < 0 or hi >= 2048:
@@ -167,8 +170,8 @@ class MimiStream:
     def reset(self) -> None:
         _lib.check(self.lib.sopro_mimi_stream_reset(self._h, int(torch.cuda.current_stream(self.engine.device).cuda_stream)))
 
-    def step(self, codes_qn: torch.Tensor) -> torch.Tensor:
-        codes = self.engine._validated(codes_qn)
+    def step(self, codes_qn: torch.Tensor, trusted: bool = False) -> torch.Tensor:
+        codes = self.engine._validated(codes_qn, trusted)
         Q, n = codes.shape
         if Q != self.engine.num_quantizers:
             raise ValueError(f"expected {self.engine.num_quantizers} codebooks, got {Q}")
@@ -289,7 +292,7 @@ class MimiStreamDecoder:
 
     @torch.inference_mode()
     def decode_step(self, codes_chunk_tq: torch.Tensor, state: Optional[MimiDecodeState] = None, *,
-                    overlap_frames: int = 2) -> Tuple[torch.Tensor, MimiDecodeState]:
+                    overlap_frames: int = 2, _trusted: bool = False) -> Tuple[torch.Tensor, MimiDecodeState]:
         if state is None:
             state = MimiDecodeState()
         n_new = int(codes_chunk_tq.size(0))
@@ -298,7 +301,7 @@ class MimiStreamDecoder:
         if state.decoder_past_key_values is None:
             state.decoder_past_key_values = self.codec.engine.stream(self.max_chunk_frames)
         chunk = codes_chunk_tq.to(self.codec.device)
-        wav_new = state.decoder_past_key_values.step(chunk.permute(1, 0))
+        wav_new = state.decoder_past_key_values.step(chunk.permute(1, 0), _trusted)
         state.frames_seen += n_new
         state.samples_emitted += int(wav_new.size(1))
         state.tail_codes_tq = chunk[-max(int(overlap_frames), 0):].detach() if overlap_frames > 0 else None

@@ -331,13 +331,19 @@ class SoproModel:
             lo = noise.drawn
             blk = noise.rows_keep(st["launched"] + per, nk)
             if blk.size(0):
-                tape[0, lo: lo + blk.size(0)].copy_(blk)
+                n_new = int(blk.size(0))
+                if stage is not None:  # pinned staging rows: the upload is asynchronous, ordered before the launch on this stream
+                    stage[lo: lo + n_new].copy_(blk)
+                    tape[0, lo: lo + n_new].copy_(stage[lo: lo + n_new], non_blocking=True)
+                else:
+                    tape[0, lo: lo + n_new].copy_(blk)
             ses.run(per)
             st["launched"] = min(steps, st["launched"] + per)
 
         try:
             # the session keeps a pointer to this device tape; each launch's rows are drawn and uploaded just before it
             tape = torch.zeros(1, steps, nk, device=self.device)
+            stage = torch.empty(steps, nk, pin_memory=True) if self.device.type == "cuda" else None
             ses.begin(cond[:, :steps], txt, [L], tape, samp)
             t = 0
             while t < steps:

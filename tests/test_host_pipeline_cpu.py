@@ -127,7 +127,10 @@ class _FakeMimiStream:
     def __init__(self, eng):
         self.eng, self.hist = eng, None
 
-    def step(self, codes_qn):
+    def reset(self):  # a pooled state handed to the next utterance (MimiStream.reset)
+        self.hist = None
+
+    def step(self, codes_qn, trusted=False):
         self.hist = codes_qn if self.hist is None else torch.cat([self.hist, codes_qn], dim=1)
         wav = self.eng.decode(self.hist.unsqueeze(0)).reshape(1, -1)
         return wav[:, (self.hist.shape[1] - codes_qn.shape[1]) * 1920:]
