@@ -194,6 +194,11 @@ int sopro_ar_debug_sampled(sopro_ar_session_t* s, int32_t* dst, void* stream);
 /* copy the text K/V built by sopro_ar_begin into k_dst / v_dst, each
  * [n_attn_layers, batch, H, Lpad, Dh] f32 (device), Lpad = max_text_len rounded up to 4 */
 int sopro_ar_debug_kv(sopro_ar_session_t* s, float* k_dst, float* v_dst, void* stream);
+/* Host-only views of the operand images the engines build (no device needed): the tensor-core image of an AR step matrix
+ * W [N][K] ([K / D slices][groups of 8 rows][D / 64 chunks][8 x 128 B, 16-byte units XOR row]; glu: group = 4 channels, value
+ * rows then gate rows) and the NAR refiner's W6 [N][6K] (bf16 terms of the six product pairs mm, lh, hl, mh, hm, hh). */
+int sopro_debug_pack_umma(const float* W, int N, int K, int d_model, int glu, uint8_t* out, int64_t bytes);
+int sopro_debug_pack_w6(const float* W, int N, int K, uint16_t* out);
 /* The kernel's sampler (sample_token, sampling.py:24-93) on ONE logits row, outside the step: HOST buffers; `hist` = the
  * n_hist tokens generated so far (repetition penalty looks at the last 50), `noise` = the Exp(1) draws of this step (first
  * noise_k columns of the tape row: >= top_k when top_p < 1, vocab otherwise), `recovery` != 0 samples with the recovery

@@ -139,6 +139,8 @@ SYMBOLS = {
     "sopro_noise_create": (_I, [C.c_uint64, _VP]),
     "sopro_noise_rows": (_I, [_VP, _I, _I, _I, _VP]),
     "sopro_noise_destroy": (_I, [_VP]),
+    "sopro_debug_pack_umma": (_I, [_VP, _I, _I, _I, _I, _VP, C.c_int64]),
+    "sopro_debug_pack_w6": (_I, [_VP, _I, _I, _VP]),
     "sopro_debug_sample": (_I, [_VP, _I, _VP, _I, _VP, _I, _VP, _I, _I, _VP]),
     "sopro_mimi_create": (_I, [C.POINTER(MimiConfigC), C.POINTER(MimiWeights), _I, C.POINTER(_VP)]),
     "sopro_mimi_destroy": (_I, [_VP]),

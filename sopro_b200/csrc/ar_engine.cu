@@ -468,6 +468,18 @@ int sopro_ar_session_set_team(sopro_ar_session_t* s, int utts_per_team) {
   return SOPRO_OK;
 }
 
+// test hook (host only): the tensor-core operand image of W [N][K] (see Arena::add_packed) -> out, `bytes` = its size
+int sopro_debug_pack_umma(const float* W, int N, int K, int D, int glu, uint8_t* out, int64_t bytes) {
+  if (!W || !out || N < 1 || K < 1 || D < 64 || D % 64 || K % D) return fail(SOPRO_ERR_INVALID, "bad argument");
+  Arena A;
+  int G = 0;
+  const size_t off = A.add_packed(W, N, K, D, glu != 0, &G);
+  const size_t need = (size_t)(K / D) * G * (D / 64) * 1024;
+  if ((int64_t)need != bytes) return fail(SOPRO_ERR_INVALID, "image is %zu bytes, caller expects %lld", need, (long long)bytes);
+  memcpy(out, A.host.data() + off, need);
+  return SOPRO_OK;
+}
+
 int sopro_ar_session_set_contraction(sopro_ar_session_t* s, int mode) {
   if (!s) return fail(SOPRO_ERR_INVALID, "null session");
   if (mode < -1 || mode > 1) return fail(SOPRO_ERR_INVALID, "contraction mode must be -1, 0 or 1");

@@ -585,6 +585,15 @@ int sopro_nar_destroy(sopro_nar_t* n) {
   return SOPRO_OK;
 }
 
+// test hook (host only): the W6 image pack_w6 builds for W [N][K] -> out [N][6K] bf16 bit patterns
+int sopro_debug_pack_w6(const float* W, int N, int K, uint16_t* out) {
+  if (!W || !out || N < 1 || K < 1) return fail(SOPRO_ERR_INVALID, "bad argument");
+  std::vector<uint16_t> T;
+  const size_t off = pack_w6(T, W, (size_t)N, (size_t)K);
+  memcpy(out, T.data() + off, (size_t)N * kPairs * K * 2);
+  return SOPRO_OK;
+}
+
 int sopro_nar_set_contraction(sopro_nar_t* n, int mode) {
   if (!n || mode < -1 || mode > 1) return fail(SOPRO_ERR_INVALID, "bad argument");
   if (mode == 1 && !n->tc_ok) return fail(SOPRO_ERR_INVALID, "this NAR geometry has no tensor-core images");
