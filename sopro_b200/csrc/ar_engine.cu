@@ -162,6 +162,11 @@ struct sopro_ar_session {
   int timing_step = -1;
   bool begun = false;
   std::vector<UttState> host_st;
+  // pinned staging of begin()'s small uploads (text lengths, sampler parameters, initial states): the copies are asynchronous
+  // and begin() does not wait for the stream (it used to synchronise because the sources were pageable vectors)
+  unsigned char* pin = nullptr;
+  size_t pin_bytes = 0;
+  cudaEvent_t pin_done = nullptr;  // last begin()'s uploads have left the staging buffer
 };
 
 extern "C" {
@@ -395,6 +400,8 @@ static void session_free(sopro_ar_session* s) {
   cudaFree(s->tiles);
   cudaFree(s->n_tiles);
   cudaFree(s->stage_tiles);
+  if (s->pin) cudaFreeHost(s->pin);
+  if (s->pin_done) cudaEventDestroy(s->pin_done);
   cudaFree(s->h_cond);
   cudaFree(s->h_txt);
   cudaFree(s->h_noise);
@@ -565,11 +572,27 @@ int sopro_ar_begin(sopro_ar_session_t* s, int batch, int steps, const float* con
   s->noise = noise;
   s->t_pos = 0;
   s->host_st.assign(batch, UttState{0, -1, 0, 0, 0, {0, 0, 0}});
-  CK(cudaMemcpyAsync(s->text_len, lens.data(), (size_t)batch * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s->samp, sd.data(), (size_t)batch * sizeof(SamplingDev), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(s->st, s->host_st.data(), (size_t)batch * sizeof(UttState), cudaMemcpyHostToDevice, st));
-  // the pageable host vectors above die at return: make the copies complete first
-  CK(cudaStreamSynchronize(st));
+  {
+    const size_t b_len = align_up((size_t)batch * 4, 64), b_samp = align_up((size_t)batch * sizeof(SamplingDev), 64),
+                 b_st = (size_t)batch * sizeof(UttState);
+    if (s->pin_bytes < b_len + b_samp + b_st) {
+      if (s->pin_done) CK(cudaEventSynchronize(s->pin_done));
+      if (s->pin) cudaFreeHost(s->pin);
+      s->pin = nullptr;
+      s->pin_bytes = 0;
+      CK(cudaMallocHost(reinterpret_cast<void**>(&s->pin), b_len + b_samp + b_st));
+      s->pin_bytes = b_len + b_samp + b_st;
+    }
+    if (!s->pin_done) CK(cudaEventCreateWithFlags(&s->pin_done, cudaEventDisableTiming));
+    else CK(cudaEventSynchronize(s->pin_done));  // the previous begin()'s copies have read the staging buffer (normally long ago)
+    memcpy(s->pin, lens.data(), (size_t)batch * 4);
+    memcpy(s->pin + b_len, sd.data(), (size_t)batch * sizeof(SamplingDev));
+    memcpy(s->pin + b_len + b_samp, s->host_st.data(), b_st);
+    CK(cudaMemcpyAsync(s->text_len, s->pin, (size_t)batch * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->samp, s->pin + b_len, (size_t)batch * sizeof(SamplingDev), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(s->st, s->pin + b_len + b_samp, b_st, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(s->pin_done, st));
+  }
   CK(cudaMemsetAsync(s->ring, 0, (size_t)e->ring_floats_per_utt * batch * 4, st));
   CK(cudaMemsetAsync(s->tokens, 0, (size_t)batch * steps * 4, st));
   CK(cudaMemsetAsync(s->sampled, 0, (size_t)batch * steps * 4, st));
