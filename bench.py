@@ -338,6 +338,8 @@ def extras(tts, ref, cfg, dev, peaks):
         if i >= 2:
             ts.append(t1 - t0)
     out["ttfa_ms_p50"] = float(np.median(ts)) * 1e3
+    out["ttfa_ms_min"] = float(np.min(ts)) * 1e3  # p50 moves with the box's power state (sw_power_cap boxes: +1.5 ms); the floor does not
+    out["ttfa_ms_p90"] = float(np.percentile(ts, 90)) * 1e3
     out["ttfa_first_chunk_samples"] = int(c.numel())
     # RTF: whole synthesize() (tokenize + prefill + AR + NAR + Mimi) / audio seconds
     t, wav = timed(lambda: tts.synthesize(text, ref=ref, max_frames=FRAMES, seed=1, min_gen_frames=10 ** 9), 3, warm=1)
