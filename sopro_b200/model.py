@@ -115,7 +115,7 @@ class _Noise:
         self.marks: List[Tuple[int, torch.Tensor]] = []  # (first row of a block, generator state before it)
         self.drawn = 0
         self._native = None  # private generators: the library's host-side mt19937 (bit-equal to torch, skips unread draws)
-        if seed is not None and _native_noise_ok():
+        if seed is not None and int(seed) >= 0 and _native_noise_ok():  # (negative seeds: torch's own remapping, torch's path)
             import ctypes as C
 
             from . import _lib
