@@ -312,6 +312,45 @@ int64_t sopro_mimi_stream_frames(const sopro_mimi_stream_t* s);        /* MimiDe
 int sopro_mimi_decode_step(sopro_mimi_stream_t* s, const int32_t* codes, int n, float* wav, void* stream);
 int sopro_mimi_decode_step_host(sopro_mimi_stream_t* s, const int32_t* codes_host, int n, float* wav_host, void* stream);
 
+/* ---- Mimi ENCODE (waveform -> codes): MimiCodec.encode_file's model call (reference codec/mimi.py:41-63 ->
+ * MimiModel.encode, modeling_mimi.py:1455-1488, 1522-1611), once per reference voice.  SEANet encoder (:454-497:
+ * conv k7, 4 x [ResnetBlock, ELU, strided conv kernel 2r stride r] with r = reversed(ratios), ELU, conv k3), the
+ * encoder transformer (same layer as the decoder's), the 25 -> 12.5 Hz conv (kernel 4, stride 2, replicate padding,
+ * :1419-1429) and the split residual vector quantizer's nearest-neighbour search (:1262-1280, :1311-1338).  fp32
+ * throughout (the codes are an argmin): batch 1, any sample count >= 1; every strided conv pads its input on the right
+ * to a full window (MimiConv1d._get_extra_padding_for_conv1d, :273-285), so T = ceil(ceil(..ceil(n/4)../8)/2).
+ * HOST fp32 pointers in state_dict layouts; `cfg` is the decoder's sopro_mimi_config_t. */
+typedef struct sopro_mimi_enc_stage_weights {
+  const float *res1_w, *res1_b;   /* encoder.layers.{1+3s}.block.1.conv [C/2, C, 3], [C/2]   (C = 64 << s) */
+  const float *res2_w, *res2_b;   /* encoder.layers.{1+3s}.block.3.conv [C, C/2, 1], [C] */
+  const float *down_w, *down_b;   /* encoder.layers.{3+3s}.conv [2C, C, 2r], [2C],  r = ratios[n_ratios-1-s] */
+} sopro_mimi_enc_stage_weights_t;
+
+typedef struct sopro_mimi_encoder_weights {
+  const float *conv0_w, *conv0_b;                    /* encoder.layers.0.conv [F, 1, 7], [F] */
+  sopro_mimi_enc_stage_weights_t stage[SOPRO_MIMI_MAX_RATIOS];
+  const float *last_w, *last_b;                      /* encoder.layers.14.conv [hidden, 16F, 3], [hidden] */
+  sopro_mimi_layer_weights_t layer[SOPRO_MIMI_MAX_LAYERS]; /* encoder_transformer.layers.* */
+  const float* downsample_w;                         /* downsample.conv.weight [hidden, hidden, 4], no bias */
+  const float* sem_in_proj;                          /* quantizer.semantic_...input_proj.weight [Dc, hidden] */
+  const float* ac_in_proj;                           /* quantizer.acoustic_...input_proj.weight [Dc, hidden] */
+  const float* embed;                                /* [n_q, vocab, Dc] as in sopro_mimi_weights_t */
+} sopro_mimi_encoder_weights_t;
+
+typedef struct sopro_mimi_encoder sopro_mimi_encoder_t;
+int sopro_mimi_encoder_create(const sopro_mimi_config_t* cfg, const sopro_mimi_encoder_weights_t* host_weights, int device,
+                              sopro_mimi_encoder_t** out);
+int sopro_mimi_encoder_destroy(sopro_mimi_encoder_t* e);
+/* MimiModel.get_encoded_length (:1490-1503): frames produced for n_samples input samples; < 0 on bad arguments */
+int64_t sopro_mimi_encoded_frames(const sopro_mimi_encoder_t* e, int64_t n_samples);
+/* wav [n_samples] f32 @24 kHz (device) -> codes [n_q, T] i32 (device), T = sopro_mimi_encoded_frames(n_samples).
+ * `latent` (optional, device [T, hidden] f32) receives the pre-quantizer embeddings (tests compare them with the
+ * oracle's; the codes are their nearest neighbours). */
+int sopro_mimi_encode(sopro_mimi_encoder_t* e, const float* wav, int64_t n_samples, int32_t* codes, float* latent, void* stream);
+/* same with HOST buffers; synchronises the stream */
+int sopro_mimi_encode_host(sopro_mimi_encoder_t* e, const float* wav_host, int64_t n_samples, int32_t* codes_host,
+                           float* latent_host, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * NAR refiner: SoproTTSModel.nar_refine (reference model.py:307-347) over NARSinglePass.forward_stage
  * (nn/nar.py:89-116), NARStageAdapter (nn/nar.py:13-32), SSMLiteBlock.forward (nn/blocks.py:143-148) and

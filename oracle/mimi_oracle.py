@@ -1,4 +1,4 @@
-"""CPU oracle for the Mimi codec DECODE path.  TEST INFRASTRUCTURE ONLY (see oracle/ar_oracle.py).
+"""CPU oracle for the Mimi codec: the DECODE path and (further down) the ENCODE path.  TEST INFRASTRUCTURE ONLY (see oracle/ar_oracle.py).
 
 The arithmetic of this path does not live in /root/reference: the reference calls
 ``transformers.MimiModel.decode`` (reference codec/mimi.py:65-72, 152-156; dependency
@@ -64,7 +64,8 @@ def rope(q: Tensor, k: Tensor, theta: float = 10000.0):
     return q * cos + rot(q) * sin, k * cos + rot(k) * sin
 
 
-def transformer(sd: SD, x: Tensor, n_layers: int = 8, n_heads: int = 8, window: int = 250, eps: float = 1e-5) -> Tensor:
+def transformer(sd: SD, x: Tensor, n_layers: int = 8, n_heads: int = 8, window: int = 250, eps: float = 1e-5,
+                prefix: str = "decoder_transformer") -> Tensor:
     """MimiTransformerModel (:1001-1140) / MimiTransformerLayer.forward (:966-993) /
     MimiAttention.forward (:681-738): pre-LayerNorm, RoPE, causal sliding-window softmax in fp32,
     LayerScale on both residual branches, GELU(erf) MLP."""
@@ -74,7 +75,7 @@ def transformer(sd: SD, x: Tensor, n_layers: int = 8, n_heads: int = 8, window: 
     allowed = (i[None, :] <= i[:, None]) & (i[:, None] - i[None, :] < window)
     bias = torch.zeros(T, T).masked_fill(~allowed, float("-inf"))
     for l in range(n_layers):
-        p = f"decoder_transformer.layers.{l}."
+        p = f"{prefix}.layers.{l}."
         h = F.layer_norm(x, (C,), sd[p + "input_layernorm.weight"], sd[p + "input_layernorm.bias"], eps)
         sp = lambda t: t.view(B, T, n_heads, Dh).transpose(1, 2)  # noqa: E731
         q, k, v = (sp(F.linear(h, sd[p + f"self_attn.{n}_proj.weight"])) for n in ("q", "k", "v"))
@@ -125,7 +126,76 @@ def mimi_decode(sd: SD, codes_bqt: Tensor) -> Tensor:
     return seanet_decoder(sd, x).transpose(1, 2)
 
 
-from sopro_b200.weights import synth_mimi_state_dict  # noqa: E402,F401  (seeded random decode-path weights)
+from sopro_b200.weights import synth_mimi_encoder_state_dict, synth_mimi_state_dict  # noqa: E402,F401  (seeded random weights)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ENCODE path (waveform -> codes): what the reference runs once per reference voice, ``MimiCodec.encode_file`` ->
+# ``MimiModel.encode`` (reference codec/mimi.py:41-63; modeling_mimi.py:1455-1488, 1522-1611).  Pinned against the
+# installed MimiModel.encode by tests/test_mimi_oracle.py.
+# ---------------------------------------------------------------------------------------------------------------
+def conv1d_mimi(x_btc: Tensor, w: Tensor, b, stride: int = 1, dilation: int = 1, pad_mode: str = "constant") -> Tensor:
+    """MimiConv1d.forward (:331-351), causal: left pad (k_eff - stride), right pad the "extra padding" that makes the
+    last window full (:273-285), mode "constant" (zeros) or "replicate"."""
+    k_eff = (w.size(-1) - 1) * dilation + 1
+    pad_total = k_eff - stride
+    L = x_btc.size(1)
+    n_frames = math.ceil((L - k_eff + pad_total) / stride + 1) - 1
+    extra = n_frames * stride + k_eff - pad_total - L
+    xt = F.pad(x_btc.transpose(1, 2), (pad_total, extra), mode=pad_mode)
+    return F.conv1d(xt, w, b, stride=stride, dilation=dilation).transpose(1, 2)
+
+
+def encoded_frames(n_samples: int) -> int:
+    """MimiModel.get_encoded_length (:1490-1503): every strided conv rounds up."""
+    n = int(n_samples)
+    for r in reversed(UPSAMPLING_RATIOS):
+        n = -(-n // r)
+    return -(-n // 2)
+
+
+def seanet_encoder(sd: SD, x_bt1: Tensor) -> Tensor:
+    """MimiEncoder (:454-497): conv k7 -> 4 x [ResnetBlock, ELU, conv(kernel 2r, stride r, C -> 2C)] (r = 4,5,6,8)
+    -> ELU -> conv k3 -> [B, T', 512]."""
+    x = conv1d_mimi(x_bt1, sd["encoder.layers.0.conv.weight"], sd["encoder.layers.0.conv.bias"])
+    li = 1
+    for r in reversed(UPSAMPLING_RATIOS):
+        p = f"encoder.layers.{li}.block."
+        h = conv1d_mimi(F.elu(x), sd[p + "1.conv.weight"], sd[p + "1.conv.bias"])
+        h = conv1d_mimi(F.elu(h), sd[p + "3.conv.weight"], sd[p + "3.conv.bias"])
+        x = x + h
+        x = conv1d_mimi(F.elu(x), sd[f"encoder.layers.{li + 2}.conv.weight"], sd[f"encoder.layers.{li + 2}.conv.bias"], stride=r)
+        li += 3
+    return conv1d_mimi(F.elu(x), sd[f"encoder.layers.{li + 1}.conv.weight"], sd[f"encoder.layers.{li + 1}.conv.bias"])
+
+
+def mimi_encode_latent(sd: SD, wav_b1n: Tensor) -> Tensor:
+    """MimiModel._encode_frame up to the quantizer (:1469-1484): SEANet encoder, encoder transformer, the 25 -> 12.5 Hz
+    conv (kernel 4, stride 2, no bias, replicate padding, :1419-1429).  wav [B,1,N] -> [B, T, 512]."""
+    x = seanet_encoder(sd, wav_b1n.transpose(1, 2))
+    x = transformer(sd, x, prefix="encoder_transformer")
+    return conv1d_mimi(x, sd["downsample.conv.weight"], None, stride=2, pad_mode="replicate")
+
+
+def rvq_encode(sd: SD, emb_btc: Tensor, n_q: int = 32, n_sem: int = 1) -> Tensor:
+    """MimiSplitResidualVectorQuantizer.encode (:1311-1338): the semantic and the acoustic RVQ both start from the same
+    embeddings, each through its own bias-free 1x1 input_proj 512 -> 256 (:1267-1268); then residual nearest-neighbour
+    search (:1272-1279) with MimiEuclideanCodebook.quantize = argmin of torch.cdist (:1197-1203).  -> codes [B, Q, T]."""
+    out = []
+    for grp, n in (("semantic", n_sem), ("acoustic", n_q - n_sem)):
+        pre = f"quantizer.{grp}_residual_vector_quantizer."
+        res = F.linear(emb_btc, sd[pre + "input_proj.weight"].squeeze(-1))  # [B,T,256]
+        for i in range(n):
+            e = codebook(sd, pre + f"layers.{i}.codebook.")
+            idx = torch.cdist(res.reshape(1, -1, res.size(-1)).float(), e[None].float(), p=2)[0].argmin(dim=-1).view(res.shape[:-1])
+            res = res - F.embedding(idx, e)
+            out.append(idx)
+    return torch.stack(out, dim=1)
+
+
+def mimi_encode(sd: SD, wav_b1n: Tensor, n_q: int = 32) -> Tensor:
+    """MimiModel.encode (:1522-1611) without streaming caches: wav [B,1,N] f32 @24 kHz -> codes [B, Q, ceil(N/1920)]."""
+    return rvq_encode(sd, mimi_encode_latent(sd, wav_b1n), n_q=n_q)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -75,6 +75,16 @@ class MimiWeights(C.Structure):
                 ("stage", MimiStageWeights * MIMI_MAX_RATIOS), ("last_w", _FP), ("last_b", _FP)]
 
 
+class MimiEncStageWeights(C.Structure):
+    _fields_ = [(n, _FP) for n in ("res1_w", "res1_b", "res2_w", "res2_b", "down_w", "down_b")]
+
+
+class MimiEncoderWeights(C.Structure):
+    _fields_ = [("conv0_w", _FP), ("conv0_b", _FP), ("stage", MimiEncStageWeights * MIMI_MAX_RATIOS), ("last_w", _FP),
+                ("last_b", _FP), ("layer", MimiLayerWeights * MIMI_MAX_LAYERS), ("downsample_w", _FP), ("sem_in_proj", _FP),
+                ("ac_in_proj", _FP), ("embed", _FP)]
+
+
 class SsmBlockWeights(C.Structure):
     _fields_ = [(n, C.POINTER(C.c_float)) for n in
                 ("norm_w", "glu_w", "glu_b", "dw_w", "dw_b", "ffn_norm_w", "ffn_w1", "ffn_b1", "ffn_w2", "ffn_b2")]
@@ -156,6 +166,11 @@ SYMBOLS = {
     "sopro_mimi_stream_frames": (C.c_int64, [_VP]),
     "sopro_mimi_decode_step": (_I, [_VP, _VP, _I, _VP, _VP]),
     "sopro_mimi_decode_step_host": (_I, [_VP, _VP, _I, _VP, _VP]),
+    "sopro_mimi_encoder_create": (_I, [C.POINTER(MimiConfigC), C.POINTER(MimiEncoderWeights), _I, C.POINTER(_VP)]),
+    "sopro_mimi_encoder_destroy": (_I, [_VP]),
+    "sopro_mimi_encoded_frames": (C.c_int64, [_VP, C.c_int64]),
+    "sopro_mimi_encode": (_I, [_VP, _VP, C.c_int64, _VP, _VP, _VP]),
+    "sopro_mimi_encode_host": (_I, [_VP, _VP, C.c_int64, _VP, _VP, _VP]),
     "sopro_nar_create": (_I, [_VP, _VP, _I, C.POINTER(_VP)]),
     "sopro_nar_destroy": (_I, [_VP]),
     "sopro_nar_set_forced": (_I, [_VP, _VP]),

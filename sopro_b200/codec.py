@@ -1,9 +1,9 @@
 """Mimi codec boundary: the reference's ``MimiCodec`` / ``MimiStreamDecoder`` / ``MimiDecodeState``
 (reference codec/mimi.py:18-181) over the CUDA decode engine in libsopro_b200.so.
 
-DECODE (``decode_full`` / ``decode_step``) runs entirely in our kernels.  ENCODE (``encode_file``: once per
-reference voice, SURVEY.md §8f-4, out of the hot path) delegates to ``transformers.MimiModel.encode`` when a
-HF model is attached, exactly like the reference does."""
+DECODE (``decode_full`` / ``decode_step``) and ENCODE (``encode_file`` / ``encode_wav``: once per reference voice,
+SURVEY.md §8f-4) both run entirely in our kernels; ``transformers`` is only the place the checkpoint's state_dict is
+read from when none is passed in."""
 from __future__ import annotations
 
 import ctypes as C
@@ -23,6 +23,123 @@ def _f32(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to(device="cpu", dtype=torch.float32).contiguous()
 
 
+def _mimi_config(num_quantizers: int) -> "_lib.MimiConfigC":
+    c = _lib.MimiConfigC()
+    c.hidden, c.codebook_dim, c.n_q, c.n_sem, c.vocab = 512, 256, int(num_quantizers), 1, 2048
+    c.n_layers, c.n_heads, c.ffn, c.window = 8, 8, 2048, 250
+    c.num_filters, c.kernel, c.last_kernel, c.res_kernel, c.compress = 64, 7, 3, 3, 2
+    c.n_ratios = len(UPSAMPLING_RATIOS)
+    for i, r in enumerate(UPSAMPLING_RATIOS):
+        c.ratios[i] = r
+    c.norm_eps, c.rope_theta = 1e-5, 10000.0
+    return c
+
+
+def _codebooks(sd: Dict[str, torch.Tensor], num_quantizers: int) -> torch.Tensor:
+    """embed = embed_sum / clamp(cluster_usage, eps)  (modeling_mimi.py:1192-1196); semantic first -> [Q, 2048, 256]"""
+    embs = []
+    for grp, n in (("semantic", 1), ("acoustic", int(num_quantizers) - 1)):
+        for i in range(n):
+            p = f"quantizer.{grp}_residual_vector_quantizer.layers.{i}.codebook."
+            embs.append(_f32(sd[p + "embed_sum"]) / _f32(sd[p + "cluster_usage"]).clamp(min=1e-5)[:, None])
+    return torch.stack(embs)
+
+
+ENCODER_KEYS = ("encoder.layers.0.conv.weight", "encoder_transformer.layers.0.self_attn.q_proj.weight", "downsample.conv.weight",
+                "quantizer.semantic_residual_vector_quantizer.input_proj.weight")
+
+
+class MimiEncoderEngine:
+    """Device-resident Mimi ENCODER (waveform -> codes), ``MimiModel.encode`` as ``MimiCodec.encode_file`` calls it
+    (reference codec/mimi.py:41-63).  fp32, batch 1."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device, num_quantizers: int = 32):
+        self.lib = _lib.load()
+        dev = torch.device(device if not isinstance(device, int) else f"cuda:{device}")
+        if dev.type != "cuda":
+            raise _lib.SoproError("MimiEncoderEngine needs a CUDA device; there is no CPU path")
+        self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
+        sd = state_dict
+        missing = [k for k in ENCODER_KEYS if k not in sd]
+        if missing:
+            raise KeyError(f"state_dict has no Mimi encoder weights (e.g. {missing[0]})")
+        self.num_quantizers = int(num_quantizers)
+        c = _mimi_config(self.num_quantizers)
+        keep = []
+
+        def ptr(t: torch.Tensor):
+            t = _f32(t)
+            keep.append(t)
+            return C.cast(t.data_ptr(), C.POINTER(C.c_float))
+
+        w = _lib.MimiEncoderWeights()
+        w.conv0_w, w.conv0_b = ptr(sd["encoder.layers.0.conv.weight"]), ptr(sd["encoder.layers.0.conv.bias"])
+        li = 1
+        for s in range(len(UPSAMPLING_RATIOS)):
+            S, p = w.stage[s], f"encoder.layers.{li}.block."
+            S.res1_w, S.res1_b = ptr(sd[p + "1.conv.weight"]), ptr(sd[p + "1.conv.bias"])
+            S.res2_w, S.res2_b = ptr(sd[p + "3.conv.weight"]), ptr(sd[p + "3.conv.bias"])
+            S.down_w, S.down_b = ptr(sd[f"encoder.layers.{li + 2}.conv.weight"]), ptr(sd[f"encoder.layers.{li + 2}.conv.bias"])
+            li += 3
+        w.last_w, w.last_b = ptr(sd[f"encoder.layers.{li + 1}.conv.weight"]), ptr(sd[f"encoder.layers.{li + 1}.conv.bias"])
+        for l in range(8):
+            p, L = f"encoder_transformer.layers.{l}.", w.layer[l]
+            L.ln1_w, L.ln1_b = ptr(sd[p + "input_layernorm.weight"]), ptr(sd[p + "input_layernorm.bias"])
+            L.q_w, L.k_w = ptr(sd[p + "self_attn.q_proj.weight"]), ptr(sd[p + "self_attn.k_proj.weight"])
+            L.v_w, L.o_w = ptr(sd[p + "self_attn.v_proj.weight"]), ptr(sd[p + "self_attn.o_proj.weight"])
+            L.ls1 = ptr(sd[p + "self_attn_layer_scale.scale"])
+            L.ln2_w, L.ln2_b = ptr(sd[p + "post_attention_layernorm.weight"]), ptr(sd[p + "post_attention_layernorm.bias"])
+            L.fc1_w, L.fc2_w = ptr(sd[p + "mlp.fc1.weight"]), ptr(sd[p + "mlp.fc2.weight"])
+            L.ls2 = ptr(sd[p + "mlp_layer_scale.scale"])
+        w.downsample_w = ptr(sd["downsample.conv.weight"])
+        w.sem_in_proj = ptr(sd["quantizer.semantic_residual_vector_quantizer.input_proj.weight"].squeeze(-1))
+        w.ac_in_proj = ptr(sd["quantizer.acoustic_residual_vector_quantizer.input_proj.weight"].squeeze(-1))
+        w.embed = ptr(_codebooks(sd, self.num_quantizers))
+        h = C.c_void_p()
+        _lib.check(self.lib.sopro_mimi_encoder_create(C.byref(c), C.byref(w), self.device.index, C.byref(h)))
+        self._h = h
+        del keep
+
+    def frames(self, n_samples: int) -> int:
+        """MimiModel.get_encoded_length: every strided conv rounds up."""
+        t = int(self.lib.sopro_mimi_encoded_frames(self._h, int(n_samples)))
+        if t < 0:
+            raise ValueError(f"cannot encode {n_samples} samples")
+        return t
+
+    def encode(self, wav: torch.Tensor, *, return_latent: bool = False):
+        """wav [n] / [1, n] / [1, 1, n] f32 @24 kHz (any device) -> codes [Q, T] int64 on the engine's device
+        (and, on request, the pre-quantizer embeddings [T, 512])."""
+        wav = wav.reshape(-1).to(device=self.device, dtype=torch.float32).contiguous()
+        n = int(wav.numel())
+        T = self.frames(n)
+        codes = torch.empty((self.num_quantizers, T), dtype=torch.int32, device=self.device)
+        lat = torch.empty((T, 512), dtype=torch.float32, device=self.device) if return_latent else None
+        _lib.check(self.lib.sopro_mimi_encode(self._h, wav.data_ptr(), n, codes.data_ptr(), lat.data_ptr() if lat is not None else None,
+                                              int(torch.cuda.current_stream(self.device).cuda_stream)))
+        codes = codes.to(torch.long)
+        return (codes, lat) if return_latent else codes
+
+    def encode_host(self, wav: np.ndarray) -> np.ndarray:
+        wav = np.ascontiguousarray(wav, dtype=np.float32).reshape(-1)
+        T = self.frames(wav.size)
+        codes = np.empty((self.num_quantizers, T), dtype=np.int32)
+        _lib.check(self.lib.sopro_mimi_encode_host(self._h, wav.ctypes.data, int(wav.size), codes.ctypes.data, None,
+                                                   int(torch.cuda.current_stream(self.device).cuda_stream)))
+        return codes
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.sopro_mimi_encoder_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class MimiEngine:
     """Device-resident Mimi decoder built from a ``MimiModel`` state_dict (decode-path tensors only)."""
 
@@ -35,14 +152,7 @@ class MimiEngine:
             raise _lib.SoproError("MimiEngine needs a CUDA device; there is no CPU path")
         self.device = torch.device("cuda", dev.index if dev.index is not None else 0)
         sd = state_dict
-        c = _lib.MimiConfigC()
-        c.hidden, c.codebook_dim, c.n_q, c.n_sem, c.vocab = 512, 256, int(num_quantizers), 1, 2048
-        c.n_layers, c.n_heads, c.ffn, c.window = 8, 8, 2048, 250
-        c.num_filters, c.kernel, c.last_kernel, c.res_kernel, c.compress = 64, 7, 3, 3, 2
-        c.n_ratios = len(UPSAMPLING_RATIOS)
-        for i, r in enumerate(UPSAMPLING_RATIOS):
-            c.ratios[i] = r
-        c.norm_eps, c.rope_theta = 1e-5, 10000.0
+        c = _mimi_config(num_quantizers)
         self.num_quantizers = int(num_quantizers)
         keep = []
 
@@ -51,14 +161,8 @@ class MimiEngine:
             keep.append(t)
             return C.cast(t.data_ptr(), C.POINTER(C.c_float))
 
-        # embed = embed_sum / clamp(cluster_usage, eps)  (modeling_mimi.py:1192-1196); semantic first
-        embs = []
-        for grp, n in (("semantic", 1), ("acoustic", self.num_quantizers - 1)):
-            for i in range(n):
-                p = f"quantizer.{grp}_residual_vector_quantizer.layers.{i}.codebook."
-                embs.append(_f32(sd[p + "embed_sum"]) / _f32(sd[p + "cluster_usage"]).clamp(min=1e-5)[:, None])
         w = _lib.MimiWeights()
-        w.embed = ptr(torch.stack(embs))
+        w.embed = ptr(_codebooks(sd, self.num_quantizers))
         w.sem_out_proj = ptr(sd["quantizer.semantic_residual_vector_quantizer.output_proj.weight"].squeeze(-1))
         w.ac_out_proj = ptr(sd["quantizer.acoustic_residual_vector_quantizer.output_proj.weight"].squeeze(-1))
         w.upsample_w = ptr(sd["upsample.conv.weight"])
@@ -202,7 +306,8 @@ class MimiStream:
 
 
 class MimiCodec:
-    """reference codec/mimi.py:18-72.  ``hf_model`` (a transformers MimiModel) is only used by ``encode_file``."""
+    """reference codec/mimi.py:18-72.  ``hf_model`` (a transformers MimiModel) is only a source of the state_dict; both
+    directions run on the CUDA engines.  The encoder engine is built on first use (a voice is encoded once)."""
 
     def __init__(self, num_quantizers: int, device: str = "cuda", model_id: str = "kyutai/mimi", *,
                  state_dict: Optional[Dict[str, torch.Tensor]] = None, hf_model=None, precision: str = "bf16_tc"):
@@ -218,6 +323,10 @@ class MimiCodec:
             state_dict = hf_model.state_dict()
         self._num_quantizers = int(num_quantizers)
         self.engine = MimiEngine(state_dict, self.device, num_quantizers=self._num_quantizers, precision=precision)
+        self._encoder: Optional[MimiEncoderEngine] = None
+        enc = ("encoder.", "encoder_transformer.", "downsample.", "quantizer.")
+        self._encoder_sd = ({k: v for k, v in state_dict.items() if k.startswith(enc)}
+                            if all(k in state_dict for k in ENCODER_KEYS) else None)
 
     @property
     def codebook_size(self) -> int:
@@ -230,8 +339,6 @@ class MimiCodec:
     @torch.no_grad()
     def encode_file(self, wav_path: str, *, crop_seconds: Optional[float] = None) -> torch.Tensor:
         """reference codec/mimi.py:41-63 (VAD trim -> resample -> centre crop -> MimiModel.encode)."""
-        if self.model is None:
-            raise RuntimeError("encode_file needs the HF MimiModel encoder (pass hf_model=...); decode does not")
         from .audio import center_crop_audio, load_audio_file, resample, trim_silence_energy
 
         wav, sr = load_audio_file(wav_path)
@@ -240,9 +347,22 @@ class MimiCodec:
         if crop_seconds is not None and crop_seconds > 0:
             hop = int(round(TARGET_SR / 12.5))
             wav = center_crop_audio(wav, max(1, int(round(crop_seconds * 12.5))) * hop)
-        self.model.to(self.device)
-        out = self.model.encode(wav.unsqueeze(0).to(self.device), return_dict=True)
-        return out.audio_codes[0].permute(1, 0).contiguous()
+        return self.encode_wav(wav)
+
+    @property
+    def encoder(self) -> MimiEncoderEngine:
+        if self._encoder is None:
+            if self._encoder_sd is None:
+                raise RuntimeError("this MimiCodec was built from a decode-only state_dict: no Mimi encoder weights to encode with")
+            self._encoder = MimiEncoderEngine(self._encoder_sd, self.device, num_quantizers=self._num_quantizers)
+            self._encoder_sd = None
+        return self._encoder
+
+    @torch.no_grad()
+    def encode_wav(self, wav: torch.Tensor) -> torch.Tensor:
+        """mono waveform @24 kHz ([n], [1, n] or [1, 1, n]) -> codes [T, Q] int64 on the device: the model call of
+        ``encode_file`` (reference codec/mimi.py:59-62), on the CUDA encoder."""
+        return self.encoder.encode(wav).permute(1, 0).contiguous()
 
     @torch.no_grad()
     def decode_full(self, codes_tq: torch.Tensor) -> torch.Tensor:

@@ -1472,3 +1472,422 @@ int sopro_mimi_decode_host(sopro_mimi_t* m, const int32_t* codes_host, int B, in
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// ENCODE: waveform -> codes (MimiModel.encode, modeling_mimi.py:1455-1488, 1522-1611; the reference calls it once per
+// reference voice, codec/mimi.py:41-63).  fp32 throughout on the kernels above: every conv is the implicit GEMM; a conv
+// of kernel 2r and stride r over [L][C] is the 2-tap stride-1 conv over the same memory read as [L/r][r*C] (L padded
+// with zero rows to a multiple of r: MimiConv1d's "extra padding", :273-285; its causal left padding of r rows is the
+// tap at superrow -1).
+// =====================================================================================================================
+namespace mimi {
+// first conv: wav [L] -> y [L][F], kernel k, causal (left zero pad k-1), weight [F][k]
+__global__ void enc_conv0_kernel(const float* __restrict__ wav, const float* __restrict__ w, const float* __restrict__ bias,
+                                 float* __restrict__ y, long long L, int F, int k) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * F) return;
+  const long long t = i / F;
+  const int c = (int)(i - t * F);
+  float acc = __ldg(bias + c);
+  for (int j = 0; j < k; ++j) {
+    const long long ti = t + j - (k - 1);
+    if (ti >= 0) acc = fmaf(__ldg(w + c * k + j), __ldg(wav + ti), acc);
+  }
+  y[i] = acc;
+}
+
+// replicate padding for the 25 -> 12.5 Hz conv: y rows [0, left) = x[0], [left, left+T) = x, [left+T, rows) = x[T-1]
+__global__ void replicate_pad_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int C, int left, int rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)rows * C) return;
+  const int r = (int)(i / C), c = (int)(i - (long long)r * C);
+  int src = r - left;
+  src = src < 0 ? 0 : (src >= T ? T - 1 : src);
+  y[i] = x[(size_t)src * C + c];
+}
+
+// Residual nearest-neighbour search (MimiResidualVectorQuantizer.encode :1262-1280 with MimiEuclideanCodebook.quantize
+// :1197-1203): one CTA per frame, the residual (Dc = 32*DPL floats) in registers, lane-sliced; a warp scans every 8th
+// code vector, squared distance summed directly (the reference's cdist goes through |x|^2+|e|^2-2xe, same minimiser),
+// lowest index wins ties (torch.argmin).  proj [T][2*Dc] = [semantic input_proj | acoustic input_proj] of the latent.
+template <int DPL>
+__global__ void __launch_bounds__(256) rvq_encode_kernel(const float* __restrict__ proj, const float* __restrict__ embed,
+                                                         int* __restrict__ codes, int T, int n_q, int n_sem, int V) {
+  constexpr int Dc = 32 * DPL;
+  __shared__ float best_d[8];
+  __shared__ int best_i[8];
+  __shared__ int winner;
+  const int t = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float r[DPL];
+  for (int q = 0; q < n_q; ++q) {
+    if (q == 0 || q == n_sem) {
+      const float* p = proj + (size_t)t * 2 * Dc + (q == 0 ? 0 : Dc) + lane * DPL;
+#pragma unroll
+      for (int i = 0; i < DPL; ++i) r[i] = p[i];
+    }
+    const float* E = embed + (size_t)q * V * Dc;
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
+    for (int k = warp; k < V; k += 8) {
+      const float* e = E + (size_t)k * Dc + lane * DPL;
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < DPL; i += 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(e + i));
+        float d = r[i] - v.x;
+        acc = fmaf(d, d, acc);
+        d = r[i + 1] - v.y;
+        acc = fmaf(d, d, acc);
+        d = r[i + 2] - v.z;
+        acc = fmaf(d, d, acc);
+        d = r[i + 3] - v.w;
+        acc = fmaf(d, d, acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (acc < bd) {  // k ascends within a warp: strict < keeps the lowest index
+        bd = acc;
+        bi = k;
+      }
+    }
+    if (lane == 0) {
+      best_d[warp] = bd;
+      best_i[warp] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float d = best_d[0];
+      int ix = best_i[0];
+      for (int w = 1; w < 8; ++w)
+        if (best_d[w] < d || (best_d[w] == d && best_i[w] < ix)) {
+          d = best_d[w];
+          ix = best_i[w];
+        }
+      winner = ix;
+      codes[(size_t)q * T + t] = ix;
+    }
+    __syncthreads();
+    const float* e = E + (size_t)winner * Dc + lane * DPL;
+#pragma unroll
+    for (int i = 0; i < DPL; ++i) r[i] -= __ldg(e + i);
+    // (best_d / best_i / winner are rewritten only after the next __syncthreads pair)
+  }
+}
+}  // namespace mimi
+
+struct sopro_mimi_encoder {
+  int device = 0;
+  sopro_mimi_config_t cfg{};
+  float* dev = nullptr;
+  size_t c0w = 0, c0b = 0, lw = 0, lb = 0, down_w = 0, inproj = 0, embed = 0;
+  struct Stage {
+    size_t r1w, r1b, r2w, r2b, dw, db;
+    int ratio, cin;
+  };
+  std::vector<Stage> stages;
+  std::vector<sopro_mimi::Layer> layers;  // fp32 offsets only
+  float* rope = nullptr;
+  int rope_T2 = 0;
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  float* wav_dev = nullptr;   // staging of the *_host entry point
+  int* codes_dev = nullptr;
+  float* lat_dev = nullptr;
+  size_t wav_cap = 0, codes_cap = 0, lat_cap = 0;
+};
+
+namespace {
+constexpr long long kEncMaxSamples = 24000LL * 600;  // ten minutes of audio; a reference voice is seconds
+
+struct EncPlan {
+  long long len[SOPRO_MIMI_MAX_RATIOS + 1];   // rows entering stage s (len[0] = samples), len[n_ratios] = transformer positions
+  long long padded[SOPRO_MIMI_MAX_RATIOS];    // len[s] rounded up to the stage's stride
+  long long T;                                // frames
+  size_t buf, xsz, need;
+};
+
+EncPlan enc_plan(const sopro_mimi_config_t& c, long long n) {
+  EncPlan p{};
+  p.len[0] = n;
+  size_t widest = 0;
+  int ch = c.num_filters;
+  for (int s = 0; s < c.n_ratios; ++s) {
+    const int r = c.ratios[c.n_ratios - 1 - s];
+    p.padded[s] = (p.len[s] + r - 1) / r * r;
+    p.len[s + 1] = p.padded[s] / r;
+    widest = std::max(widest, (size_t)p.padded[s] * ch);
+    ch *= 2;
+  }
+  const long long T2 = p.len[c.n_ratios];
+  p.T = (T2 + 1) / 2;
+  widest = std::max(widest, (size_t)T2 * ch);                                   // last conv input [T2][16F]
+  widest = std::max(widest, (size_t)T2 * (size_t)std::max(3 * c.hidden, c.ffn));  // QKV / MLP hidden
+  widest = std::max(widest, (size_t)(2 * p.T + 2) * c.hidden);                  // replicate-padded downsample input
+  p.buf = (widest + 63) / 64 * 64;
+  p.xsz = ((size_t)T2 * c.hidden + 63) / 64 * 64;
+  p.need = (3 * p.buf + 2 * p.xsz) * 4;
+  return p;
+}
+}  // namespace
+
+extern "C" {
+
+int sopro_mimi_encoder_create(const sopro_mimi_config_t* cfg, const sopro_mimi_encoder_weights_t* w, int device,
+                              sopro_mimi_encoder_t** out) {
+  if (!cfg || !w || !out) return mfail(SOPRO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) return mfail(SOPRO_ERR_UNSUPPORTED, "no CUDA device; the Mimi encoder has no CPU fallback");
+  if (device < 0 || device >= ndev) return mfail(SOPRO_ERR_INVALID, "device %d out of range", device);
+  cudaDeviceProp prop;
+  MCK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return mfail(SOPRO_ERR_UNSUPPORTED, "device is sm_%d%d; this build targets sm_100a only", prop.major, prop.minor);
+  const int C = cfg->hidden, Dc = cfg->codebook_dim, Q = cfg->n_q, V = cfg->vocab, NL = cfg->n_layers, FF = cfg->ffn, F0 = cfg->num_filters;
+  if (C % 64 || Dc != 256 || C != 2 * Dc || NL < 1 || NL > SOPRO_MIMI_MAX_LAYERS || cfg->n_ratios < 1 || cfg->n_ratios > SOPRO_MIMI_MAX_RATIOS ||
+      cfg->n_heads < 1 || C % cfg->n_heads || (C / cfg->n_heads) % 4 || FF % 16 || F0 % 16 || cfg->compress != 2 || Q < 1 || cfg->n_sem < 1 ||
+      cfg->n_sem > Q || cfg->kernel < 1 || cfg->kernel > 16)
+    return mfail(SOPRO_ERR_INVALID, "unsupported Mimi encoder geometry (hidden=%d codebook_dim=%d)", C, Dc);
+  MCK(cudaSetDevice(device));
+  sopro_mimi_encoder* e = new sopro_mimi_encoder();
+  e->device = device;
+  e->cfg = *cfg;
+  DevArena A;
+  // conv weights [Cout][Cin][k] -> [Cout][(tap, ci)]; a strided conv's taps j = j2*r + rr are ordered (j2, rr, ci), which
+  // is the same formula with k = 2r
+  auto repack_conv = [&](const float* src, int cout, int cin, int k) {
+    std::vector<float> r((size_t)cout * k * cin);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int j = 0; j < k; ++j) r[((size_t)co * k + j) * cin + ci] = src[((size_t)co * cin + ci) * k + j];
+    return A.add(r.data(), r.size());
+  };
+  e->c0w = A.add(w->conv0_w, (size_t)F0 * cfg->kernel);
+  e->c0b = A.add(w->conv0_b, F0);
+  int ch = F0;
+  for (int s = 0; s < cfg->n_ratios; ++s) {
+    const sopro_mimi_enc_stage_weights_t& S = w->stage[s];
+    sopro_mimi_encoder::Stage d;
+    d.ratio = cfg->ratios[cfg->n_ratios - 1 - s];
+    d.cin = ch;
+    d.r1w = repack_conv(S.res1_w, ch / 2, ch, cfg->res_kernel);
+    d.r1b = A.add(S.res1_b, ch / 2);
+    d.r2w = repack_conv(S.res2_w, ch, ch / 2, 1);
+    d.r2b = A.add(S.res2_b, ch);
+    d.dw = repack_conv(S.down_w, 2 * ch, ch, 2 * d.ratio);
+    d.db = A.add(S.down_b, 2 * ch);
+    e->stages.push_back(d);
+    ch *= 2;
+  }
+  e->lw = repack_conv(w->last_w, C, ch, cfg->last_kernel);
+  e->lb = A.add(w->last_b, C);
+  for (int l = 0; l < NL; ++l) {
+    const sopro_mimi_layer_weights_t& L = w->layer[l];
+    sopro_mimi::Layer d{};
+    d.ln1w = A.add(L.ln1_w, C);
+    d.ln1b = A.add(L.ln1_b, C);
+    std::vector<float> qkv((size_t)3 * C * C);
+    memcpy(qkv.data(), L.q_w, (size_t)C * C * 4);
+    memcpy(qkv.data() + (size_t)C * C, L.k_w, (size_t)C * C * 4);
+    memcpy(qkv.data() + (size_t)2 * C * C, L.v_w, (size_t)C * C * 4);
+    d.qkv = A.add(qkv.data(), qkv.size());
+    d.wo = A.add(L.o_w, (size_t)C * C);
+    d.ls1 = A.add(L.ls1, C);
+    d.ln2w = A.add(L.ln2_w, C);
+    d.ln2b = A.add(L.ln2_b, C);
+    d.fc1 = A.add(L.fc1_w, (size_t)FF * C);
+    d.fc2 = A.add(L.fc2_w, (size_t)C * FF);
+    d.ls2 = A.add(L.ls2, C);
+    e->layers.push_back(d);
+  }
+  e->down_w = repack_conv(w->downsample_w, C, C, 4);
+  {  // [2*Dc][C]: semantic input_proj rows, then acoustic
+    std::vector<float> cat((size_t)2 * Dc * C);
+    memcpy(cat.data(), w->sem_in_proj, (size_t)Dc * C * 4);
+    memcpy(cat.data() + (size_t)Dc * C, w->ac_in_proj, (size_t)Dc * C * 4);
+    e->inproj = A.add(cat.data(), cat.size());
+  }
+  e->embed = A.add(w->embed, (size_t)Q * V * Dc);
+  cudaError_t err = cudaMalloc(&e->dev, A.host.size() * 4);
+  if (err == cudaSuccess) err = cudaMemcpy(e->dev, A.host.data(), A.host.size() * 4, cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) {
+    if (e->dev) cudaFree(e->dev);
+    delete e;
+    return mfail(SOPRO_ERR_CUDA, "Mimi encoder weight upload failed: %s", cudaGetErrorString(err));
+  }
+  *out = e;
+  return SOPRO_OK;
+}
+
+int sopro_mimi_encoder_destroy(sopro_mimi_encoder_t* e) {
+  if (!e) return SOPRO_OK;
+  cudaSetDevice(e->device);
+  cudaFree(e->dev);
+  cudaFree(e->rope);
+  cudaFree(e->ws);
+  cudaFree(e->wav_dev);
+  cudaFree(e->codes_dev);
+  cudaFree(e->lat_dev);
+  delete e;
+  return SOPRO_OK;
+}
+
+int64_t sopro_mimi_encoded_frames(const sopro_mimi_encoder_t* e, int64_t n_samples) {
+  if (!e || n_samples < 1 || n_samples > kEncMaxSamples) return -1;
+  return enc_plan(e->cfg, n_samples).T;
+}
+
+int sopro_mimi_encode(sopro_mimi_encoder_t* e, const float* wav, int64_t n_samples, int32_t* codes, float* latent, void* stream) {
+  if (!e || !wav || !codes) return mfail(SOPRO_ERR_INVALID, "null argument");
+  if (n_samples < 1 || n_samples > kEncMaxSamples)
+    return mfail(SOPRO_ERR_INVALID, "n_samples=%lld outside [1, %lld]", (long long)n_samples, kEncMaxSamples);
+  MCK(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const sopro_mimi_config_t& c = e->cfg;
+  const int C = c.hidden, H = c.n_heads, Dh = C / H, FF = c.ffn, Dc = c.codebook_dim;
+  const EncPlan P = enc_plan(c, n_samples);
+  const int T2 = (int)P.len[c.n_ratios], T = (int)P.T;
+  if (e->rope_T2 < T2) {  // RoPE table [cos rows | sin rows], as the decoder's
+    cudaFree(e->rope);
+    e->rope = nullptr;
+    e->rope_T2 = 0;
+    const int cap = std::max(T2, 256);
+    std::vector<float> tab((size_t)2 * cap * (Dh / 2));
+    for (int t = 0; t < cap; ++t)
+      for (int d = 0; d < Dh / 2; ++d) {
+        const float inv = 1.0f / powf(c.rope_theta, (float)(2 * d) / (float)Dh);
+        const float f = (float)t * inv;
+        tab[(size_t)t * (Dh / 2) + d] = cosf(f);
+        tab[(size_t)(cap + t) * (Dh / 2) + d] = sinf(f);
+      }
+    MCK(cudaMalloc(&e->rope, tab.size() * 4));
+    MCK(cudaMemcpyAsync(e->rope, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
+    MCK(cudaStreamSynchronize(st));
+    e->rope_T2 = cap;
+  }
+  if (e->ws_bytes < P.need) {
+    cudaFree(e->ws);
+    e->ws = nullptr;
+    e->ws_bytes = 0;
+    cudaError_t ae = cudaMalloc(&e->ws, P.need);
+    if (ae != cudaSuccess) return mfail(SOPRO_ERR_CUDA, "Mimi encoder workspace %zu MB: %s", P.need >> 20, cudaGetErrorString(ae));
+    e->ws_bytes = P.need;
+  }
+  float* b0 = e->ws;
+  float* b1 = b0 + P.buf;
+  float* b2 = b1 + P.buf;
+  float* x = b2 + P.buf;
+  float* ln = x + P.xsz;
+  const float* Wd = e->dev;
+  GemmOp g{};
+  // conv over rows [Tin][cin] (row stride cin), `taps` taps, left pad `pad` rows, M output rows
+  auto conv = [&](const float* A, long long Tin, long long M, int cin, int taps, int pad, const float* W, const float* bias, int N,
+                  float* Cc, int elu, int epi, const float* R, const float* scale) {
+    g = GemmOp{};
+    g.A = A; g.W = W; g.C = Cc; g.R = R; g.bias = bias; g.scale = scale;
+    g.M = (int)M; g.N = N; g.K = taps * cin; g.Min = (int)Tin; g.Cin = cin; g.taps = taps; g.dil = 1; g.pad = pad; g.ldc = N;
+    g.bias_mod = N; g.epi = epi; g.a_elu = elu;
+    g.a_bs = Tin * cin; g.c_bs = M * N; g.r_bs = M * N;
+    return launch_gemm(g, 1, st);
+  };
+  int rc;
+  // ---- SEANet encoder
+  float* cur = b0;   // stage input [len][ch]
+  float* hid = b1;   // resblock hidden [len][ch/2]
+  float* nxt = b2;
+  {
+    const long long tot = n_samples * c.num_filters;
+    enc_conv0_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(wav, Wd + e->c0w, Wd + e->c0b, cur, n_samples, c.num_filters, c.kernel);
+    MCK(cudaGetLastError());
+  }
+  int ch = c.num_filters;
+  for (int s = 0; s < c.n_ratios; ++s) {
+    const sopro_mimi_encoder::Stage& S = e->stages[s];
+    const long long Ls = P.len[s], Lp = P.padded[s];
+    const int r = S.ratio;
+    // ResnetBlock (:412-451): x + conv1(ELU(conv3(ELU(x))))
+    if ((rc = conv(cur, Ls, Ls, ch, c.res_kernel, c.res_kernel - 1, Wd + S.r1w, Wd + S.r1b, ch / 2, hid, 1, EPI_NONE, nullptr, nullptr))) return rc;
+    if ((rc = conv(hid, Ls, Ls, ch / 2, 1, 0, Wd + S.r2w, Wd + S.r2b, ch, cur, 1, EPI_RES, cur, nullptr))) return rc;
+    // ELU + conv kernel 2r stride r: zero rows up to a multiple of r, then 2 taps over [Lp/r][r*ch]
+    if (Lp > Ls) MCK(cudaMemsetAsync(cur + (size_t)Ls * ch, 0, (size_t)(Lp - Ls) * ch * 4, st));
+    if ((rc = conv(cur, Lp / r, Lp / r, r * ch, 2, 1, Wd + S.dw, Wd + S.db, 2 * ch, nxt, 1, EPI_NONE, nullptr, nullptr))) return rc;
+    std::swap(cur, nxt);
+    ch *= 2;
+  }
+  // ELU + conv k3 -> residual stream x [T2][C]
+  if ((rc = conv(cur, T2, T2, ch, c.last_kernel, c.last_kernel - 1, Wd + e->lw, Wd + e->lb, C, x, 1, EPI_NONE, nullptr, nullptr))) return rc;
+  // ---- encoder transformer (MimiTransformerLayer.forward :966-993), fp32 path of the decoder
+  {
+    const unsigned ln_grid = (unsigned)((T2 + 7) / 8);
+    const size_t asm_bytes = (size_t)8 * (Dh + c.window) * 4;
+    auto lin = [&](const float* A, int K, const float* W, int N, float* Cc, int epi, const float* R, const float* scale) {
+      return conv(A, T2, T2, K, 1, 0, W, nullptr, N, Cc, 0, epi, R, scale);
+    };
+    for (const sopro_mimi::Layer& L : e->layers) {
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln1w, Wd + L.ln1b, ln, (long long)T2, C, c.norm_eps);
+      if ((rc = lin(ln, C, Wd + L.qkv, 3 * C, b0, EPI_NONE, nullptr, nullptr))) return rc;
+      rope_kernel<<<dim3(T2, 1), 256, 0, st>>>(b0, e->rope, T2, e->rope_T2, C, H, 0, nullptr, nullptr, 1);
+      attn_kernel<<<dim3((T2 + 7) / 8, H, 1), 256, asm_bytes, st>>>(b0, b1, T2, C, H, c.window, 0, nullptr, nullptr, 1);
+      MCK(cudaGetLastError());
+      if ((rc = lin(b1, C, Wd + L.wo, C, x, EPI_RES_SCALE, x, Wd + L.ls1))) return rc;
+      layernorm_kernel<<<ln_grid, 256, 0, st>>>(x, Wd + L.ln2w, Wd + L.ln2b, ln, (long long)T2, C, c.norm_eps);
+      if ((rc = lin(ln, C, Wd + L.fc1, FF, b0, EPI_GELU, nullptr, nullptr))) return rc;
+      if ((rc = lin(b0, FF, Wd + L.fc2, C, x, EPI_RES_SCALE, x, Wd + L.ls2))) return rc;
+    }
+  }
+  // ---- 25 -> 12.5 Hz: kernel 4, stride 2, no bias, replicate padding (2 rows left, 0 or 1 right)
+  {
+    const int rows = 2 * T + 2;
+    const long long tot = (long long)rows * C;
+    replicate_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(x, b0, T2, C, 2, rows);
+    MCK(cudaGetLastError());
+    float* lat = latent ? latent : b1;
+    if ((rc = conv(b0, rows / 2, T, 2 * C, 2, 0, Wd + e->down_w, nullptr, C, lat, 0, EPI_NONE, nullptr, nullptr))) return rc;
+    // ---- quantizer: both input projections in one GEMM, then the residual search
+    if ((rc = conv(lat, T, T, C, 1, 0, Wd + e->inproj, nullptr, 2 * Dc, b2, 0, EPI_NONE, nullptr, nullptr))) return rc;
+    rvq_encode_kernel<8><<<T, 256, 0, st>>>(b2, Wd + e->embed, codes, T, c.n_q, c.n_sem, c.vocab);
+    MCK(cudaGetLastError());
+  }
+  return SOPRO_OK;
+}
+
+int sopro_mimi_encode_host(sopro_mimi_encoder_t* e, const float* wav_host, int64_t n_samples, int32_t* codes_host,
+                           float* latent_host, void* stream) {
+  if (!e || !wav_host || !codes_host) return mfail(SOPRO_ERR_INVALID, "null argument");
+  if (n_samples < 1 || n_samples > kEncMaxSamples)
+    return mfail(SOPRO_ERR_INVALID, "n_samples=%lld outside [1, %lld]", (long long)n_samples, kEncMaxSamples);
+  MCK(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long T = enc_plan(e->cfg, n_samples).T;
+  const size_t nc = (size_t)e->cfg.n_q * T, nl = (size_t)T * e->cfg.hidden;
+  if (e->wav_cap < (size_t)n_samples) {
+    cudaFree(e->wav_dev);
+    e->wav_dev = nullptr;
+    e->wav_cap = 0;
+    MCK(cudaMalloc(&e->wav_dev, (size_t)n_samples * 4));
+    e->wav_cap = (size_t)n_samples;
+  }
+  if (e->codes_cap < nc) {
+    cudaFree(e->codes_dev);
+    e->codes_dev = nullptr;
+    e->codes_cap = 0;
+    MCK(cudaMalloc(&e->codes_dev, nc * 4));
+    e->codes_cap = nc;
+  }
+  if (latent_host && e->lat_cap < nl) {
+    cudaFree(e->lat_dev);
+    e->lat_dev = nullptr;
+    e->lat_cap = 0;
+    MCK(cudaMalloc(&e->lat_dev, nl * 4));
+    e->lat_cap = nl;
+  }
+  MCK(cudaMemcpyAsync(e->wav_dev, wav_host, (size_t)n_samples * 4, cudaMemcpyHostToDevice, st));
+  const int rc = sopro_mimi_encode(e, e->wav_dev, n_samples, e->codes_dev, latent_host ? e->lat_dev : nullptr, st);
+  if (rc) return rc;
+  MCK(cudaMemcpyAsync(codes_host, e->codes_dev, nc * 4, cudaMemcpyDeviceToHost, st));
+  if (latent_host) MCK(cudaMemcpyAsync(latent_host, e->lat_dev, nl * 4, cudaMemcpyDeviceToHost, st));
+  MCK(cudaStreamSynchronize(st));
+  return SOPRO_OK;
+}
+
+}  // extern "C"

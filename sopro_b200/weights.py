@@ -318,3 +318,43 @@ def synth_mimi_state_dict(seed: int = 5, layer_scale: float = 0.3) -> Dict[str, 
     sd[f"decoder.layers.{li + 1}.conv.weight"] = U("lw", (1, 64, 3), 1 / math.sqrt(64 * 3))
     sd[f"decoder.layers.{li + 1}.conv.bias"] = U("lb", (1,), 0.02)
     return sd
+
+
+def synth_mimi_encoder_state_dict(seed: int = 5, layer_scale: float = 0.3) -> Dict[str, torch.Tensor]:
+    """Seeded random weights for the ENCODE path of ``MimiModel`` (SEANet encoder, encoder transformer, the
+    replicate-padded downsampling conv); the quantizer's codebooks and input projections come from
+    ``synth_mimi_state_dict``.  Same hashing, same platform independence."""
+    def U(name, shape, bound):
+        import zlib
+        n = int(np.prod(shape))
+        return torch.from_numpy(hash_uniform(n, (zlib.crc32(name.encode()) << 20) ^ seed) * np.float32(bound)).view(shape)
+
+    sd: Dict[str, torch.Tensor] = {}
+    sd["encoder.layers.0.conv.weight"] = U("e0w", (64, 1, 7), 1.5)
+    sd["encoder.layers.0.conv.bias"] = U("e0b", (64,), 0.05)
+    li, c = 1, 64
+    for r in (4, 5, 6, 8):  # reversed(upsampling_ratios), modeling_mimi.py:465
+        p = f"encoder.layers.{li}.block."
+        sd[p + "1.conv.weight"] = U(p + "1w", (c // 2, c, 3), 1.7 / math.sqrt(c * 3))
+        sd[p + "1.conv.bias"] = U(p + "1b", (c // 2,), 0.02)
+        sd[p + "3.conv.weight"] = U(p + "3w", (c, c // 2, 1), 1.7 / math.sqrt(c // 2))
+        sd[p + "3.conv.bias"] = U(p + "3b", (c,), 0.02)
+        sd[f"encoder.layers.{li + 2}.conv.weight"] = U(f"ed{li}w", (2 * c, c, 2 * r), 2.5 / math.sqrt(c * 2 * r))
+        sd[f"encoder.layers.{li + 2}.conv.bias"] = U(f"ed{li}b", (2 * c,), 0.02)
+        li += 3
+        c *= 2
+    sd[f"encoder.layers.{li + 1}.conv.weight"] = U("elw", (512, c, 3), 2.5 / math.sqrt(c * 3))
+    sd[f"encoder.layers.{li + 1}.conv.bias"] = U("elb", (512,), 0.02)
+    for l in range(8):
+        p = f"encoder_transformer.layers.{l}."
+        for n in ("q", "k", "v", "o"):
+            sd[p + f"self_attn.{n}_proj.weight"] = U(p + n, (512, 512), 1 / 22.6)
+        sd[p + "mlp.fc1.weight"] = U(p + "f1", (2048, 512), 1 / 22.6)
+        sd[p + "mlp.fc2.weight"] = U(p + "f2", (512, 2048), 1 / 45.0)
+        for n in ("input_layernorm", "post_attention_layernorm"):
+            sd[p + n + ".weight"] = 1.0 + U(p + n + "w", (512,), 0.2)
+            sd[p + n + ".bias"] = U(p + n + "b", (512,), 0.1)
+        sd[p + "self_attn_layer_scale.scale"] = layer_scale + U(p + "ls1", (512,), 0.1)
+        sd[p + "mlp_layer_scale.scale"] = layer_scale + U(p + "ls2", (512,), 0.1)
+    sd["downsample.conv.weight"] = U("down", (512, 512, 4), 2.0 / math.sqrt(512 * 4))
+    return sd

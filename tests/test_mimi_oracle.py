@@ -72,3 +72,52 @@ def test_bf16_operand_model_stays_near_the_fp32_restatement():
     err1 = float((M.mimi_decode_bf16_operands(sd, torch.randint(0, 2048, (1, 32, 5), generator=torch.Generator().manual_seed(1)))
                   - M.mimi_decode(sd, torch.randint(0, 2048, (1, 32, 5), generator=torch.Generator().manual_seed(1)))).abs().max())
     assert abs(err1 - 8.16e-4) <= 1e-4  # same error as the GPU measured on these codes (profiles/r01e_summary.md)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ENCODE path
+# ---------------------------------------------------------------------------------------------------------------
+def _full_sd():
+    sd = dict(M.synth_mimi_state_dict())
+    sd.update(M.synth_mimi_encoder_state_dict())
+    return sd
+
+
+def _golden_encode():
+    import os
+
+    import numpy as np
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mimi_encode.npz"))
+
+
+def _golden_waveform(n):
+    from tests.golden.make_mimi_encode_golden import waveform
+
+    return waveform(n)
+
+
+def test_encode_restatement_matches_the_committed_transformers_codes():
+    """tests/golden/mimi_encode.npz holds MimiModel.encode's codes (transformers 5.5.0, generated here by
+    tests/golden/make_mimi_encode_golden.py); the restatement reproduces every id, ragged lengths included."""
+    sd, g = _full_sd(), _golden_encode()
+    for n in (999, 5760, 13951, 48077):
+        want = torch.from_numpy(g[f"codes_{n}"].astype("int64"))
+        got = M.mimi_encode(sd, _golden_waveform(n))[0]
+        assert got.shape == want.shape == (32, M.encoded_frames(n))
+        assert bool((got == want).all()), (n, int((got != want).sum()))
+    assert len(set(g["codes_48077"][0].tolist())) > 10  # the quantizer is not stuck on one entry
+
+
+@pytest.mark.parametrize("n", [1, 7, 1919, 1921, 24000 + 13])
+def test_encode_restatement_matches_transformers_live(n):
+    tr = pytest.importorskip("transformers")
+    sd = _full_sd()
+    m = tr.MimiModel(tr.MimiConfig(num_quantizers=32)).eval()
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    wav = torch.randn(1, 1, n, generator=torch.Generator().manual_seed(n)) * 0.3
+    want = m.encode(wav, return_dict=True).audio_codes
+    got = M.mimi_encode(sd, wav)
+    assert got.shape == want.shape and bool((got == want).all())
+    assert M.encoded_frames(n) == int(m.get_encoded_length(torch.tensor(n))) == got.shape[-1]
