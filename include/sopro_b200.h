@@ -477,6 +477,59 @@ int sopro_prefill_run(sopro_prefill_t* p, const int32_t* text_ids, const int32_t
                       int sv_shared, const float* const* ref_k, const float* const* ref_v, int Tr, float style_strength,
                       int n_frames, float* txt_seq, float* txt_pool, float* cond_ar, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Reference preparation: SoproTTSModel.prepare_reference (reference model.py:152-170), once per voice, from the
+ * voice's codes: Token2SV (nn/speaker.py:12-61, AttentiveStatsPool nn/blocks.py:165-188) -> sv_ref;
+ * _encode_reference_seq (model.py:136-150) -> ref_seq; RefXAttnStack.build_kv_caches (nn/ref.py) -> the K / V the
+ * prefill engine reads.  fp32.  HOST fp32 weight pointers, state_dict layouts.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct sopro_refprep_config {
+  int32_t d_model;        /* 384 */
+  int32_t sv_embed_dim;   /* 192: Token2SV's d */
+  int32_t sv_dim;         /* cfg.sv_student_dim (192) */
+  int32_t n_codebooks;    /* 32 */
+  int32_t codebook_size;  /* 2048 */
+  int32_t sv_kernel;      /* 7 (nn/speaker.py:24,27) */
+  int32_t ref_enc_layers; /* cfg.ref_enc_layers (2) */
+  int32_t ref_enc_kernel; /* 7 */
+  int32_t ref_layers;     /* cfg.ref_xattn_layers (3) */
+  int32_t ref_heads;      /* cfg.ref_xattn_heads (2) */
+} sopro_refprep_config_t;
+
+typedef struct sopro_refprep_kv_layer {
+  const float* nkv_w;     /* ref_xattn.blocks.{i}.nkv.weight [D] */
+  const float* k_w;       /* ...k_proj.weight [D, D] */
+  const float* v_w;       /* ...v_proj.weight [D, D] */
+} sopro_refprep_kv_layer_t;
+
+typedef struct sopro_refprep_weights {
+  const float* sv_emb;          /* token2sv.emb.weight [Q*V, d] */
+  const float* sv_cb_weights;   /* token2sv.cb_weights [Q] (softmax taken by the engine) */
+  const float *sv_dw0_w, *sv_dw0_b; /* token2sv.enc.0.dw [d, 1, k], [d] */
+  const float *sv_dw1_w, *sv_dw1_b; /* token2sv.enc.3.dw */
+  const float *pool_w0, *pool_b0;   /* token2sv.pool.attn.0 [d, d], [d] */
+  const float* pool_w2;             /* token2sv.pool.attn.2.weight [1, d] */
+  float pool_b2;                    /* token2sv.pool.attn.2.bias */
+  const float *proj_w, *proj_b;     /* token2sv.proj [sv, 2d], [sv] */
+  const float* cb_embed;            /* cb_embed.emb.weight [>= Q*V, D] (the first Q*V rows are read) */
+  const float* ref_cb_weights;      /* ref_cb_weights [Q] */
+  sopro_ssm_block_weights_t ref_block[SOPRO_MAX_SSM_LAYERS]; /* ref_enc_blocks.{i} */
+  const float* ref_norm_w;          /* ref_enc_norm.weight */
+  sopro_refprep_kv_layer_t layer[SOPRO_PREFILL_MAX_REF_LAYERS];
+} sopro_refprep_weights_t;
+
+typedef struct sopro_refprep sopro_refprep_t;
+int sopro_refprep_create(const sopro_refprep_config_t* cfg, const sopro_refprep_weights_t* host_weights, int device,
+                         sopro_refprep_t** out);
+int sopro_refprep_destroy(sopro_refprep_t* p);
+/* DEVICE pointers: tokens [Tr, Q] i32 -> sv [sv_dim], ref_seq [Tr, D]; ref_k / ref_v: HOST arrays of ref_layers device
+ * pointers, each [H, Tr, D/H] (PreparedReference.ref_kv_caches[i]["k"/"v"], model.py:45-50). */
+int sopro_refprep_run(sopro_refprep_t* p, const int32_t* tokens, int Tr, float* sv, float* ref_seq, float* const* ref_k,
+                      float* const* ref_v, void* stream);
+/* synchronises `stream`; SOPRO_ERR_INVALID if a run since the last check met a code outside [0, codebook_size) (the
+ * reference's embedding lookup raises IndexError); clears the flag */
+int sopro_refprep_check(sopro_refprep_t* p, void* stream);
+
 /* test hook: one tensor-core implicit GEMM (no reference counterpart).  X bf16 [B][rows][cin] (device),
  * W bf16 [N][taps*cin] (device); out[b][m][n] = epi(sum_j sum_ci X[b][m + j*dil - pad][ci] * W[n][j*cin+ci] +
  * bias[n % bias_mod]); epi: 0 none, 1 GELU(erf), 2 R + scale*acc, 3 R + acc; out_f32 / out_bf16 may be null;

@@ -122,6 +122,22 @@ class PrefillWeights(C.Structure):
                 ("ref_layer", PrefillRefLayer * 8), ("cond_norm_w", C.POINTER(C.c_float))]
 
 
+class RefPrepConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("d_model", "sv_embed_dim", "sv_dim", "n_codebooks", "codebook_size", "sv_kernel",
+                                         "ref_enc_layers", "ref_enc_kernel", "ref_layers", "ref_heads")]
+
+
+class RefPrepKvLayer(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_float)) for n in ("nkv_w", "k_w", "v_w")]
+
+
+class RefPrepWeights(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_float)) for n in ("sv_emb", "sv_cb_weights", "sv_dw0_w", "sv_dw0_b", "sv_dw1_w", "sv_dw1_b",
+                                                    "pool_w0", "pool_b0", "pool_w2")] + [("pool_b2", C.c_float)] + [
+        (n, C.POINTER(C.c_float)) for n in ("proj_w", "proj_b", "cb_embed", "ref_cb_weights")] + [
+        ("ref_block", SsmBlockWeights * 16), ("ref_norm_w", C.POINTER(C.c_float)), ("layer", RefPrepKvLayer * 8)]
+
+
 # every symbol include/sopro_b200.h declares: name -> (restype, argtypes)
 _VP, _I, _I32P = C.c_void_p, C.c_int, C.POINTER(C.c_int32)
 SYMBOLS = {
@@ -179,6 +195,10 @@ SYMBOLS = {
     "sopro_nar_refine": (_I, [_VP, _VP, C.c_int64, _VP, _VP, _I, _I, _VP, _VP]),
     "sopro_prefill_create": (_I, [_VP, _VP, _I, C.POINTER(_VP)]),
     "sopro_prefill_destroy": (_I, [_VP]),
+    "sopro_refprep_create": (_I, [C.POINTER(RefPrepConfig), C.POINTER(RefPrepWeights), _I, C.POINTER(_VP)]),
+    "sopro_refprep_destroy": (_I, [_VP]),
+    "sopro_refprep_run": (_I, [_VP, _VP, _I, _VP, _VP, _VP, _VP, _VP]),
+    "sopro_refprep_check": (_I, [_VP, _VP]),
     "sopro_prefill_run": (_I, [_VP, _VP, _VP, _I, _I, _VP, _I, _VP, _VP, _I, C.c_float, _I, _VP, _VP, _VP, _VP]),
     "sopro_debug_tc_gemm": (_I, [_VP, _I, C.c_int64, _I, _I, _I, _I, _VP, _I, _VP, _I, _I, _VP, _VP, _VP, _VP, _I, _VP]),
 }

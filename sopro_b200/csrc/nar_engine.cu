@@ -1079,3 +1079,314 @@ int sopro_prefill_run(sopro_prefill_t* p, const int32_t* text_ids, const int32_t
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// Reference preparation: SoproTTSModel.prepare_reference (reference model.py:152-170), once per voice, from the voice's
+// codes [Tr][Q]:
+//   Token2SV (nn/speaker.py:12-61): softmax(cb_weights)-weighted sum of per-codebook embeddings -> 2 x (depthwise conv k7,
+//       non-causal, GELU) -> AttentiveStatsPool (nn/blocks.py:165-188: softmax_t(w2 . tanh(W0 h + b0) + b2), weighted mean
+//       and std) -> Linear -> L2 normalise                                               -> sv_ref [sv_dim]
+//   _encode_reference_seq (model.py:136-150): softmax(ref_cb_weights)-weighted sum of cb_embed rows -> SSMLiteBlocks
+//       (non-causal) -> RMSNorm                                                           -> ref_seq [Tr][D]
+//   RefXAttnStack.build_kv_caches (nn/ref.py): per layer K = Wk RMSNorm_kv(ref_seq), V = Wv RMSNorm_kv(ref_seq), stored
+//       [H][Tr][D/H]                                                                      -> the prefill engine's ref_k / ref_v
+// fp32 (everything here feeds cond_ar, an input of the id-exact AR kernel).
+// =================================================================================================
+namespace pstage {
+
+// out[t][c] = sum_q w[q] * emb[(q*V + tok[t][q]) * dim + c], q ascending (the reference's loop order); a code outside
+// [0, V) is clamped and flagged
+__global__ void __launch_bounds__(128) codes_mix_kernel(const int* __restrict__ tok, const float* __restrict__ emb,
+                                                        const float* __restrict__ w, float* __restrict__ out, int Q, int V, int dim,
+                                                        int* __restrict__ bad) {
+  const int t = blockIdx.x;
+  extern __shared__ int ids[];
+  for (int q = threadIdx.x; q < Q; q += blockDim.x) {
+    int id = tok[(size_t)t * Q + q];
+    if (id < 0 || id >= V) {
+      atomicExch(bad, 1);
+      id = min(max(id, 0), V - 1);
+    }
+    ids[q] = id;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < dim; c += blockDim.x) {
+    float acc = 0.f;
+    for (int q = 0; q < Q; ++q) acc = __fadd_rn(acc, __fmul_rn(__ldg(w + q), __ldg(emb + ((size_t)q * V + ids[q]) * dim + c)));
+    out[(size_t)t * dim + c] = acc;
+  }
+}
+
+// y[t][c] = gelu(bias[c] + sum_j x[t + j - left][c] * w[c][j])   (DepthwiseConv1d non-causal + GELU, zero padding)
+__global__ void __launch_bounds__(128) dwconv_gelu_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, float* __restrict__ y, int T, int D, int k,
+                                                          int left) {
+  const int t = blockIdx.x;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const int r = t + j - left;
+      if (r >= 0 && r < T) acc = fmaf(x[(size_t)r * D + c], __ldg(w + c * k + j), acc);
+    }
+    y[(size_t)t * D + c] = dense::gelu_erf(acc + __ldg(bias + c));
+  }
+}
+
+// AttentiveStatsPool tail: u [T][D] = W0 h + b0 (from the dense kernel); logits[t] = w2 . tanh(u[t]) + b2; a = softmax_t;
+// mu = sum_t a h; std = sqrt(max(sum_t a (h - mu)^2, 1e-6)); out = [mu | std]  (one CTA; T floats of shared memory)
+__global__ void __launch_bounds__(256) attn_stats_pool_kernel(const float* __restrict__ u, const float* __restrict__ h,
+                                                              const float* __restrict__ w2, float b2, float* __restrict__ out, int T,
+                                                              int D) {
+  extern __shared__ float a[];
+  __shared__ float red[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < T; t += 8) {
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) s = fmaf(__ldg(w2 + c), tanhf(u[(size_t)t * D + c]), s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) a[t] = s + b2;
+  }
+  __syncthreads();
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < T; t += 256) mx = fmaxf(mx, a[t]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < 8; ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int t = threadIdx.x; t < T; t += 256) {
+    const float e = expf(a[t] - mx);
+    a[t] = e;
+    sum += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.0f / sum;
+  for (int c = threadIdx.x; c < D; c += 256) {
+    float mu = 0.f;
+    for (int t = 0; t < T; ++t) mu = fmaf(h[(size_t)t * D + c], a[t] * inv, mu);
+    float var = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float d = h[(size_t)t * D + c] - mu;
+      var = fmaf(a[t] * inv, d * d, var);
+    }
+    out[c] = mu;
+    out[D + c] = sqrtf(fmaxf(var, 1e-6f));
+  }
+}
+
+// F.normalize(e, eps): e / max(||e||, eps), one warp
+__global__ void l2_normalize_kernel(const float* __restrict__ e, float* __restrict__ out, int n, float eps) {
+  const int lane = threadIdx.x;
+  float s = 0.f;
+  for (int i = lane; i < n; i += 32) s = fmaf(e[i], e[i], s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float d = fmaxf(sqrtf(s), eps);
+  for (int i = lane; i < n; i += 32) out[i] = e[i] / d;
+}
+
+// [T][H*Dh] -> [H][T][Dh]
+__global__ void heads_major_kernel(const float* __restrict__ x, float* __restrict__ y, int T, int H, int Dh) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)T * H * Dh) return;
+  const int d = (int)(i % Dh), t = (int)((i / Dh) % T), h = (int)(i / ((long long)Dh * T));
+  y[i] = x[(size_t)t * H * Dh + h * Dh + d];
+}
+
+}  // namespace pstage
+
+struct sopro_refprep {
+  int device = 0;
+  sopro_refprep_config_t cfg{};
+  float* dev = nullptr;
+  size_t sv_emb = 0, sv_w = 0, dw0_w = 0, dw0_b = 0, dw1_w = 0, dw1_b = 0, pool_w0 = 0, pool_b0 = 0, pool_w2 = 0, proj_w = 0, proj_b = 0,
+         cb_embed = 0, ref_w = 0, ref_norm_w = 0;
+  float pool_b2 = 0.f;
+  BlockOff blk[SOPRO_MAX_SSM_LAYERS]{};
+  struct Layer {
+    size_t nkv_w, k_w, v_w;
+  } layer[SOPRO_PREFILL_MAX_REF_LAYERS]{};
+  float* ws = nullptr;
+  size_t ws_bytes = 0;
+  int* bad = nullptr;
+};
+
+extern "C" {
+
+int sopro_refprep_create(const sopro_refprep_config_t* cfg, const sopro_refprep_weights_t* w, int device, sopro_refprep_t** out) {
+  if (!cfg || !w || !out) return fail(SOPRO_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev <= 0) return fail(SOPRO_ERR_UNSUPPORTED, "no CUDA device; the reference preparation has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(SOPRO_ERR_INVALID, "device %d out of range", device);
+  cudaDeviceProp prop;
+  PCK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(SOPRO_ERR_UNSUPPORTED, "device is sm_%d%d; this build targets sm_100a only", prop.major, prop.minor);
+  const int D = cfg->d_model, d = cfg->sv_embed_dim, SV = cfg->sv_dim, Q = cfg->n_codebooks, V = cfg->codebook_size, NL = cfg->ref_enc_layers,
+            RL = cfg->ref_layers, H = cfg->ref_heads;
+  if (D < 32 || D > 512 || D % 16 || d < 16 || d % 16 || SV < 16 || SV % 16 || Q < 1 || Q > 64 || V < 1 || NL < 0 || NL > SOPRO_MAX_SSM_LAYERS ||
+      RL < 0 || RL > SOPRO_PREFILL_MAX_REF_LAYERS || H < 1 || D % H || cfg->sv_kernel < 1 || cfg->sv_kernel > 64 || cfg->ref_enc_kernel < 1 ||
+      cfg->ref_enc_kernel > 64)
+    return fail(SOPRO_ERR_INVALID, "unsupported reference-preparation geometry");
+  if (!w->sv_emb || !w->sv_cb_weights || !w->sv_dw0_w || !w->sv_dw0_b || !w->sv_dw1_w || !w->sv_dw1_b || !w->pool_w0 || !w->pool_b0 || !w->pool_w2 ||
+      !w->proj_w || !w->proj_b || !w->cb_embed || !w->ref_cb_weights || !w->ref_norm_w)
+    return fail(SOPRO_ERR_INVALID, "reference preparation: null weight pointer");
+  for (int i = 0; i < NL; ++i)
+    if (!block_ok(w->ref_block[i])) return fail(SOPRO_ERR_INVALID, "reference encoder block %d: null weight", i);
+  for (int i = 0; i < RL; ++i)
+    if (!w->layer[i].nkv_w || !w->layer[i].k_w || !w->layer[i].v_w) return fail(SOPRO_ERR_INVALID, "ref layer %d: null weight", i);
+  PCK(cudaSetDevice(device));
+  sopro_refprep* p = new sopro_refprep();
+  p->device = device;
+  p->cfg = *cfg;
+  FArena A;
+  auto softmax = [&](const float* x) {  // F.softmax(cb_weights, dim=0), fp32
+    std::vector<float> s(Q);
+    float mx = x[0];
+    for (int q = 1; q < Q; ++q) mx = std::max(mx, x[q]);
+    float sum = 0.f;
+    for (int q = 0; q < Q; ++q) sum += (s[q] = expf(x[q] - mx));
+    for (int q = 0; q < Q; ++q) s[q] /= sum;
+    return A.add(s.data(), Q);
+  };
+  p->sv_emb = A.add(w->sv_emb, (size_t)Q * V * d);
+  p->sv_w = softmax(w->sv_cb_weights);
+  p->dw0_w = A.add(w->sv_dw0_w, (size_t)d * cfg->sv_kernel);
+  p->dw0_b = A.add(w->sv_dw0_b, d);
+  p->dw1_w = A.add(w->sv_dw1_w, (size_t)d * cfg->sv_kernel);
+  p->dw1_b = A.add(w->sv_dw1_b, d);
+  p->pool_w0 = A.add(w->pool_w0, (size_t)d * d);
+  p->pool_b0 = A.add(w->pool_b0, d);
+  p->pool_w2 = A.add(w->pool_w2, d);
+  p->pool_b2 = w->pool_b2;
+  p->proj_w = A.add(w->proj_w, (size_t)SV * 2 * d);
+  p->proj_b = A.add(w->proj_b, SV);
+  p->cb_embed = A.add(w->cb_embed, (size_t)Q * V * D);
+  p->ref_w = softmax(w->ref_cb_weights);
+  for (int i = 0; i < NL; ++i) add_block(A, w->ref_block[i], D, cfg->ref_enc_kernel, &p->blk[i]);
+  p->ref_norm_w = A.add(w->ref_norm_w, D);
+  for (int i = 0; i < RL; ++i) {
+    p->layer[i].nkv_w = A.add(w->layer[i].nkv_w, D);
+    p->layer[i].k_w = A.add(w->layer[i].k_w, (size_t)D * D);
+    p->layer[i].v_w = A.add(w->layer[i].v_w, (size_t)D * D);
+  }
+  cudaError_t err = cudaMalloc(&p->dev, A.host.size() * 4);
+  if (err == cudaSuccess) err = cudaMemcpy(p->dev, A.host.data(), A.host.size() * 4, cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMalloc(&p->bad, 256);
+  if (err == cudaSuccess) err = cudaMemset(p->bad, 0, 256);
+  if (err != cudaSuccess) {
+    if (p->dev) cudaFree(p->dev);
+    if (p->bad) cudaFree(p->bad);
+    delete p;
+    return fail(SOPRO_ERR_CUDA, "reference-preparation weight upload failed: %s", cudaGetErrorString(err));
+  }
+  *out = p;
+  return SOPRO_OK;
+}
+
+int sopro_refprep_destroy(sopro_refprep_t* p) {
+  if (!p) return SOPRO_OK;
+  cudaSetDevice(p->device);
+  cudaFree(p->dev);
+  cudaFree(p->ws);
+  cudaFree(p->bad);
+  delete p;
+  return SOPRO_OK;
+}
+
+int sopro_refprep_run(sopro_refprep_t* p, const int32_t* tokens, int Tr, float* sv, float* ref_seq, float* const* ref_k, float* const* ref_v,
+                      void* stream) {
+  if (!p || !tokens || !sv || !ref_seq) return fail(SOPRO_ERR_INVALID, "null argument");
+  const sopro_refprep_config_t& c = p->cfg;
+  if (Tr < 1 || Tr > 4096) return fail(SOPRO_ERR_INVALID, "Tr=%d outside [1, 4096]", Tr);
+  if (c.ref_layers > 0 && (!ref_k || !ref_v)) return fail(SOPRO_ERR_INVALID, "ref_k / ref_v missing");
+  for (int i = 0; i < c.ref_layers; ++i)
+    if (!ref_k[i] || !ref_v[i]) return fail(SOPRO_ERR_INVALID, "ref_k[%d] / ref_v[%d] is null", i, i);
+  PCK(cudaSetDevice(p->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = c.d_model, d = c.sv_embed_dim, SV = c.sv_dim, Q = c.n_codebooks, V = c.codebook_size, H = c.ref_heads;
+  auto al = [](size_t x) { return (x + 63) / 64 * 64; };
+  const size_t rows = (size_t)Tr;
+  const size_t need = (al(rows * D) * 3 + al(rows * 4 * D) + al(2 * (size_t)d) + al((size_t)SV)) * 4;
+  if (p->ws_bytes < need) {
+    PCK(cudaStreamSynchronize(st));
+    cudaFree(p->ws);
+    p->ws = nullptr;
+    p->ws_bytes = 0;
+    cudaError_t e = cudaMalloc(&p->ws, need);
+    if (e != cudaSuccess) return fail(SOPRO_ERR_CUDA, "reference-preparation workspace: %s", cudaGetErrorString(e));
+    p->ws_bytes = need;
+  }
+  float* x = p->ws;
+  float* h = x + al(rows * D);
+  float* q = h + al(rows * D);
+  float* hid = q + al(rows * D);
+  float* stats = hid + al(rows * 4 * D);  // [2d]
+  float* e = stats + al(2 * (size_t)d);   // [SV]
+  const float* W = p->dev;
+  int rc;
+  dense::DenseOp g{};
+  // ---- Token2SV (d <= D: the [Tr][d] buffers live in x / h / q)
+  codes_mix_kernel<<<Tr, 128, Q * sizeof(int), st>>>(tokens, W + p->sv_emb, W + p->sv_w, x, Q, V, d, p->bad);
+  PCK(cudaGetLastError());
+  const int left = (c.sv_kernel - 1) / 2;
+  dwconv_gelu_kernel<<<Tr, 128, 0, st>>>(x, W + p->dw0_w, W + p->dw0_b, h, Tr, d, c.sv_kernel, left);
+  dwconv_gelu_kernel<<<Tr, 128, 0, st>>>(h, W + p->dw1_w, W + p->dw1_b, x, Tr, d, c.sv_kernel, left);
+  PCK(cudaGetLastError());
+  g.A = x; g.W = W + p->pool_w0; g.bias = W + p->pool_b0; g.C = q; g.M = Tr; g.N = d; g.K = d; g.ldc = d; g.epi = dense::EPI_BIAS;
+  if ((rc = launch_dense(g, 1, st))) return rc;
+  attn_stats_pool_kernel<<<1, 256, (size_t)Tr * 4, st>>>(q, x, W + p->pool_w2, p->pool_b2, stats, Tr, d);
+  PCK(cudaGetLastError());
+  g = dense::DenseOp{};
+  g.A = stats; g.W = W + p->proj_w; g.bias = W + p->proj_b; g.C = e; g.M = 1; g.N = SV; g.K = 2 * d; g.ldc = SV; g.epi = dense::EPI_BIAS;
+  if ((rc = launch_dense(g, 1, st))) return rc;
+  l2_normalize_kernel<<<1, 32, 0, st>>>(e, sv, SV, 1e-6f);
+  PCK(cudaGetLastError());
+  // ---- reference encoder
+  codes_mix_kernel<<<Tr, 128, Q * sizeof(int), st>>>(tokens, W + p->cb_embed, W + p->ref_w, x, Q, V, D, p->bad);
+  PCK(cudaGetLastError());
+  for (int i = 0; i < c.ref_enc_layers; ++i)
+    if ((rc = ssm_block(W, p->blk[i], x, h, hid, nullptr, 1, Tr, D, c.ref_enc_kernel, 1, false, st))) return rc;
+  dense::rmsnorm_rows_kernel<<<(unsigned)((Tr + 7) / 8), 256, 0, st>>>(x, W + p->ref_norm_w, nullptr, nullptr, ref_seq, (long long)Tr, D);
+  PCK(cudaGetLastError());
+  // ---- cached K / V of every reference cross-attention layer, heads-major
+  const long long tot = (long long)Tr * D;
+  for (int i = 0; i < c.ref_layers; ++i) {
+    for (int kv = 0; kv < 2; ++kv) {
+      g = dense::DenseOp{};
+      g.A = ref_seq; g.W = W + (kv ? p->layer[i].v_w : p->layer[i].k_w); g.norm_w = W + p->layer[i].nkv_w; g.C = h; g.M = Tr; g.N = D; g.K = D;
+      g.ldc = D; g.epi = dense::EPI_BIAS;
+      if ((rc = launch_dense(g, 1, st))) return rc;
+      heads_major_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(h, kv ? ref_v[i] : ref_k[i], Tr, H, D / H);
+      PCK(cudaGetLastError());
+    }
+  }
+  return SOPRO_OK;
+}
+
+/* Synchronises `stream`; SOPRO_ERR_INVALID if a run since the last check met a code outside [0, codebook_size). */
+int sopro_refprep_check(sopro_refprep_t* p, void* stream) {
+  if (!p) return fail(SOPRO_ERR_INVALID, "null argument");
+  PCK(cudaSetDevice(p->device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  int bad = 0;
+  PCK(cudaMemcpyAsync(&bad, p->bad, 4, cudaMemcpyDeviceToHost, st));
+  PCK(cudaStreamSynchronize(st));
+  if (bad) {
+    PCK(cudaMemsetAsync(p->bad, 0, 4, st));
+    return fail(SOPRO_ERR_INVALID, "reference codes outside [0, %d)", p->cfg.codebook_size);
+  }
+  return SOPRO_OK;
+}
+
+}  // extern "C"

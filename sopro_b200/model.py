@@ -23,7 +23,7 @@ from .codec import MimiCodec
 from .config import TARGET_SR, SoproTTSConfig
 from .engine import ArEngine, ArSession, Sampling
 from .nar import NarEngine
-from .prefill_cuda import PrefillEngine
+from .prefill_cuda import PrefillEngine, RefPrepEngine
 from .prefill import PreparedReference
 from .weights import load_safetensors, read_safetensors_cfg
 
@@ -200,10 +200,7 @@ class SoproModel:
         self.eos_id = int(cfg.codebook_size)
         self.weight_dtype = weight_dtype
         self.engine = ArEngine(cfg, state_dict, self.device, weight_dtype)
-        # prefill / NAR weights live on the device as fp32 torch tensors
-        skip = ("ar.blocks.", "ar.head.", "ar.norm.")
-        self.sd = {k: v.detach().to(self.device, torch.float32) for k, v in state_dict.items()
-                   if not k.startswith(skip) and v.is_floating_point()}
+        # (every stage owns its device copy of the weights it needs inside its CUDA engine; no torch-side copy is kept)
         self.text_pos = P.sinusoid_table(int(cfg.max_text_len) + 8, int(cfg.d_model), self.device)
         self.frame_pos = P.sinusoid_table(int(cfg.pos_emb_max) + 8, int(cfg.d_model), self.device)
         # AR sessions are CHECKED OUT per generator / call and returned when it ends (ar_stream is a suspended
@@ -212,6 +209,7 @@ class SoproModel:
         self._sessions_busy: set = set()
         self._sessions_lock = threading.Lock()
         self.prefill = PrefillEngine(cfg, state_dict, self.device, self.text_pos, self.frame_pos)
+        self.refprep = RefPrepEngine(cfg, state_dict, self.device)
         self.nar = NarEngine(cfg, state_dict, self.device)
 
     # ---- geometry helpers (reference model.py:119-131)
@@ -249,10 +247,18 @@ class SoproModel:
         with self._sessions_lock:
             self._sessions_busy.discard(id(ses))
 
-    # ---- prefill (torch)
+    # ---- prefill
     @torch.no_grad()
     def prepare_reference(self, ref_tokens_tq: torch.Tensor, *, device=None) -> PreparedReference:
-        return P.prepare_reference(self.sd, self.cfg, ref_tokens_tq, self.device)
+        """reference model.py:152-170 on the CUDA reference-preparation engine (Token2SV, reference encoder, cached K/V)."""
+        ref_btq = ref_tokens_tq.unsqueeze(0).to(device=self.device, dtype=torch.long)
+        sv, seq, caches = self.refprep.run(ref_btq[0])
+        return PreparedReference(ref_tokens_btq=ref_btq, sv_ref=sv, ref_seq=seq, ref_kv_caches=caches)
+
+    @torch.no_grad()
+    def speaker_vector(self, ref_tokens_tq: torch.Tensor) -> torch.Tensor:
+        """Token2SV alone (SoproTTS.encode_speaker, reference model.py:458-475) -> [sv_dim]"""
+        return self.refprep.run(ref_tokens_tq.to(self.device))[0].squeeze(0)
 
     @torch.no_grad()
     def prepare_conditioning(self, text_ids_1d: torch.Tensor, ref: PreparedReference, *, max_frames: int, device=None,
@@ -559,9 +565,7 @@ class SoproTTS:
 
     @torch.inference_mode()
     def encode_speaker(self, **kw) -> torch.Tensor:
-        ref = self.encode_reference(**kw).unsqueeze(0)
-        lengths = torch.tensor([int(ref.size(1))], device=self.device, dtype=torch.long)
-        return P.token2sv(self.model.sd, self.cfg, ref, lengths).squeeze(0).detach()
+        return self.model.speaker_vector(self.encode_reference(**kw)).detach()
 
     @torch.inference_mode()
     def prepare_reference(self, *, ref_audio_path: Optional[str] = None, ref_tokens_tq: Optional[torch.Tensor] = None,

@@ -1,8 +1,10 @@
-"""Once-per-utterance / parallel-in-time stages around the hot path, as plain torch ops on the
-engine's device (SURVEY.md §8a "upstream-of-path" and §8f): text encoder, speaker vector, reference
-encoder + cross-attention, FiLM, and the NAR refiner.  They feed the CUDA kernels (cond_ar, txt_seq
-are kernel INPUTS) or consume their output (NAR), so they follow the reference's arithmetic op by op;
-they are written functionally over the flat state_dict (names = the reference's checkpoint keys).
+"""The stages around the hot path (text encoder, speaker vector, reference encoder + cross-attention, FiLM, NAR refiner)
+restated as plain torch ops over the flat state_dict, following the reference's arithmetic op by op (names = the
+reference's checkpoint keys).  Since round 2 every one of them runs in a CUDA engine of libsopro_b200.so
+(``prefill_cuda.PrefillEngine`` / ``RefPrepEngine``, ``nar.NarEngine``); what the product still takes from this module
+is the ``PreparedReference`` dataclass and ``sinusoid_table``.  The functions stay as the CPU restatement the parity
+tests check the engines against (itself checked against the unmodified reference by tests/golden/make_golden_e2e.py
+and tests/test_host_cpu.py).
 
 Reference map (paths relative to the reference's src/sopro/):
   ssm_block          nn/blocks.py:143-148 (+ DepthwiseConv1d.forward :63-74)

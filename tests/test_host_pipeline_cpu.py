@@ -107,6 +107,17 @@ class _FakePrefill:
         return txt, lens, torch.cat([p["txt_pool"] for p in preps]), torch.cat([p["cond_ar"] for p in preps])
 
 
+class _FakeRefPrep:
+    """sopro_b200.prefill_cuda.RefPrepEngine.run through the torch restatement."""
+
+    def __init__(self, m):
+        self.m = m
+
+    def run(self, ref_tokens_tq):
+        r = P.prepare_reference(self.m.sd, self.m.cfg, ref_tokens_tq, torch.device("cpu"))
+        return r.sv_ref, r.ref_seq, r.ref_kv_caches
+
+
 class _FakeNar:
     """sopro_b200.nar.NarEngine.refine through oracle/nar_oracle.py, utterance by utterance over its valid frames."""
 
@@ -177,7 +188,7 @@ def tts():
     import threading
 
     m._sessions, m._sessions_busy, m._sessions_lock = {}, set(), threading.Lock()
-    m.prefill, m.nar = _FakePrefill(m), _FakeNar(m)
+    m.prefill, m.nar, m.refprep = _FakePrefill(m), _FakeNar(m), _FakeRefPrep(m)
     t = SoproTTS(model=m, cfg=cfg, tokenizer=IdsTokenizer(1000), codec=_FakeCodec(M.synth_mimi_state_dict()), device="cpu")
     t.ref = t.prepare_reference(ref_tokens_tq=torch.randint(0, 2048, (12, 32), generator=torch.Generator().manual_seed(7)))
     return t

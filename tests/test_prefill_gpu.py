@@ -86,3 +86,79 @@ def test_public_prepare_conditioning_feeds_the_ar_kernel():
     assert prep["txt_seq"].shape == (1, 52, 384) and prep["cond_ar"].shape == (1, 41, 384) and prep["text_mask"].all()
     many = tts.model.prepare_conditioning_batch([inp["text_ids"], inp["text_ids"][:9]], ref, max_frames=40, style_strength=1.0)
     assert torch.equal(many[0]["cond_ar"], prep["cond_ar"]) and many[1]["txt_seq"].shape == (1, 9, 384)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference preparation (sopro_refprep_*: Token2SV, reference encoder, cached K / V; reference model.py:152-170)
+# ---------------------------------------------------------------------------------------------------------------
+def _refprep():
+    from sopro_b200.prefill_cuda import RefPrepEngine
+
+    if "rp" not in _S:
+        cfg, sd, _ = e2e_inputs()
+        _S["rp"] = RefPrepEngine(cfg, sd, 0)
+    return _S["rp"]
+
+
+def test_refprep_matches_reference_fixture_rows():
+    """sv_ref, ref_seq rows and cached-K rows the unmodified reference wrote (tests/golden/e2e_prefill.npz)."""
+    rp = _refprep()
+    _, _, inp = e2e_inputs()
+    g = np.load(os.path.join(GOLD, "e2e_prefill.npz"))
+    sv, seq, caches = rp.run(inp["ref_tokens_tq"])
+    assert sv.shape == (1, 192) and seq.shape == (1, 38, 384) and len(caches) == 3 and caches[0]["k"].shape == (1, 2, 38, 192)
+    np.testing.assert_allclose(sv.cpu().numpy(), g["sv_ref"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(seq[0, :4].cpu().numpy(), g["ref_seq_rows"], rtol=0, atol=2e-5)
+    assert abs(float(seq.abs().mean()) - float(g["ref_seq_absmean"])) < 1e-5
+    np.testing.assert_allclose(caches[2]["k"][0, :, :2].cpu().numpy(), g["k2_rows"], rtol=0, atol=2e-5)
+    assert abs(float(sv.norm()) - 1.0) < 1e-5 and caches[0]["key_padding_mask"] is None
+
+
+@pytest.mark.parametrize("Tr,seed", [(1, 3), (5, 4), (38, 5), (150, 6)])
+def test_refprep_equals_the_cpu_restatement(Tr, seed):
+    """Every output tensor against sopro_b200/prefill.py on the CPU, short and long voices."""
+    from sopro_b200 import prefill as P
+
+    rp = _refprep()
+    cfg, sd, _ = e2e_inputs()
+    tok = torch.randint(0, 2048, (Tr, 32), generator=torch.Generator().manual_seed(seed))
+    want = P.prepare_reference(sd, cfg, tok, torch.device("cpu"))
+    sv, seq, caches = rp.run(tok)
+    assert float((sv.cpu() - want.sv_ref).abs().max()) <= 2e-6
+    assert float((seq.cpu() - want.ref_seq).abs().max()) <= 2e-5 * max(1.0, float(want.ref_seq.abs().max()))
+    for got, ref in zip(caches, want.ref_kv_caches):
+        for n in ("k", "v"):
+            assert got[n].shape == ref[n].shape
+            assert float((got[n].cpu() - ref[n]).abs().max()) <= 2e-5 * max(1.0, float(ref[n].abs().max()))
+
+
+def test_refprep_rejects_codes_outside_the_codebook():
+    rp = _refprep()
+    tok = torch.randint(0, 2048, (7, 32), generator=torch.Generator().manual_seed(1))
+    tok[3, 5] = 2048
+    with pytest.raises(IndexError):
+        rp.run(tok)
+    rp.run(tok.clamp(max=2047))  # the flag was cleared
+    with pytest.raises(ValueError):
+        rp.run(tok[:, :31])
+
+
+def test_public_prepare_reference_runs_on_the_engine_and_feeds_the_prefill():
+    from sopro_b200 import SoproTTS
+    from sopro_b200 import prefill as P
+    from sopro_b200.tokenizer import IdsTokenizer
+    from sopro_b200.weights import synth_mimi_state_dict
+
+    cfg, sd, inp = e2e_inputs()
+    if "tts" not in _S:
+        _S["tts"] = SoproTTS.from_state_dict(cfg, sd, IdsTokenizer(1000), synth_mimi_state_dict(), device="cuda:0")
+    tts = _S["tts"]
+    ref = tts.prepare_reference(ref_tokens_tq=inp["ref_tokens_tq"])
+    want = P.prepare_reference(sd, cfg, inp["ref_tokens_tq"], torch.device("cpu"))
+    assert ref.ref_tokens_btq.shape == (1, 38, 32) and ref.ref_tokens_btq.dtype == torch.long
+    assert float((ref.sv_ref.cpu() - want.sv_ref).abs().max()) <= 2e-6
+    sv = tts.encode_speaker(ref_tokens_tq=inp["ref_tokens_tq"])
+    assert sv.shape == (192,) and float((sv.cpu() - want.sv_ref[0]).abs().max()) <= 2e-6
+    prep = tts.model.prepare_conditioning(inp["text_ids"], ref, max_frames=inp["max_frames"], style_strength=inp["style_strength"])
+    g = np.load(os.path.join(GOLD, "e2e_prefill.npz"))
+    np.testing.assert_allclose(prep["cond_ar"][0, g["cond_rows_idx"].tolist()].cpu().numpy(), g["cond_rows"], rtol=0, atol=2e-5)
