@@ -427,7 +427,7 @@ int sopro_nar_set_graphs(sopro_nar_t* n, int enabled);
  * reference voice: TextEncoder (nn/text.py:16-44) -> txt_seq, txt_pool; base = txt_pool + frame sinusoid;
  * SpeakerFiLM (nn/speaker.py:64-85); RefXAttnStack with cached K/V (nn/ref.py:57-108, 111-160); cond_norm -> cond_ar.
  * fp32 (cond_ar / txt_seq feed the id-exact AR kernel).  HOST fp32 weight pointers, state_dict layouts.
- * prepare_reference (once per voice: Token2SV, reference encoder, K/V projections) stays with the caller.
+ * prepare_reference (once per voice: Token2SV, reference encoder, K/V projections) is sopro_refprep_* below.
  * ------------------------------------------------------------------------------------------------ */
 #define SOPRO_PREFILL_MAX_REF_LAYERS 8
 
