@@ -345,6 +345,23 @@ def extras(tts, ref, cfg, dev, peaks):
     t, wav = timed(lambda: tts.synthesize(text, ref=ref, max_frames=FRAMES, seed=1, min_gen_frames=10 ** 9), 3, warm=1)
     out["rtf_batch1"] = t / (wav.shape[-1] / 24000.0)
     out["synthesize_batch1_ms"] = t * 1e3
+    # reference-voice ingestion (once per voice): Mimi ENCODE of a 10 s recording, then prepare_reference
+    try:
+        from sopro_b200.codec import MimiEncoderEngine
+        from sopro_b200.weights import synth_mimi_encoder_state_dict, synth_mimi_state_dict
+
+        esd = dict(synth_mimi_state_dict())
+        esd.update(synth_mimi_encoder_state_dict())
+        enc = MimiEncoderEngine(esd, dev, 32)
+        voice = ((torch.rand(24000 * 10, generator=torch.Generator().manual_seed(9)) - 0.5) * 0.6).to(dev)
+        t, vcodes = timed(lambda: enc.encode(voice), 3, warm=1)
+        out["voice_encode_ms_10s"] = t * 1e3
+        t, _ = timed(lambda: tts.model.prepare_reference(vcodes.permute(1, 0).contiguous()), 5, warm=2)
+        out["prepare_reference_ms"] = t * 1e3
+        enc.close()
+        del enc, esd
+    except Exception as e:  # a side measurement must never cost the bench line
+        out["voice_encode_error"] = repr(e)
     # Mimi standalone: 25 x 400 = 10k frames
     codes = torch.randint(0, 2048, (25, 32, 400), generator=torch.Generator().manual_seed(5)).to(dev)
     t, _ = timed(lambda: tts.codec.engine.decode(codes), 3, warm=1)
