@@ -205,3 +205,48 @@ def test_native_noise_tape_is_bit_equal_to_torch_and_skips_the_unread_draws():
     first, second = a.rows_keep(13, 50), a.rows_keep(40, 50)
     ref = torch.empty(40, 2049).exponential_(1.0, generator=torch.Generator().manual_seed(77))[:, :50]
     assert torch.equal(torch.cat([first, second]), ref)
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """sopro_b200/_lib.py restates every struct of include/sopro_b200.h in ctypes: sizes and the offset of every field
+    must equal what the C compiler lays out (a drifted field silently shifts every pointer behind it)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+
+    from sopro_b200 import _lib
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    pairs = {
+        "sopro_ar_config_t": _lib.ArConfig, "sopro_ar_layer_weights_t": _lib.ArLayerWeights, "sopro_ar_weights_t": _lib.ArWeights,
+        "sopro_ar_sampling_t": _lib.ArSampling, "sopro_mimi_config_t": _lib.MimiConfigC,
+        "sopro_mimi_layer_weights_t": _lib.MimiLayerWeights, "sopro_mimi_stage_weights_t": _lib.MimiStageWeights,
+        "sopro_mimi_weights_t": _lib.MimiWeights, "sopro_mimi_enc_stage_weights_t": _lib.MimiEncStageWeights,
+        "sopro_mimi_encoder_weights_t": _lib.MimiEncoderWeights, "sopro_ssm_block_weights_t": _lib.SsmBlockWeights,
+        "sopro_nar_config_t": _lib.NarConfig, "sopro_nar_weights_t": _lib.NarWeights, "sopro_prefill_config_t": _lib.PrefillConfig,
+        "sopro_prefill_ref_layer_t": _lib.PrefillRefLayer, "sopro_prefill_weights_t": _lib.PrefillWeights,
+        "sopro_refprep_config_t": _lib.RefPrepConfig, "sopro_refprep_kv_layer_t": _lib.RefPrepKvLayer,
+        "sopro_refprep_weights_t": _lib.RefPrepWeights,
+    }
+    hdr = open(os.path.join(ROOT, "include", "sopro_b200.h")).read()
+    import re
+
+    declared = set(re.findall(r"^\} (sopro_[a-z0-9_]+_t);", hdr, flags=re.M))
+    assert declared == set(pairs), (declared ^ set(pairs))
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sopro_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src, exe = tmp_path / "layout.c", tmp_path / "layout"
+    src.write_text("\n".join(lines))
+    r = subprocess.run([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr  # also fails when a ctypes field name does not exist in the C struct
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == C.sizeof(cls), (cname, got[cname], C.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
