@@ -250,3 +250,25 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
         assert int(got[cname]) == C.sizeof(cls), (cname, got[cname], C.sizeof(cls))
         for fname, _ in cls._fields_:
             assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_encode_file_host_preparation_matches_the_reference_fixture():
+    """tests/golden/audio_prep.json: what the reference's trim_silence_energy + center_crop_audio keep of seeded signals
+    (reference audio.py:30-87, 148-155; written by tests/golden/make_audio_golden.py)."""
+    import json
+
+    from sopro_b200.audio import center_crop_audio, trim_silence_energy
+    from tests.golden.make_audio_golden import CASES, signal
+
+    with open(os.path.join(ROOT, "tests", "golden", "audio_prep.json")) as f:
+        g = json.load(f)
+    for i, (name, sr, n, lo, hi, floor) in enumerate(CASES):
+        w = signal(sr, n, lo, hi, floor, i)
+        t = trim_silence_energy(w, sr)
+        c = center_crop_audio(t, 12 * 1920)
+        want = g[name]
+        assert int(t.shape[-1]) == want["trim_len"] and int(c.shape[-1]) == want["crop_len"], name
+        assert float(t[0, 0]) == want["trim_first"] and float(t[0, -1]) == want["trim_last"], name
+        assert abs(float(t.double().sum()) - want["trim_sum"]) < 1e-9 and abs(float(c.double().sum()) - want["crop_sum"]) < 1e-9, name
+        assert float(c[0, 0]) == want["crop_first"], name
+    assert g["margins_24k"]["trim_len"] < 72000 and g["short_burst_24k"]["trim_len"] == 48000
